@@ -1,0 +1,372 @@
+"""CPU ORACLE - TEST INFRASTRUCTURE ONLY.
+
+A plain-numpy restatement (closed forms + analytic gradients, no autograd, no torch ops) of the
+reference's training hot path.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+`--impl reference` legs may import this file; the product path (ultra_pytorch_b200/) never does and
+fails loudly when its CUDA library is missing.
+
+Parity status: PINNED against outputs of the reference itself - tests/test_oracle_vs_golden.py checks
+every function below against tests/golden/*.npz, which tests/golden/make_goldens.py produced by running
+the unmodified reference (oracle/_ref) through BaseAlgorithm.train()/validation().  The reference's own
+tests hold no golden vectors for this path.
+
+Each function cites the reference file:line it restates (paths relative to the reference root).
+`dt` is the arithmetic dtype: np.float32 mirrors the reference's fp32 path, np.float64 gives a
+high-precision yardstick.
+"""
+import numpy as np
+
+LN_EPS = 1e-5          # nn.LayerNorm default, ultra/ranking_model/DNN.py:46-47
+ADAGRAD_EPS = 1e-10    # torch.optim.Adagrad default, ultra/learning_algorithm/ipw_rank.py:96
+CLIP_EPS = 1e-6        # torch.nn.utils.clip_grad_norm_, ultra/learning_algorithm/base_algorithm.py:224
+
+
+# ----------------------------------------------------------------------------------------------
+# parameters
+# ----------------------------------------------------------------------------------------------
+def param_names(n_layers):
+    """state_dict order of ultra/ranking_model/DNN.py:43-55 (layer_norm{j} then linear{j})."""
+    names = []
+    for j in range(n_layers):
+        names += ["sequential.layer_norm%d.weight" % j, "sequential.layer_norm%d.bias" % j,
+                  "sequential.linear%d.weight" % j, "sequential.linear%d.bias" % j]
+    return names
+
+
+def layer_sizes(feature_size, hidden):
+    """(K_j, N_j) per linear layer; the last layer maps to 1 (DNN.py:36)."""
+    outs = list(hidden) + [1]
+    ks = [feature_size] + list(hidden)
+    return list(zip(ks, outs))
+
+
+# ----------------------------------------------------------------------------------------------
+# A2: host gather  (ultra/learning_algorithm/base_algorithm.py:134-154)
+# ----------------------------------------------------------------------------------------------
+def gather_rows(features, docids_lb, dt=np.float32):
+    """features [n_docs,F] (f64 in the feed), docids_lb int [L,B] with n_docs == PAD.
+    Returns x [L*B, F] in position-major row order (row = l*B + b), cast like DNN.py:72-73."""
+    F = features.shape[1]
+    padded = np.concatenate([np.asarray(features), np.zeros((1, F))], axis=0)
+    L, B = docids_lb.shape
+    return padded[docids_lb.reshape(-1)].astype(dt)
+
+
+# ----------------------------------------------------------------------------------------------
+# A3: DNN forward / backward  (ultra/ranking_model/DNN.py:43-55,77)
+# ----------------------------------------------------------------------------------------------
+def elu(z):
+    return np.where(z > 0, z, np.expm1(np.minimum(z, 0)))
+
+
+def dnn_forward(x, params, n_layers, dt=np.float32):
+    """x [M,K0].  params: dict name -> ndarray.  Returns (scores [M], cache)."""
+    cache = []
+    h = x.astype(dt)
+    for j in range(n_layers):
+        g = params["sequential.layer_norm%d.weight" % j].astype(dt)
+        b = params["sequential.layer_norm%d.bias" % j].astype(dt)
+        W = params["sequential.linear%d.weight" % j].astype(dt)
+        c = params["sequential.linear%d.bias" % j].astype(dt)
+        mean = h.mean(axis=1, keepdims=True, dtype=dt)
+        var = ((h - mean) ** 2).mean(axis=1, keepdims=True, dtype=dt)
+        rstd = (1.0 / np.sqrt(var + dt(LN_EPS))).astype(dt)
+        xhat = ((h - mean) * rstd).astype(dt)
+        a = (xhat * g + b).astype(dt)
+        z = (a @ W.T + c).astype(dt)
+        last = j == n_layers - 1
+        y = z if last else elu(z).astype(dt)
+        cache.append((xhat, rstd, a, z, y))
+        h = y
+    return h[:, 0], cache
+
+
+def dnn_backward(dscores, cache, params, n_layers, dt=np.float32):
+    """dscores [M] -> dict name -> grad (autograd of DNN.py:77 restated)."""
+    grads = {}
+    dy = dscores.astype(dt)[:, None]
+    for j in reversed(range(n_layers)):
+        xhat, rstd, a, z, y = cache[j]
+        g = params["sequential.layer_norm%d.weight" % j].astype(dt)
+        W = params["sequential.linear%d.weight" % j].astype(dt)
+        last = j == n_layers - 1
+        dz = dy if last else (dy * np.where(z > 0, dt(1.0), y + dt(1.0))).astype(dt)
+        grads["sequential.linear%d.weight" % j] = (dz.T @ a).astype(dt)
+        grads["sequential.linear%d.bias" % j] = dz.sum(axis=0).astype(dt)
+        da = (dz @ W).astype(dt)
+        grads["sequential.layer_norm%d.weight" % j] = (da * xhat).sum(axis=0).astype(dt)
+        grads["sequential.layer_norm%d.bias" % j] = da.sum(axis=0).astype(dt)
+        dxhat = (da * g).astype(dt)
+        m1 = dxhat.mean(axis=1, keepdims=True, dtype=dt)
+        m2 = (dxhat * xhat).mean(axis=1, keepdims=True, dtype=dt)
+        dy = (rstd * (dxhat - m1 - xhat * m2)).astype(dt)
+    return grads
+
+
+def ranking_scores(features, docids_lb, params, n_layers, dt=np.float32):
+    """BaseAlgorithm.ranking_model (base_algorithm.py:118-132): returns scores [B,L] and the cache."""
+    L, B = docids_lb.shape
+    x = gather_rows(features, docids_lb, dt)
+    s, cache = dnn_forward(x, params, n_layers, dt)
+    return s.reshape(L, B).T.copy(), cache
+
+
+def scores_grad_to_rows(dscores_bl):
+    """[B,L] gradient -> position-major row vector [L*B] (inverse of the reshape above)."""
+    return np.ascontiguousarray(dscores_bl.T).reshape(-1)
+
+
+# ----------------------------------------------------------------------------------------------
+# A4: listwise softmax loss  (base_algorithm.py:18-30, 309-330)
+# ----------------------------------------------------------------------------------------------
+def log_softmax(s, dt):
+    m = s.max(axis=1, keepdims=True)
+    e = np.exp(s - m)
+    return (s - m - np.log(e.sum(axis=1, keepdims=True, dtype=dt))).astype(dt)
+
+
+def softmax_loss(scores, labels, pw=None, dt=np.float32):
+    """Returns (loss, dloss/dscores [B,L], num = sum_b l_b, den = sum w).
+    loss = sum_b [ -sum_l (w/W_b) log_softmax(s)_l * W_b ] / sum w;  pads are NOT masked."""
+    s = scores.astype(dt)
+    y = labels.astype(dt)
+    pw = np.ones_like(y) if pw is None else pw.astype(dt)
+    w = ((y + dt(1e-7)) * pw).astype(dt)
+    Wb = w.sum(axis=1, keepdims=True, dtype=dt)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        d = np.nan_to_num(w / Wb).astype(dt)
+    lsm = log_softmax(s, dt)
+    per_list = (-(d * lsm).sum(axis=1, dtype=dt) * Wb[:, 0]).astype(dt)
+    den = w.sum(dtype=dt)
+    num = per_list.sum(dtype=dt)
+    loss = num / den
+    sm = np.exp(lsm)
+    dsum = d.sum(axis=1, keepdims=True, dtype=dt)       # 1 unless the list is empty (then 0)
+    grad = ((sm * dsum - d) * Wb / den).astype(dt)
+    return dt(loss), grad, dt(num), dt(den)
+
+
+# ----------------------------------------------------------------------------------------------
+# A5: IPW weights  (ipw_rank.py:116-128, utils/propensity_estimator.py:22-42)
+# ----------------------------------------------------------------------------------------------
+def ipw_weights(clicks, table, dt=np.float32):
+    B, L = clicks.shape
+    idx = np.minimum(np.arange(L), len(table) - 1)
+    t = np.asarray(table, dtype=np.float64)[idx].astype(dt)     # torch.as_tensor(list of python floats) -> f32
+    return np.where(clicks > 0, t[None, :], dt(0.0)).astype(dt)
+
+
+# ----------------------------------------------------------------------------------------------
+# A8-A10: DLA  (dla.py:24-48, 179-266, 287-306)
+# ----------------------------------------------------------------------------------------------
+def dla_losses(scores, clicks, prop_w, prop_b, ranker_loss_weight=1.0, dt=np.float32):
+    """prop_w [L] (= DenoisingNet.linear_layer.weight[0]), prop_b scalar.
+    Returns dict(loss, rank_loss, exam_loss, dscores [B,L], dprop_w [L], dprop_b)."""
+    s = scores.astype(dt)
+    B, L = s.shape
+    pre = (prop_w.astype(dt) + dt(prop_b)).astype(dt)          # Linear(onehot_l) = W[0,l] + b   (dla.py:32-46)
+    prop = elu(pre).astype(dt)                                   # [L], identical for every list
+    prop_bl = np.broadcast_to(prop[None, :], (B, L)).astype(dt)
+    sm_p = np.exp(log_softmax(prop_bl, dt))
+    pw = (sm_p[:, :1] / sm_p).astype(dt)                         # get_normalized_weights (dla.py:287-301)
+    rank_loss, dscores, _, _ = softmax_loss(s, clicks, pw, dt)
+    sm_s = np.exp(log_softmax(s, dt))
+    rw = (sm_s[:, :1] / sm_s).astype(dt)
+    exam_loss, dprop_bl, _, _ = softmax_loss(prop_bl, clicks, rw, dt)
+    dprop = dprop_bl.sum(axis=0, dtype=dt)
+    dpre = (dprop * np.where(pre > 0, dt(1.0), prop + dt(1.0))).astype(dt)
+    return dict(loss=dt(exam_loss + dt(ranker_loss_weight) * rank_loss), rank_loss=rank_loss, exam_loss=exam_loss,
+                dscores=(dt(ranker_loss_weight) * dscores).astype(dt), dprop_w=dpre, dprop_b=dpre.sum(dtype=dt))
+
+
+# ----------------------------------------------------------------------------------------------
+# A11: PairDebias  (pairwise_debias.py:106-174, base_algorithm.py:228-248)
+# ----------------------------------------------------------------------------------------------
+def softplus(x):
+    return np.maximum(x, 0) + np.log1p(np.exp(-np.abs(x)))
+
+
+def sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def pairdebias(scores, clicks, t_plus, t_minus, em_step=0.05, reg_p=1.0, dt=np.float32):
+    """i, j are DISPLAY positions.  Includes the reference's x batch_size factor ([B]*[B,1] -> [B,B]
+    broadcast at base_algorithm.py:246-247).  Returns dict(loss, dscores, t_plus, t_minus, T_plus, T_minus)."""
+    s = scores.astype(dt)
+    c = clicks.astype(dt)
+    B, L = s.shape
+    tp = t_plus.reshape(-1).astype(dt)
+    tm = t_minus.reshape(-1).astype(dt)
+    mask = np.minimum(dt(1.0), np.maximum(c[:, :, None] - c[:, None, :], dt(0.0)))      # [B,i,j]
+    diff = (s[:, None, :] - s[:, :, None]).astype(dt)                                    # s_j - s_i
+    pl = softplus(diff).astype(dt)
+    P = (dt(B) * (mask * pl).sum(axis=0, dtype=dt)).astype(dt)                           # [i,j]
+    np.fill_diagonal(P, 0.0)
+    loss = (P / tp[:, None] / tm[None, :]).sum(dtype=dt)
+    T_plus = (P / tm[None, :]).sum(axis=1, dtype=dt)
+    T_minus = (P / tp[:, None]).sum(axis=0, dtype=dt)
+    sg = sigmoid(diff).astype(dt)                                                         # sigma(s_j - s_i)
+    coef = (dt(B) * mask * sg / (tp[None, :, None] * tm[None, None, :])).astype(dt)
+    offdiag = dt(1.0) - np.eye(L, dtype=dt)
+    coef = coef * offdiag[None]
+    dscores = (-coef.sum(axis=2, dtype=dt) + coef.sum(axis=1, dtype=dt)).astype(dt)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        new_tp = ((1 - em_step) * tp + em_step * np.power(T_plus / T_plus[0], 1.0 / (reg_p + 1))).astype(dt)
+        new_tm = ((1 - em_step) * tm + em_step * np.power(T_minus / T_minus[0], 1.0 / (reg_p + 1))).astype(dt)
+    return dict(loss=dt(loss), dscores=dscores, t_plus=new_tp, t_minus=new_tm, T_plus=T_plus, T_minus=T_minus)
+
+
+# ----------------------------------------------------------------------------------------------
+# A12: LambdaRank  (lambda_rank.py:96-140, 247-291; utils/metrics.py:156-170)
+# ----------------------------------------------------------------------------------------------
+def safe_div(n, d):
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(d == 0, np.zeros_like(n), n / d)
+
+
+def lambdarank(scores, labels, t_plus, t_minus, sigma=1.0, em_step=0.05, reg_p=1.0, dt=np.float32):
+    """i, j are PREDICTED-RANK positions (stable descending sort).  Reproduces BCE-with-logits applied to the
+    probability p_ij and the batch-global natural-log IDCG.  Returns dict like pairdebias + idcg."""
+    s = scores.astype(dt)
+    y = labels.astype(dt)
+    B, L = s.shape
+    tp = t_plus.reshape(-1).astype(dt)
+    tm = t_minus.reshape(-1).astype(dt)
+    order = np.argsort(-s, axis=1, kind="stable")
+    ps = np.take_along_axis(s, order, axis=1)
+    ys = np.take_along_axis(y, order, axis=1)
+    S = np.clip(ys[:, :, None] - ys[:, None, :], -1.0, 1.0).astype(dt)
+    Pbar = (dt(0.5) * (dt(1.0) + S)).astype(dt)
+    sij = (ps[:, :, None] - ps[:, None, :]).astype(dt)
+    with np.errstate(over="ignore"):
+        p = (dt(1.0) / (np.exp(-dt(sigma) * sij) + dt(1.0))).astype(dt)
+    ideal = -np.sort(-y, axis=1)
+    pos = np.arange(1, L + 1, dtype=dt)
+    idcg = ((np.power(dt(2.0), ideal) - dt(1.0)) / np.log(pos + dt(1.0))[None, :]).sum(dtype=dt)   # ONE scalar
+    gains = ((np.power(dt(2.0), ys) - dt(1.0)) / idcg).astype(dt)
+    disc = (dt(1.0) / np.log2(np.arange(L, dtype=dt) + dt(2.0))).astype(dt)
+    delta = (np.abs(gains[:, :, None] - gains[:, None, :]) * np.abs(disc[None, :, None] - disc[None, None, :])).astype(dt)
+    term = (delta * (np.maximum(p, 0) - p * Pbar + np.log1p(np.exp(-np.abs(p))))).astype(dt)
+    pair = term.sum(axis=0, dtype=dt)                                                       # [i,j]
+    T_plus = (pair / tm[None, :]).sum(axis=1, dtype=dt)
+    T_minus = (pair.T / tp[None, :]).sum(axis=1, dtype=dt)
+    loss = safe_div(pair, tp[:, None] * tm[None, :]).sum(dtype=dt)
+    # gradient wrt the sorted scores, then scattered back through the permutation
+    inv = safe_div(np.ones((L, L), dtype=dt), tp[:, None] * tm[None, :])
+    dterm_dp = (delta * (sigmoid(p) - Pbar)).astype(dt)
+    dp_ds = (dt(sigma) * p * (dt(1.0) - p)).astype(dt)
+    A = (dterm_dp * dp_ds * inv[None]).astype(dt)                                           # d/d(ps_i - ps_j)
+    dps = (A.sum(axis=2, dtype=dt) - A.sum(axis=1, dtype=dt)).astype(dt)
+    dscores = np.zeros_like(s)
+    np.put_along_axis(dscores, order, dps, axis=1)
+    new_tp = ((1 - em_step) * tp + em_step * np.power(safe_div(T_plus, T_plus[0]), 1.0 / (reg_p + 1))).astype(dt)
+    new_tm = ((1 - em_step) * tm + em_step * np.power(safe_div(T_minus, T_minus[0]), 1.0 / (reg_p + 1))).astype(dt)
+    return dict(loss=dt(loss), dscores=dscores, t_plus=new_tp, t_minus=new_tm, T_plus=T_plus, T_minus=T_minus,
+                idcg=dt(idcg))
+
+
+# ----------------------------------------------------------------------------------------------
+# A7: clip_grad_norm_ + Adagrad / SGD  (base_algorithm.py:208-226, dla.py:141-166)
+# ----------------------------------------------------------------------------------------------
+def clip_grad_norm(grads, names, max_norm, dt=np.float32):
+    """Returns (total_norm, clipped grads).  torch: coef = max_norm/(norm+1e-6) clamped to 1, always applied."""
+    total = np.sqrt(sum((np.linalg.norm(grads[n].astype(dt).reshape(-1)) ** 2 for n in names))).astype(dt)
+    coef = min(float(max_norm) / (float(total) + CLIP_EPS), 1.0)
+    return total, {n: (grads[n].astype(dt) * dt(coef)).astype(dt) for n in names}
+
+
+def adagrad_step(params, grads, state_sum, names, lr, dt=np.float32):
+    """In place.  torch.optim.Adagrad with lr_decay=0, weight_decay=0, initial_accumulator_value=0."""
+    for n in names:
+        g = grads[n].astype(dt)
+        state_sum[n] = (state_sum[n] + g * g).astype(dt)
+        params[n] = (params[n] - dt(lr) * g / (np.sqrt(state_sum[n]) + dt(ADAGRAD_EPS))).astype(dt)
+
+
+def sgd_step(params, grads, names, lr, dt=np.float32):
+    for n in names:
+        params[n] = (params[n] - dt(lr) * grads[n].astype(dt)).astype(dt)
+
+
+# ----------------------------------------------------------------------------------------------
+# whole train steps (what BaseAlgorithm.train does, per algorithm)
+# ----------------------------------------------------------------------------------------------
+class OracleTrainer:
+    """Replays `train(input_feed)` of NA / IPW / DLA / PairDebias / LambdaRank on the CPU.
+
+    State mirrors the reference objects: params (ranker state_dict), Adagrad accumulators (persistent for
+    NA/IPW/PairDebias/LambdaRank, re-created every step for DLA, dla.py:153-154), t_plus/t_minus, the
+    DenoisingNet parameters."""
+
+    def __init__(self, algo, params, feature_size, hidden, L_train, ipw_table=None, prop_params=None,
+                 learning_rate=None, max_gradient_norm=5.0, sigma=1.0, em_step=0.05, reg_p=1.0, dt=np.float32):
+        self.algo = algo
+        self.dt = dt
+        self.hidden = list(hidden)
+        self.n_layers = len(hidden) + 1
+        self.names = param_names(self.n_layers)
+        self.params = {n: np.array(params[n], dtype=dt) for n in self.names}
+        self.state_sum = {n: np.zeros_like(self.params[n]) for n in self.names}
+        self.F = feature_size
+        self.L = L_train
+        defaults = {"na": 0.05, "ipw": 0.05, "dla": 0.05, "pairdebias": 0.005, "lambdarank": 0.05}
+        self.lr = defaults[algo] if learning_rate is None else learning_rate
+        self.max_norm = max_gradient_norm
+        self.sigma, self.em_step, self.reg_p = sigma, em_step, reg_p
+        self.ipw_table = ipw_table
+        if algo == "dla":
+            self.prop_w = np.array(prop_params["linear_layer.weight"], dtype=dt).reshape(-1)
+            self.prop_b = dt(np.array(prop_params["linear_layer.bias"]).reshape(-1)[0])
+        if algo in ("pairdebias", "lambdarank"):
+            self.t_plus = np.ones(L_train, dtype=dt)
+            self.t_minus = np.ones(L_train, dtype=dt)
+        self.last = {}
+
+    def scores(self, features, docids_bl):
+        L = docids_bl.shape[1]
+        s, cache = ranking_scores(features, np.ascontiguousarray(docids_bl.T), self.params, self.n_layers, self.dt)
+        return s, cache
+
+    def train(self, features, docids_bl, labels_bl):
+        """docids_bl / labels_bl are [B, L_feed]; only the first L_train positions are used."""
+        dt = self.dt
+        d = docids_bl[:, :self.L]
+        y = labels_bl[:, :self.L].astype(dt)
+        s, cache = self.scores(features, d)
+        extra = {}
+        if self.algo == "na":
+            loss, ds, _, _ = softmax_loss(s, y, None, dt)
+        elif self.algo == "ipw":
+            pw = ipw_weights(y, self.ipw_table, dt)
+            loss, ds, _, _ = softmax_loss(s, y, pw, dt)
+        elif self.algo == "dla":
+            r = dla_losses(s, y, self.prop_w, self.prop_b, 1.0, dt)
+            loss, ds = r["loss"], r["dscores"]
+            extra = r
+        elif self.algo == "pairdebias":
+            r = pairdebias(s, y, self.t_plus, self.t_minus, self.em_step, self.reg_p, dt)
+            loss, ds = r["loss"], r["dscores"]
+            self.t_plus, self.t_minus = r["t_plus"], r["t_minus"]
+        elif self.algo == "lambdarank":
+            r = lambdarank(s, y, self.t_plus, self.t_minus, self.sigma, self.em_step, self.reg_p, dt)
+            loss, ds = r["loss"], r["dscores"]
+            self.t_plus, self.t_minus = r["t_plus"], r["t_minus"]
+        else:
+            raise ValueError(self.algo)
+        grads = dnn_backward(scores_grad_to_rows(ds), cache, self.params, self.n_layers, dt)
+        self.last = dict(scores=s, dscores=ds, grads=grads, loss=loss)
+        norm, clipped = clip_grad_norm(grads, self.names, self.max_norm, dt)
+        if self.algo == "dla":
+            pg = {"w": extra["dprop_w"], "b": np.asarray(extra["dprop_b"])}
+            _, pc = clip_grad_norm(pg, ["w", "b"], self.max_norm, dt)
+            self.last["grad_prop_w"], self.last["grad_prop_b"] = pg["w"], pg["b"]
+            # fresh Adagrad every step (dla.py:153-154): accumulators start from zero
+            fresh = {n: np.zeros_like(self.params[n]) for n in self.names}
+            adagrad_step(self.params, clipped, fresh, self.names, self.lr, dt)
+            pp = {"w": self.prop_w, "b": np.asarray(self.prop_b, dtype=dt)}
+            adagrad_step(pp, pc, {"w": np.zeros_like(self.prop_w), "b": np.zeros((), dtype=dt)}, ["w", "b"], self.lr, dt)
+            self.prop_w, self.prop_b = pp["w"], dt(pp["b"])
+        else:
+            adagrad_step(self.params, clipped, self.state_sum, self.names, self.lr, dt)
+        return float(loss)
