@@ -1,0 +1,136 @@
+/*
+ * ultra_b200.h - C ABI of the B200-native (sm_100a) training hot path for ULTRA (unbiased learning to rank).
+ *
+ * This header is the drop-in boundary.  Every entry point replaces a chain of ATen ops + autograd in the
+ * reference (ULTR-Community/ULTRA_pytorch; paths below are relative to the reference root).  The reference has
+ * no FFI of its own (it is pure Python on torch ops), so the "binding a maintainer would add" is a ctypes stub;
+ * see INTEGRATION.md and ultra_pytorch_b200/_capi.py.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host; no torch types anywhere;
+ *   - every launcher takes the cudaStream_t (as void*) to launch on, never synchronises, never allocates:
+ *     scratch comes from the caller's `workspace` (size from the matching *_workspace_bytes call; the caller
+ *     must zero it ONCE after allocation - the kernels keep their ticket counters at zero between calls);
+ *   - return value 0 = ok; otherwise an error code, message via ub200_last_error();
+ *   - all floating point is IEEE fp32 ("f32"); reductions are deterministic (fixed order, no float atomics);
+ *   - scores / labels / dscores are row-major [B, L] (one ranked list per row); the DNN processes M = L*B
+ *     rows in the reference's position-major order (row = l*B + b, ultra/ranking_model/DNN.py:72,
+ *     ultra/learning_algorithm/base_algorithm.py:132).
+ *
+ * Flat parameter layout (`params`, `grads`, optimizer state): for j = 0..n_hidden (n_hidden+1 linear layers,
+ * the last one maps to 1 output), in the reference's state_dict order (DNN.py:43-55):
+ *     layer_norm{j}.weight [K_j] | layer_norm{j}.bias [K_j] | linear{j}.weight [N_j, K_j] | linear{j}.bias [N_j]
+ * with K_0 = F, K_j = hidden[j-1], N_j = hidden[j] (N_last = 1).
+ */
+#ifndef ULTRA_B200_H_
+#define ULTRA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UB200_MAX_LAYERS 8
+
+#if defined(__GNUC__)
+#define UB200_API __attribute__((visibility("default")))
+#else
+#define UB200_API
+#endif
+
+/* ---- misc ------------------------------------------------------------------------------------------- */
+UB200_API const char* ub200_last_error(void);
+UB200_API int ub200_abi_version(void);
+/* number of kernel launches issued through this library since it was loaded (bench.py's gpu_launches) */
+UB200_API unsigned long long ub200_launch_count(void);
+/* number of parameters of the DNN ranker for (F, hidden[]) in the flat layout above */
+UB200_API size_t ub200_mlp_param_count(int F, const int* hidden, int n_hidden);
+
+/* ---- K1: DNN ranker forward / backward ----------------------------------------------------------------
+ * Replaces: host gather base_algorithm.py:148-152, cat + f64->f32 cast DNN.py:72-73, the nn.Sequential of
+ * [LayerNorm -> Linear -> ELU] x n_hidden + LayerNorm -> Linear(1) DNN.py:43-55,77, split/cat DNN.py:87-88 +
+ * base_algorithm.py:132, and loss.backward() through all of it base_algorithm.py:222.
+ *
+ *   feats   [n_feat_rows, F] f32, row n_docs (the last one the caller uses) is the all-zero PAD row
+ *   docid   [L*B] int32, position-major (docid[l*B+b]) row index into feats; NULL = identity (row r reads feats[r])
+ *   scores  [B, L] f32 out (scores[b*L+l])
+ *   training != 0 keeps the activations + LayerNorm statistics in `workspace` for ub200_mlp_backward
+ */
+UB200_API size_t ub200_mlp_workspace_bytes(int L, int B, int F, const int* hidden, int n_hidden, int training);
+UB200_API int ub200_mlp_forward(const float* feats, const int32_t* docid, int L, int B, int F,
+                      const int* hidden, int n_hidden, const float* params,
+                      float* scores, void* workspace, size_t workspace_bytes, int training, void* stream);
+/* dscores [B, L]; grads (flat layout) is overwritten.  Must follow ub200_mlp_forward(training=1) on the same
+ * workspace, inputs and parameters. */
+UB200_API int ub200_mlp_backward(const float* feats, const int32_t* docid, int L, int B, int F,
+                       const int* hidden, int n_hidden, const float* params, const float* dscores,
+                       float* grads, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K2: listwise softmax cross-entropy, forward + gradient ----------------------------------------------
+ * Replaces BaseAlgorithm.softmax_loss base_algorithm.py:309-330 (+ :18-30) and its autograd, and the pure-Python
+ * IPW weight loop ipw_rank.py:116-128 -> propensity_estimator.py:22-42.
+ *   weight_mode 0: pw = 1 (NavieAlgorithm, navie_algorithm.py:105-106)
+ *   weight_mode 1: pw_bl = table[min(l, table_len-1)] if labels_bl > 0 else 0 (IPWrank)
+ * Outputs are UN-NORMALISED so that data-parallel ranks can sum them before dividing:
+ *   dscores[b,l] = softmax(s_b)_l * W_b * sum_l(d_bl) - w_bl        (true gradient = dscores / sums[1])
+ *   sums[0] = sum_b l_b,  sums[1] = sum_bl w_bl                      (loss = sums[0] / sums[1])
+ */
+UB200_API size_t ub200_loss_workspace_bytes(int B, int L);
+UB200_API int ub200_softmax_ce(const float* scores, const float* labels, int B, int L, int weight_mode,
+                     const float* table, int table_len, float* dscores, float* sums,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* DLA: both softmax losses of dla.py:196-224 in one pass, plus the DenoisingNet (dla.py:24-48) forward/backward
+ * and get_normalized_weights (dla.py:287-301).
+ *   prop_w [L] = DenoisingNet.linear_layer.weight[0,:], prop_b [1] = its bias
+ *   dscores  [B,L]  un-normalised d(rank_loss)/d(scores)                 (divide by sums[1])
+ *   dprop    [L+1]  un-normalised d(exam_loss)/d(prop_w[0..L-1], prop_b) (divide by sums[3])
+ *   sums[4] = { rank num, rank den, exam num, exam den }; loss = sums[2]/sums[3] + ranker_loss_weight*sums[0]/sums[1]
+ */
+UB200_API int ub200_dla_loss(const float* scores, const float* clicks, int B, int L, const float* prop_w, const float* prop_b,
+                   float* dscores, float* dprop, float* sums, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K3: pairwise losses -----------------------------------------------------------------------------------
+ * LambdaRank (lambda_rank.py:116-135, dcg :247-266, compute_delta_ndcg :268-291): i, j = predicted-rank positions
+ * (stable descending sort), BCE-with-logits applied to p_ij, batch-global natural-log IDCG.
+ *   out[0..L)   = T+_i = sum_j pair_ij / t-_j          out[L..2L) = T-_j = sum_i pair_ij / t+_i
+ *   out[2L]     = loss,   out[2L+1] = idcg             ALL computed with idcg = 1:
+ *   true loss = out[2L]/idcg, true gradient = dscores/idcg (T+/T- only enter the EM update as ratios).
+ * PairDebias (pairwise_debias.py:142-157, base_algorithm.py:228-248): i, j = display positions; outputs are
+ * WITHOUT the reference's x batch_size factor (the host multiplies by the global batch size): out has 2L+1 floats.
+ */
+UB200_API size_t ub200_pair_workspace_bytes(int B, int L);
+UB200_API int ub200_lambdarank(const float* scores, const float* labels, int B, int L, float sigma,
+                     const float* t_plus, const float* t_minus, float* dscores, float* out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+UB200_API int ub200_pairdebias(const float* scores, const float* clicks, int B, int L,
+                     const float* t_plus, const float* t_minus, float* dscores, float* out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* t <- (1-em_step)*t + em_step * (T_i / T_0)^(1/(reg_p+1)) for t+ (T = out[0..L)) and t- (T = out[L..2L));
+ * safe_div != 0 uses the reference's _safe_div (LambdaRank, lambda_rank.py:136-140), 0 a plain division
+ * (PairDebias, pairwise_debias.py:159-163). */
+UB200_API int ub200_em_update(float* t_plus, float* t_minus, const float* out, int L, float em_step, float reg_p,
+                    int safe_div, void* stream);
+
+/* ---- optimizer: clip_grad_norm_ + Adagrad / SGD on a flat buffer ---------------------------------------------
+ * Replaces BaseAlgorithm.opt_step base_algorithm.py:208-226 (clip_grad_norm_ + torch.optim.Adagrad/SGD.step) and
+ * DLA.separate_gradient_update dla.py:141-166.
+ *   g = grads * scale_const / (*den)            (den may be NULL = 1; this is where the loss normaliser is applied)
+ *   norm = ||g||_2 ; coef = min(max_norm / (norm + 1e-6), 1) if max_norm > 0 else 1 ; g *= coef
+ *   mode 0: Adagrad with persistent `state_sum`      (lr_decay 0, eps 1e-10, initial accumulator 0)
+ *   mode 1: Adagrad re-created every step (DLA quirk, dla.py:153-154): the accumulator starts from 0 each call
+ *   mode 2: SGD (grad_strategy == 'sgd')
+ * grads is overwritten with the clipped gradient (what p.grad holds after the reference's opt_step);
+ * norm_out[0] receives the pre-clip norm.
+ */
+UB200_API size_t ub200_opt_workspace_bytes(size_t n);
+UB200_API int ub200_clip_update(float* params, float* grads, float* state_sum, size_t n, const float* den, float scale_const,
+                      float max_norm, float lr, int mode, float* norm_out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ULTRA_B200_H_ */

@@ -1,0 +1,111 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol the header declares, host-side helpers
+(hparams parser, metrics restatement vs the reference's goldens) behave like the reference's."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import golden_names, load_golden, sub
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "ultra_b200.h")).read()
+    return sorted(set(re.findall(r"UB200_API[^;(]*?\b(ub200_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ultra_pytorch_b200 import build
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    syms = _header_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), "missing export %s" % s
+    lib.ub200_abi_version.restype = ctypes.c_int
+    assert lib.ub200_abi_version() == 1
+
+
+def test_ctypes_table_matches_header():
+    from ultra_pytorch_b200 import _capi
+    assert sorted(_capi.SIGNATURES.keys()) == _header_symbols()
+    # argument counts agree with the header declarations
+    text = open(os.path.join(ROOT, "include", "ultra_b200.h")).read()
+    for name, (_, args) in _capi.SIGNATURES.items():
+        m = re.search(r"\b%s\s*\(([^;]*?)\)\s*;" % name, text, re.S)
+        decl = m.group(1).strip()
+        n = 0 if decl in ("void", "") else len(decl.split(","))
+        assert n == len(args), (name, n, len(args))
+
+
+def test_param_count_and_workspace_sizes_without_gpu():
+    from ultra_pytorch_b200 import _capi
+    hid = _capi.int_array([256, 128, 64])
+    assert _capi.lib.ub200_mlp_param_count(136, hid, 3) == 77457          # SURVEY.md section 8 (config 2)
+    hid2 = _capi.int_array([512, 256, 128])
+    assert _capi.lib.ub200_mlp_param_count(136, hid2, 3) == 236561
+    assert _capi.lib.ub200_mlp_param_count(700, hid2, 3) == 526457
+    assert _capi.lib.ub200_mlp_workspace_bytes(40, 256, 136, hid, 3, 1) > 0
+    assert _capi.lib.ub200_mlp_param_count(0, hid, 3) == 0               # bad spec -> 0, no crash
+
+
+def test_product_fails_loudly_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from ultra_pytorch_b200._capi import UltraB200Error
+    from ultra_pytorch_b200.engine import RankerEngine
+    with pytest.raises(UltraB200Error):
+        RankerEngine(8, [4])
+
+
+def test_hparams_parser():
+    from ultra_pytorch_b200.hparams import HParams
+    h = HParams(hidden_layer_sizes=[512, 256, 128], activation_func='elu', learning_rate=0.05, flag=False,
+                regulation_p=1)
+    h.parse("hidden_layer_sizes=[256, 128,64],learning_rate=0.1,unknown=3,flag=True,regulation_p=2")
+    assert h.hidden_layer_sizes == [256, 128, 64] and h.learning_rate == 0.1 and h.flag is True
+    assert h.regulation_p == 2 and not hasattr(h, "unknown")
+    h.parse("")
+    h.parse("activation_func=relu")
+    assert h.activation_func == "relu" and h.hidden_layer_sizes == [256, 128, 64]
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_metrics_restatement_matches_reference_values(name):
+    """validation() metrics computed from the REFERENCE's own scores must reproduce the reference's values
+    bit for bit (same torch ops in the same order on the CPU)."""
+    from ultra_pytorch_b200 import metrics as m
+    m.MAX_LABEL = 4.0
+    g = load_golden(name)
+    scores = torch.from_numpy(g["valid/scores"])
+    # the reference hands the metrics a transposed view of the [L, B] label stack (base_algorithm.py:181-182)
+    labels = torch.from_numpy(np.transpose(np.ascontiguousarray(g["valid/labels"].astype(np.float32).T)))
+    n_docs = g["valid/features"].shape[0]
+    pad = torch.from_numpy(g["valid/docids"]) == n_docs
+    scores = torch.where(pad, torch.ones_like(scores) * -100000, scores)
+    for metric in ("ndcg", "err", "mrr"):
+        vals = m.make_ranking_metric_fn(metric, [1, 3, 5, 10])(labels, scores, None)
+        for n, v in zip([1, 3, 5, 10], vals):
+            assert v.item() == float(g["valid/metric/%s_%d" % (metric, n)]), (metric, n)
+
+
+def test_metrics_match_reference_module_when_available():
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("oracle/_ref not installed")
+    if torch.cuda.is_available():
+        pytest.skip("the reference's metrics module pins its tensors to cuda when a GPU is visible")
+    ultra = ref_shim.load()
+    from ultra_pytorch_b200 import metrics as m
+    ultra.utils.metrics.RankingMetricKey.MAX_LABEL = 4.0
+    rs = np.random.RandomState(0)
+    scores = torch.from_numpy(rs.randn(17, 12).astype(np.float32))
+    labels = torch.from_numpy(rs.randint(0, 5, size=(17, 12)).astype(np.float32))
+    for metric in ("ndcg", "err", "mrr", "arp", "precision", "map"):
+        ours = m.make_ranking_metric_fn(metric, [1, 3, 5, 10])(labels, scores, None)
+        ref = ultra.utils.make_ranking_metric_fn(metric, [1, 3, 5, 10])(labels, scores, None)
+        assert torch.equal(torch.as_tensor(ours), torch.as_tensor(ref)), metric

@@ -1,0 +1,345 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI / the plugin classes, against
+(a) the committed golden vectors produced by the unmodified reference and (b) the CPU oracle on seeded inputs.
+
+Tolerance (tests/helpers.py): |a - ref| <= 1e-5 * max(|ref|, mean|ref|) for scores and losses' gradients w.r.t.
+the scores; parameter gradients accumulate over M = L*B rows and are held to 5e-5 on the same scale (the fp32
+reference itself differs from an fp64 evaluation by ~3e-6 on scores).
+"""
+import json
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ultra_oracle as uo
+from tests.helpers import assert_close, golden_names, grad_floor, load_golden, scaled_err, sub
+
+pytestmark = pytest.mark.gpu
+
+ALGO_CLASS = {"na": "NavieAlgorithm", "ipw": "IPWrank", "dla": "DLA", "pairdebias": "PairDebias",
+              "lambdarank": "LambdaRank"}
+
+
+def _dev(x, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype, device="cuda")
+
+
+def make_feed(model, features, docids_bl, labels_bl):
+    feed = {model.letor_features_name: np.asarray(features, dtype=np.float64)}
+    for l in range(docids_bl.shape[1]):
+        feed[model.docid_inputs_name[l]] = docids_bl[:, l].astype(np.float32)
+        feed[model.labels_name[l]] = labels_bl[:, l].astype(np.float32)
+    return feed
+
+
+def build_from_golden(g, tmp_path):
+    import ultra_pytorch_b200.learning_algorithm as la
+    from ultra_pytorch_b200 import metrics as b200_metrics
+    b200_metrics.MAX_LABEL = 4.0
+    algo = str(g["meta_algo"])
+    hp = ""
+    if algo == "ipw":
+        p = os.path.join(str(tmp_path), "ipw.json")
+        with open(p, "w") as f:
+            json.dump({"IPW_list": [float(v) for v in g["ipw_table"]]}, f)
+        hp = "propensity_estimator_json=%s" % p
+    exp_settings = {
+        "learning_algorithm_hparams": hp,
+        "ranking_model": "ultra_pytorch_b200.ranking_model.DNN",
+        "ranking_model_hparams": "hidden_layer_sizes=%s" % str([int(h) for h in g["meta_hidden"]]),
+        "selection_bias_cutoff": int(g["meta_L_train"]),
+        "max_candidate_num": int(g["meta_L_max"]),
+        "metrics": ["ndcg", "err", "mrr"],
+        "metrics_topn": [1, 3, 5, 10],
+    }
+    ds = types.SimpleNamespace(feature_size=int(g["meta_F"]))
+    model = getattr(la, ALGO_CLASS[algo])(ds, exp_settings)
+    model.model.load_state_dict({k: torch.from_numpy(v) for k, v in sub(g, "init/").items()})
+    if algo == "dla":
+        model.propensity_model.load_state_dict({k: torch.from_numpy(v) for k, v in sub(g, "init_prop/").items()},
+                                               strict=False)
+    return model, algo
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_validation_matches_reference(name, tmp_path):
+    g = load_golden(name)
+    model, algo = build_from_golden(g, tmp_path)
+    feed = make_feed(model, g["valid/features"], g["valid/docids"], g["valid/labels"])
+    _, scores, summary = model.validation(feed)
+    assert isinstance(scores, torch.Tensor) and scores.is_cuda
+    assert_close(scores.cpu().numpy(), g["valid/scores"], 1e-5, name + " validation scores")
+    for k, v in sub(g, "valid/metric/").items():
+        assert abs(summary[k] - float(v)) <= 1e-6 * max(1.0, abs(float(v))), (k, summary[k], float(v))
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_train_steps_match_reference(name, tmp_path):
+    g = load_golden(name)
+    model, algo = build_from_golden(g, tmp_path)
+    named = dict(model.model.named_parameters())
+    for step in range(int(g["meta_n_steps"])):
+        pre = "step%d/" % step
+        feed = make_feed(model, g[pre + "features"], g[pre + "docids"], g[pre + "labels"])
+        loss, _, _ = model.train(feed)
+        ref_loss = float(g[pre + "loss"])
+        assert abs(loss - ref_loss) <= 2e-5 * abs(ref_loss), (name, step, loss, ref_loss)
+        gref = sub(g, pre + "grad/")
+        floor = grad_floor(gref)
+        total = np.sqrt(sum(float((v.astype(np.float64) ** 2).sum()) for v in gref.values()))
+        coef = min(1.0, 5.0 / (total + 1e-6))          # the plugin leaves the CLIPPED gradient in .grad
+        for n, ref in gref.items():
+            got = named[n].grad.detach().cpu().numpy()
+            assert_close(got, ref * coef, 5e-5, "%s step %d grad %s" % (name, step, n), floor * coef)
+        for n, ref in sub(g, pre + "param/").items():
+            ok = np.abs(gref[n]) > 1e-3 * floor         # see tests/test_oracle_vs_golden.py on zero gradients
+            got = named[n].detach().cpu().numpy()
+            assert_close(got[ok], ref[ok], 1e-4, "%s step %d param %s" % (name, step, n))
+        if algo in ("pairdebias", "lambdarank"):
+            assert_close(model.t_plus.cpu().numpy(), g[pre + "t_plus"], 2e-5, "t_plus")
+            assert_close(model.t_minus.cpu().numpy(), g[pre + "t_minus"], 2e-5, "t_minus")
+        if algo == "dla":
+            pg = sub(g, pre + "grad_prop/")
+            ptotal = np.sqrt(sum(float((v.astype(np.float64) ** 2).sum()) for v in pg.values()))
+            pcoef = min(1.0, 5.0 / (ptotal + 1e-6))
+            pfloor = 0.1 * float(np.abs(pg["linear_layer.weight"]).max())
+            lw = model.propensity_model.linear_layer
+            assert_close(lw.weight.grad.cpu().numpy(), pg["linear_layer.weight"] * pcoef, 5e-5, "dprop_w")
+            assert_close(lw.bias.grad.cpu().numpy(), pg["linear_layer.bias"] * pcoef, 5e-5, "dprop_b", pfloor * pcoef)
+        # restart every step from the reference's parameters: Adagrad's sign-like first steps amplify rounding
+        # noise on mathematically-zero gradients (identically in the reference)
+        model.model.load_state_dict({k: torch.from_numpy(v) for k, v in sub(g, pre + "param/").items()})
+        if algo == "dla":
+            model.propensity_model.load_state_dict(
+                {k: torch.from_numpy(v) for k, v in sub(g, pre + "param_prop/").items()}, strict=False)
+        if algo in ("pairdebias", "lambdarank"):
+            model.t_plus.copy_(torch.from_numpy(g[pre + "t_plus"]))
+            model.t_minus.copy_(torch.from_numpy(g[pre + "t_minus"]))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# kernel-level parity against the CPU oracle on seeded inputs (sizes the oracle finishes in seconds)
+# ---------------------------------------------------------------------------------------------------------
+def _random_params(rs, F, hidden):
+    params = {}
+    for j, (k, n) in enumerate(uo.layer_sizes(F, hidden)):
+        params["sequential.layer_norm%d.weight" % j] = (1.0 + 0.2 * rs.randn(k)).astype(np.float32)
+        params["sequential.layer_norm%d.bias" % j] = (0.2 * rs.randn(k)).astype(np.float32)
+        params["sequential.linear%d.weight" % j] = (rs.uniform(-1, 1, size=(n, k)) / np.sqrt(k)).astype(np.float32)
+        params["sequential.linear%d.bias" % j] = (rs.uniform(-1, 1, size=n) / np.sqrt(k)).astype(np.float32)
+    return params
+
+
+MLP_CASES = [
+    # F, hidden, L, B
+    (13, [7, 5], 3, 5),
+    (136, [256, 128, 64], 40, 64),
+    (700, [512, 256, 128], 20, 24),
+    (220, [512, 256, 128], 10, 33),
+    (46, [], 9, 17),
+    (136, [64], 1, 300),
+]
+
+
+@pytest.mark.parametrize("F,hidden,L,B", MLP_CASES)
+def test_mlp_forward_backward_vs_oracle(F, hidden, L, B):
+    from ultra_pytorch_b200.engine import RankerEngine
+    rs = np.random.RandomState(F + L + B)
+    n_docs = L * B - 3 if L * B > 3 else L * B
+    feats = rs.uniform(-1, 1, size=(n_docs, F)).astype(np.float32)
+    docids = rs.randint(0, n_docs + 1, size=(L, B))          # includes the PAD id n_docs
+    params = _random_params(rs, F, hidden)
+    n_layers = len(hidden) + 1
+    dsc = rs.randn(B, L).astype(np.float32)
+
+    s64, cache = uo.ranking_scores(feats, docids, params, n_layers, np.float64)
+    g64 = uo.dnn_backward(uo.scores_grad_to_rows(dsc), cache, params, n_layers, np.float64)
+
+    eng = RankerEngine(F, hidden)
+    flat = np.concatenate([params[n].reshape(-1) for n in uo.param_names(n_layers)])
+    eng.params.copy_(_dev(flat))
+    feats_dev = _dev(np.concatenate([feats, np.zeros((1, F), np.float32)]))
+    docid_dev = _dev(docids.reshape(-1), torch.int32)
+    scores = eng.forward(feats_dev, docid_dev, L, B, training=True).clone()
+    assert_close(scores.cpu().numpy(), s64, 1e-5, "scores")
+    # inference workspace path gives the same scores
+    scores_inf = eng.forward(feats_dev, docid_dev, L, B, training=False).clone()
+    assert torch.equal(scores, scores_inf)
+    eng.forward(feats_dev, docid_dev, L, B, training=True)
+    grads = eng.backward(feats_dev, docid_dev, L, B, _dev(dsc)).cpu().numpy()
+    floor = grad_floor(g64)
+    off = 0
+    for n in uo.param_names(n_layers):
+        ref = g64[n]
+        got = grads[off:off + ref.size].reshape(ref.shape)
+        off += ref.size
+        assert_close(got, ref, 5e-5, "grad " + n, floor)
+    # run-to-run determinism (fixed-order reductions)
+    eng.forward(feats_dev, docid_dev, L, B, training=True)
+    grads2 = eng.backward(feats_dev, docid_dev, L, B, _dev(dsc)).cpu().numpy()
+    assert np.array_equal(grads, grads2)
+
+
+@pytest.mark.parametrize("B,L", [(1, 1), (7, 5), (300, 40), (64, 200), (33, 45)])
+@pytest.mark.parametrize("mode", ["na", "ipw"])
+def test_softmax_ce_vs_oracle(B, L, mode):
+    from ultra_pytorch_b200.engine import RankerEngine
+    rs = np.random.RandomState(B * 7 + L)
+    eng = RankerEngine(4, [])
+    s = (2.0 * rs.randn(B, L)).astype(np.float32)
+    if mode == "ipw":
+        y = (rs.rand(B, L) < 0.2).astype(np.float32)
+        if B > 2:
+            y[1] = 0.0                      # a list without clicks: W_b = 0 -> nan_to_num path
+        table = np.linspace(1.0, 11.0, 40)
+        pw = uo.ipw_weights(y, table, np.float64)
+        tdev = _dev(table)
+    else:
+        y = rs.randint(0, 5, size=(B, L)).astype(np.float32)
+        pw, tdev = None, None
+    loss, grad, num, den = uo.softmax_loss(s, y, pw, np.float64)
+    dsc = torch.empty(B, L, device="cuda")
+    sums = torch.zeros(2, device="cuda")
+    eng.softmax_ce(_dev(s), _dev(y), 1 if mode == "ipw" else 0, tdev, dsc, sums)
+    sums_h = sums.cpu().numpy()
+    assert abs(sums_h[0] / sums_h[1] - loss) <= 1e-5 * abs(loss)
+    assert abs(sums_h[1] - den) <= 1e-5 * abs(den)
+    assert_close(dsc.cpu().numpy() / sums_h[1], grad, 1e-5, "dscores")
+    if mode == "ipw" and B > 2:
+        assert np.all(dsc.cpu().numpy()[1] == 0)
+
+
+@pytest.mark.parametrize("B,L", [(5, 4), (256, 20), (40, 100)])
+def test_dla_loss_vs_oracle(B, L):
+    from ultra_pytorch_b200.engine import RankerEngine
+    rs = np.random.RandomState(B + L)
+    eng = RankerEngine(4, [])
+    s = rs.randn(B, L).astype(np.float32)
+    c = (rs.rand(B, L) < 0.25).astype(np.float32)
+    c[:, 0] = np.maximum(c[:, 0], (rs.rand(B) < 0.5))
+    pw_ = (0.3 * rs.randn(L)).astype(np.float32)
+    pb_ = np.float32(0.1)
+    r = uo.dla_losses(s, c, pw_, pb_, 1.0, np.float64)
+    dsc = torch.empty(B, L, device="cuda")
+    dprop = torch.zeros(L + 1, device="cuda")
+    sums = torch.zeros(4, device="cuda")
+    eng.dla_loss(_dev(s), _dev(c), _dev(pw_), _dev(np.array([pb_])), dsc, dprop, sums)
+    h = sums.cpu().numpy()
+    assert abs(h[0] / h[1] - r["rank_loss"]) <= 1e-5 * abs(r["rank_loss"])
+    assert abs(h[2] / h[3] - r["exam_loss"]) <= 1e-5 * abs(r["exam_loss"])
+    assert_close(dsc.cpu().numpy() / h[1], r["dscores"], 1e-5, "dscores")
+    dp = dprop.cpu().numpy() / h[3]
+    assert_close(dp[:L], r["dprop_w"], 2e-5, "dprop_w")
+    assert abs(dp[L] - r["dprop_b"]) <= 2e-5 * max(abs(r["dprop_b"]), np.abs(r["dprop_w"]).max())
+
+
+@pytest.mark.parametrize("B,L", [(3, 2), (8, 6), (64, 40), (32, 200), (5, 300)])
+@pytest.mark.parametrize("kind", ["lambdarank", "pairdebias"])
+def test_pairwise_vs_oracle(B, L, kind):
+    from ultra_pytorch_b200.engine import RankerEngine
+    rs = np.random.RandomState(B * 3 + L)
+    eng = RankerEngine(4, [])
+    s = rs.randn(B, L).astype(np.float32)
+    tp = (1.0 + 0.3 * rs.rand(L)).astype(np.float32)
+    tm = (1.0 + 0.3 * rs.rand(L)).astype(np.float32)
+    dsc = torch.empty(B, L, device="cuda")
+    out = torch.zeros(2 * L + 2, device="cuda")
+    tpd, tmd = _dev(tp), _dev(tm)
+    if kind == "lambdarank":
+        y = rs.randint(0, 5, size=(B, L)).astype(np.float32)
+        r = uo.lambdarank(s, y, tp, tm, 1.0, 0.05, 1.0, np.float64)
+        eng.lambdarank(_dev(s), _dev(y), 1.0, tpd, tmd, dsc, out)
+        o = out.cpu().numpy()
+        idcg = o[2 * L + 1]
+        assert abs(idcg - r["idcg"]) <= 1e-5 * r["idcg"]
+        scale = 1.0 / idcg
+        eng.em_update(tpd, tmd, out, 0.05, 1.0, True)
+    else:
+        y = (rs.rand(B, L) < 0.3).astype(np.float32)
+        r = uo.pairdebias(s, y, tp, tm, 0.05, 1.0, np.float64)
+        eng.pairdebias(_dev(s), _dev(y), tpd, tmd, dsc, out)
+        o = out.cpu().numpy()
+        scale = float(B)
+        eng.em_update(tpd, tmd, out, 0.05, 1.0, False)
+    assert abs(o[2 * L] * scale - r["loss"]) <= 1e-5 * abs(r["loss"]) + 1e-12
+    assert_close(o[:L] * scale, r["T_plus"], 1e-5, "T_plus")
+    assert_close(o[L:2 * L] * scale, r["T_minus"], 1e-5, "T_minus")
+    assert_close(dsc.cpu().numpy() * scale, r["dscores"], 1e-5, "dscores")
+    if np.isfinite(r["t_plus"]).all() and np.isfinite(r["t_minus"]).all():
+        assert_close(tpd.cpu().numpy(), r["t_plus"], 1e-5, "t_plus after EM")
+        assert_close(tmd.cpu().numpy(), r["t_minus"], 1e-5, "t_minus after EM")
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_clip_update_vs_oracle(mode):
+    from ultra_pytorch_b200.engine import RankerEngine
+    rs = np.random.RandomState(mode)
+    eng = RankerEngine(4, [])
+    n = 100003
+    p = rs.randn(n).astype(np.float32)
+    g = (3.0 * rs.randn(n)).astype(np.float32)
+    st = (rs.rand(n)).astype(np.float32)
+    den = np.float32(7.5)
+    pd, gd, sd = _dev(p), _dev(g), _dev(st)
+    norm = torch.zeros(1, device="cuda")
+    eng.clip_update(pd, gd, sd, _dev(np.array([den])), 2.0, 5.0, 0.05, mode, norm)
+    gs = g.astype(np.float64) * 2.0 / den
+    nrm = np.sqrt((gs ** 2).sum())
+    gc = gs * min(1.0, 5.0 / (nrm + 1e-6))
+    assert abs(norm.item() - nrm) <= 1e-5 * nrm
+    assert_close(gd.cpu().numpy(), gc, 1e-5, "clipped grad")
+    if mode == 2:
+        ref = p - 0.05 * gc
+    else:
+        ss = gc ** 2 + (st if mode == 0 else 0.0)
+        ref = p - 0.05 * gc / (np.sqrt(ss) + 1e-10)
+        if mode == 0:
+            assert_close(sd.cpu().numpy(), ss, 1e-5, "state_sum")
+    assert_close(pd.cpu().numpy(), ref, 1e-5, "params")
+
+
+def test_lambdarank_roundtrip_properties_full_size():
+    """Size-independent properties at BASELINE config-4 size (B=256, L=200): the pairwise gradient of every list
+    sums to zero (shift invariance), T+/T- are non-negative and the kernel is run-to-run deterministic."""
+    from ultra_pytorch_b200.engine import RankerEngine
+    rs = np.random.RandomState(0)
+    B, L = 256, 200
+    eng = RankerEngine(4, [])
+    s = _dev(rs.randn(B, L))
+    y = _dev(rs.randint(0, 5, size=(B, L)))
+    tp = torch.ones(L, device="cuda")
+    tm = torch.ones(L, device="cuda")
+    outs = []
+    for _ in range(2):
+        dsc = torch.empty(B, L, device="cuda")
+        out = torch.zeros(2 * L + 2, device="cuda")
+        eng.lambdarank(s, y, 1.0, tp, tm, dsc, out)
+        outs.append((dsc.cpu().numpy(), out.cpu().numpy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    d, o = outs[0]
+    assert np.abs(d.sum(axis=1)).max() <= 1e-4 * np.abs(d).max()
+    assert (o[:2 * L] >= 0).all() and np.isfinite(o).all()
+
+
+def test_ranker_build_and_checkpoint_interchange(tmp_path):
+    """`build()` keeps the reference contract (DNN.py:58-88) and state_dict keys interchange with the reference."""
+    from ultra_pytorch_b200.ranking_model import DNN
+    g = load_golden("ipw_small")
+    F = int(g["meta_F"])
+    m = DNN("hidden_layer_sizes=%s" % [int(h) for h in g["meta_hidden"]], F)
+    assert list(m.state_dict().keys()) == list(sub(g, "init/").keys())
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sub(g, "init/").items()})
+    path = os.path.join(str(tmp_path), "x.ckpt")
+    torch.save(m.state_dict(), path)
+    back = torch.load(path)
+    for k, v in sub(g, "init/").items():
+        assert np.array_equal(back[k].cpu().numpy(), v)
+    feats = np.concatenate([g["valid/features"], np.zeros((1, F))])
+    doc = g["valid/docids"]
+    inputs = [torch.from_numpy(feats[doc[:, l]]) for l in range(doc.shape[1])]
+    outs = m.build(inputs)
+    assert len(outs) == doc.shape[1] and tuple(outs[0].shape) == (doc.shape[0], 1)
+    got = torch.cat(outs, dim=1).cpu().numpy()
+    assert_close(got, g["valid/scores"], 1e-5, "build() scores")

@@ -1,0 +1,72 @@
+"""ctypes binding of include/ultra_b200.h (the C-ABI shared library with the sm_100a kernels).
+
+There is NO fallback: if the library cannot be loaded (or built from the in-tree sources with nvcc) importing
+this module raises, and every product entry point fails loudly.
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+_c_float_p = ctypes.c_void_p   # raw device pointers (tensor.data_ptr())
+_vp = ctypes.c_void_p
+_sz = ctypes.c_size_t
+_i = ctypes.c_int
+_f = ctypes.c_float
+_ip = ctypes.POINTER(ctypes.c_int)
+
+# name -> (restype, argtypes); mirrors include/ultra_b200.h declaration by declaration
+SIGNATURES = {
+    "ub200_last_error": (ctypes.c_char_p, []),
+    "ub200_abi_version": (_i, []),
+    "ub200_launch_count": (ctypes.c_ulonglong, []),
+    "ub200_mlp_param_count": (_sz, [_i, _ip, _i]),
+    "ub200_mlp_workspace_bytes": (_sz, [_i, _i, _i, _ip, _i, _i]),
+    "ub200_mlp_forward": (_i, [_vp, _vp, _i, _i, _i, _ip, _i, _vp, _vp, _vp, _sz, _i, _vp]),
+    "ub200_mlp_backward": (_i, [_vp, _vp, _i, _i, _i, _ip, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ub200_loss_workspace_bytes": (_sz, [_i, _i]),
+    "ub200_softmax_ce": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "ub200_dla_loss": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ub200_pair_workspace_bytes": (_sz, [_i, _i]),
+    "ub200_lambdarank": (_i, [_vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ub200_pairdebias": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ub200_em_update": (_i, [_vp, _vp, _vp, _i, _f, _f, _i, _vp]),
+    "ub200_opt_workspace_bytes": (_sz, [_sz]),
+    "ub200_clip_update": (_i, [_vp, _vp, _vp, _sz, _vp, _f, _f, _f, _i, _vp, _vp, _sz, _vp]),
+}
+
+
+class UltraB200Error(RuntimeError):
+    pass
+
+
+def _load():
+    path = _build.LIBPATH
+    if not os.path.isfile(path):
+        try:
+            _build.build()
+        except Exception as e:  # noqa: BLE001
+            raise UltraB200Error(
+                "libultra_b200.so is missing and could not be built with nvcc (%s). The CUDA extension is "
+                "mandatory: there is no CPU / eager fallback. Run `python -m ultra_pytorch_b200.build`." % (e,))
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError here means the .so is stale: rebuild
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+LIB_PATH = _build.LIBPATH
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib.ub200_last_error()
+        raise UltraB200Error("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def int_array(values):
+    arr = (ctypes.c_int * max(1, len(values)))(*values)
+    return arr

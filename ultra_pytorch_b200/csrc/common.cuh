@@ -1,0 +1,98 @@
+// Shared device/host helpers for the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/ultra_b200.h"
+
+namespace ub200 {
+
+constexpr int kWarp = 32;
+constexpr float kLnEps = 1e-5f;        // nn.LayerNorm default (ultra/ranking_model/DNN.py:46-47)
+constexpr int kNumSMs = 148;           // B200
+
+void set_error(const char* fmt, ...);
+void count_launch();
+
+#define UB_CHECK(cond, code, ...)            \
+    do {                                     \
+        if (!(cond)) {                       \
+            ub200::set_error(__VA_ARGS__);   \
+            return (code);                   \
+        }                                    \
+    } while (0)
+
+#define UB_LAUNCH_CHECK(name)                                                              \
+    do {                                                                                   \
+        cudaError_t e__ = cudaGetLastError();                                              \
+        ub200::count_launch();                                                             \
+        if (e__ != cudaSuccess) {                                                          \
+            ub200::set_error("%s launch failed: %s", (name), cudaGetErrorString(e__));     \
+            return 100;                                                                    \
+        }                                                                                  \
+    } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ELU (alpha = 1): torch uses expm1 on the negative side
+__device__ __forceinline__ float elu_f(float z) { return z > 0.f ? z : expm1f(z); }
+// derivative of ELU expressed through its OUTPUT y: z>0 -> 1, else exp(z) = y + 1
+__device__ __forceinline__ float elu_grad_from_out(float y) { return y > 0.f ? 1.f : y + 1.f; }
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Deterministic "last block finishes the reduction" ticket. `counter` must be 0 on entry and is reset to 0.
+__device__ __forceinline__ bool last_block_ticket(unsigned int* counter, unsigned int nblocks) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        unsigned int t = atomicAdd(counter, 1u);
+        is_last = (t == nblocks - 1);
+        if (is_last) *counter = 0u;
+    }
+    __syncthreads();
+    if (is_last) __threadfence();
+    return is_last;
+}
+
+struct LayerDims {
+    int n_layers;                   // linear layers including the final ->1
+    int K[UB200_MAX_LAYERS];
+    int N[UB200_MAX_LAYERS];
+    size_t off_g[UB200_MAX_LAYERS], off_b[UB200_MAX_LAYERS], off_w[UB200_MAX_LAYERS], off_c[UB200_MAX_LAYERS];
+    size_t n_params;
+};
+
+inline int make_dims(int F, const int* hidden, int n_hidden, LayerDims* d) {
+    if (n_hidden < 0 || n_hidden + 1 > UB200_MAX_LAYERS || F <= 0) return 1;
+    d->n_layers = n_hidden + 1;
+    size_t off = 0;
+    int k = F;
+    for (int j = 0; j <= n_hidden; ++j) {
+        int n = (j == n_hidden) ? 1 : hidden[j];
+        if (n <= 0) return 1;
+        d->K[j] = k;
+        d->N[j] = n;
+        d->off_g[j] = off; off += k;
+        d->off_b[j] = off; off += k;
+        d->off_w[j] = off; off += (size_t)n * k;
+        d->off_c[j] = off; off += n;
+        k = n;
+    }
+    d->n_params = off;
+    return 0;
+}
+
+}  // namespace ub200

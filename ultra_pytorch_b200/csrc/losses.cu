@@ -1,0 +1,479 @@
+// K2 / K3 - ranking losses (forward value + gradient w.r.t. the scores) for sm_100a.
+//
+//  K2 softmax_ce / dla_loss : one warp per ranked list, warp-shuffle reductions, coalesced [B,L] rows.
+//  K3 lambdarank / pairdebias: one CTA per ranked list, the L x L pair tile is evaluated on the fly from
+//                              shared-memory copies of the list (scores, labels, t+/t-), never materialised.
+// All cross-list sums are deterministic: per-block partials + "last block reduces in fixed order".
+#include "common.cuh"
+
+namespace ub200 {
+
+constexpr int kLossBlocks = 2 * kNumSMs;
+
+// workspace: [counter (uint, padded to 64 floats)] [partials: kLossBlocks x width floats]
+struct LossWs {
+    unsigned int* counter;
+    float* partials;
+};
+static size_t loss_ws_bytes(int width) { return 256 + sizeof(float) * (size_t)kLossBlocks * width; }
+static LossWs loss_ws(void* ws) {
+    LossWs w;
+    w.counter = static_cast<unsigned int*>(ws);
+    w.partials = reinterpret_cast<float*>(static_cast<char*>(ws) + 256);
+    return w;
+}
+
+// deterministic reduction of partials[nblocks][width] into out[width], run by the last block
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ partials, int nblocks, int stride,
+                                                int width, float* __restrict__ out) {
+    for (int k = threadIdx.x; k < width; k += blockDim.x) {
+        float s = 0.f;
+        for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * stride + k];
+        out[k] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: softmax cross-entropy (NA / IPW) and the two DLA losses
+// ------------------------------------------------------------------------------------------------
+// Per list (base_algorithm.py:322-330): w = (y + 1e-7) * pw ; W = sum w ; d = nan_to_num(w / W) ;
+//   l = -sum_l d_l * log_softmax(s)_l * W ;  dl/ds_l = (softmax(s)_l * sum(d) - d_l) * W
+struct ListStats {
+    float lse;    // log-sum-exp of the logits
+    float W;      // sum of weighted labels
+    float dsum;   // sum of d (1, or 0 for an empty list)
+};
+
+template <int MODE>   // 0 = no weights, 1 = IPW table, 2 = DLA
+__global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict__ scores,
+                                                          const float* __restrict__ labels, int B, int L,
+                                                          const float* __restrict__ table, int table_len,
+                                                          const float* __restrict__ prop_w,
+                                                          const float* __restrict__ prop_b,
+                                                          float* __restrict__ dscores, float* __restrict__ dprop,
+                                                          float* __restrict__ sums, unsigned int* counter,
+                                                          float* __restrict__ partials) {
+    extern __shared__ float sm[];
+    // DLA shared: prop[L], sm_p[L] (softmax of prop), then per-warp accumulators acc[nw][L]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    float* prop = sm;
+    float* smp = sm + L;
+    float* acc = sm + 2 * L + (size_t)wid * L;
+    float lse_p = 0.f;
+    if (MODE == 2) {
+        const float pb = prop_b[0];
+        for (int l = threadIdx.x; l < L; l += blockDim.x) prop[l] = elu_f(prop_w[l] + pb);   // dla.py:32-46
+        for (int l = lane; l < L; l += kWarp) acc[l] = 0.f;
+        __syncthreads();
+        float m = -INFINITY;
+        for (int l = lane; l < L; l += kWarp) m = fmaxf(m, prop[l]);
+        m = warp_max(m);
+        float e = 0.f;
+        for (int l = lane; l < L; l += kWarp) e += expf(prop[l] - m);
+        e = warp_sum(e);
+        lse_p = m + logf(e);
+        if (wid == 0)
+            for (int l = lane; l < L; l += kWarp) smp[l] = expf(prop[l] - lse_p);
+        __syncthreads();
+    }
+    float num = 0.f, den = 0.f, num_e = 0.f, den_e = 0.f;
+    for (int b = blockIdx.x * nw + wid; b < B; b += gridDim.x * nw) {
+        const float* s = scores + (size_t)b * L;
+        const float* y = labels + (size_t)b * L;
+        // log-sum-exp of the scores
+        float m = -INFINITY;
+        for (int l = lane; l < L; l += kWarp) m = fmaxf(m, s[l]);
+        m = warp_max(m);
+        float e = 0.f;
+        for (int l = lane; l < L; l += kWarp) e += expf(s[l] - m);
+        e = warp_sum(e);
+        const float lse = m + logf(e);
+        // weights
+        float W = 0.f, We = 0.f;
+        float sm_s0 = 0.f, smp0 = 0.f;
+        if (MODE == 2) {
+            sm_s0 = expf(s[0] - lse);
+            smp0 = smp[0];
+        }
+        for (int l = lane; l < L; l += kWarp) {
+            float yl = y[l] + 1e-7f;
+            float pw = 1.f;
+            if (MODE == 1) pw = (y[l] > 0.f) ? table[min(l, table_len - 1)] : 0.f;
+            if (MODE == 2) {
+                pw = smp0 / smp[l];                                   // get_normalized_weights, dla.py:296-298
+                We += yl * (sm_s0 / expf(s[l] - lse));
+            }
+            W += yl * pw;
+        }
+        W = warp_sum(W);
+        if (MODE == 2) We = warp_sum(We);
+        // loss + gradient
+        float ll = 0.f, dsum = 0.f, lle = 0.f, dsum_e = 0.f;
+        for (int l = lane; l < L; l += kWarp) {
+            float yl = y[l] + 1e-7f;
+            float pw = 1.f;
+            if (MODE == 1) pw = (y[l] > 0.f) ? table[min(l, table_len - 1)] : 0.f;
+            if (MODE == 2) pw = smp0 / smp[l];
+            float w = yl * pw;
+            float d = (W != 0.f) ? w / W : 0.f;                       // nan_to_num(w / W)
+            float lsm = s[l] - lse;
+            ll = fmaf(-d, lsm, ll);
+            dsum += d;
+            if (MODE == 2) {
+                float we = yl * (sm_s0 / expf(lsm));
+                float de = (We != 0.f) ? we / We : 0.f;
+                lle = fmaf(-de, prop[l] - lse_p, lle);
+                dsum_e += de;
+            }
+        }
+        ll = warp_sum(ll);
+        dsum = warp_sum(dsum);
+        if (MODE == 2) {
+            lle = warp_sum(lle);
+            dsum_e = warp_sum(dsum_e);
+        }
+        for (int l = lane; l < L; l += kWarp) {
+            float yl = y[l] + 1e-7f;
+            float pw = 1.f;
+            if (MODE == 1) pw = (y[l] > 0.f) ? table[min(l, table_len - 1)] : 0.f;
+            if (MODE == 2) pw = smp0 / smp[l];
+            float w = yl * pw;
+            float d = (W != 0.f) ? w / W : 0.f;
+            float lsm = s[l] - lse;
+            dscores[(size_t)b * L + l] = (expf(lsm) * dsum - d) * W;
+            if (MODE == 2) {
+                float we = yl * (sm_s0 / expf(lsm));
+                float de = (We != 0.f) ? we / We : 0.f;
+                acc[l] += (smp[l] * dsum_e - de) * We;
+            }
+        }
+        num += ll * W;
+        den += W;
+        if (MODE == 2) {
+            num_e += lle * We;
+            den_e += We;
+        }
+    }
+    // block partials: [num, den, num_e, den_e, gprop[L]]
+    const int width = (MODE == 2) ? 4 + L : 2;
+    __shared__ float red[8][4];
+    if (lane == 0) {
+        red[wid][0] = num; red[wid][1] = den; red[wid][2] = num_e; red[wid][3] = den_e;
+    }
+    __syncthreads();
+    float* mine = partials + (size_t)blockIdx.x * width;
+    if (threadIdx.x < ((MODE == 2) ? 4 : 2)) {
+        float s = 0.f;
+        for (int q = 0; q < nw; ++q) s += red[q][threadIdx.x];
+        mine[threadIdx.x] = s;
+    }
+    if (MODE == 2) {
+        float* accs = sm + 2 * L;
+        for (int l = threadIdx.x; l < L; l += blockDim.x) {
+            float s = 0.f;
+            for (int q = 0; q < nw; ++q) s += accs[(size_t)q * L + l];
+            mine[4 + l] = s;
+        }
+    }
+    if (last_block_ticket(counter, gridDim.x)) {
+        if (MODE != 2) {
+            reduce_partials(partials, gridDim.x, width, 2, sums);
+        } else {
+            // sums[4], then chain the exam gradient through ELU and the Linear(L,1): dprop[l] = g_l * ELU'(pre_l),
+            // dprop[L] = sum_l dprop[l]   (dla.py:24-48)
+            __shared__ float gsum[256];
+            reduce_partials(partials, gridDim.x, width, 4, sums);
+            float local = 0.f;
+            const float pb = prop_b[0];
+            for (int l = threadIdx.x; l < L; l += blockDim.x) {
+                float g = 0.f;
+                for (int b = 0; b < (int)gridDim.x; ++b) g += partials[(size_t)b * width + 4 + l];
+                float pre = prop_w[l] + pb;
+                float gp = g * (pre > 0.f ? 1.f : expf(pre));
+                dprop[l] = gp;
+                local += gp;
+            }
+            gsum[threadIdx.x] = local;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float s = 0.f;
+                for (int q = 0; q < (int)blockDim.x; ++q) s += gsum[q];
+                dprop[L] = s;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: pairwise losses, one CTA per list
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+__device__ __forceinline__ float safe_div_f(float n, float d) { return d == 0.f ? 0.f : n / d; }
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    float s = 0.f;
+    for (int q = 0; q < nw; ++q) s += red[q];
+    return s;
+}
+
+// LAMBDA = true : LambdaRank (lambda_rank.py:116-135, 247-291) - positions are predicted ranks
+// LAMBDA = false: PairDebias (pairwise_debias.py:142-157)       - positions are display positions
+template <bool LAMBDA>
+__global__ void __launch_bounds__(256) pairwise_kernel(const float* __restrict__ scores,
+                                                        const float* __restrict__ labels, int B, int L, float sigma,
+                                                        const float* __restrict__ t_plus,
+                                                        const float* __restrict__ t_minus,
+                                                        float* __restrict__ dscores, float* __restrict__ out,
+                                                        unsigned int* counter, float* __restrict__ partials) {
+    extern __shared__ float sm[];
+    float* ps = sm;              // scores in position order (sorted for LAMBDA)
+    float* ys = ps + L;          // labels in position order
+    float* gn = ys + L;          // LAMBDA: gain 2^y - 1 ; else unused
+    float* dc = gn + L;          // LAMBDA: 1/log2(pos+2)
+    float* tp = dc + L;
+    float* tm = tp + L;
+    float* accp = tm + L;        // block accumulators of T+ / T-
+    float* accm = accp + L;
+    float* gr = accm + L;        // gradient in position order
+    float* raw_s = gr + L;       // LAMBDA: unsorted copy
+    float* raw_y = raw_s + L;
+    int* pos = reinterpret_cast<int*>(raw_y + L);   // LAMBDA: rank of original index
+    __shared__ float red[8];
+
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        tp[i] = t_plus[i];
+        tm[i] = t_minus[i];
+        accp[i] = 0.f;
+        accm[i] = 0.f;
+        if (LAMBDA) dc[i] = 1.f / log2f((float)i + 2.f);
+    }
+    float loss_acc = 0.f, idcg_acc = 0.f;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        const float* s = scores + (size_t)b * L;
+        const float* y = labels + (size_t)b * L;
+        if (LAMBDA) {
+            for (int i = threadIdx.x; i < L; i += blockDim.x) {
+                raw_s[i] = s[i];
+                raw_y[i] = y[i];
+            }
+            __syncthreads();
+            // stable descending rank by counting (torch.sort(descending=True), lambda_rank.py:116) and the ideal
+            // rank of each label for the IDCG (lambda_rank.py:126, 263-266: natural log, summed over the batch)
+            for (int i = threadIdx.x; i < L; i += blockDim.x) {
+                const float si = raw_s[i], yi = raw_y[i];
+                int r = 0, ir = 0;
+                for (int j = 0; j < L; ++j) {
+                    const float sj = raw_s[j], yj = raw_y[j];
+                    r += (sj > si) || (sj == si && j < i);
+                    ir += (yj > yi) || (yj == yi && j < i);
+                }
+                pos[i] = r;
+                ps[r] = si;
+                ys[r] = yi;
+                const float gain = exp2f(yi) - 1.f;
+                gn[r] = gain;
+                idcg_acc += gain / logf((float)ir + 2.f);
+            }
+        } else {
+            for (int i = threadIdx.x; i < L; i += blockDim.x) {
+                ps[i] = s[i];
+                ys[i] = y[i];
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < L; i += blockDim.x) {
+            const float si = ps[i], yi = ys[i], tpi = tp[i], tmi = tm[i];
+            float Tp = 0.f, Tm = 0.f, g = 0.f, ls = 0.f;
+            if (LAMBDA) {
+                const float gi = gn[i], di = dc[i];
+                for (int j = 0; j < L; ++j) {
+                    const float delta = fabsf(gi - gn[j]) * fabsf(di - dc[j]);
+                    if (delta == 0.f) continue;   // also skips j == i
+                    const float dlt = sigma * (si - ps[j]);
+                    const float pij = 1.f / (expf(-dlt) + 1.f);
+                    const float pji = 1.f / (expf(dlt) + 1.f);
+                    const float Sij = fminf(fmaxf(yi - ys[j], -1.f), 1.f);
+                    const float Pij = 0.5f * (1.f + Sij), Pji = 0.5f * (1.f - Sij);
+                    // BCEWithLogits applied to the probability p (lambda_rank.py:128)
+                    const float tij = delta * (pij - pij * Pij + log1pf(expf(-pij)));
+                    const float tji = delta * (pji - pji * Pji + log1pf(expf(-pji)));
+                    const float inv_ij = safe_div_f(1.f, tpi * tm[j]);
+                    const float inv_ji = safe_div_f(1.f, tp[j] * tmi);
+                    Tp += tij / tm[j];
+                    Tm += tji / tp[j];
+                    ls = fmaf(tij, inv_ij, ls);
+                    const float aij = delta * (sigmoid_f(pij) - Pij) * sigma * pij * (1.f - pij) * inv_ij;
+                    const float aji = delta * (sigmoid_f(pji) - Pji) * sigma * pji * (1.f - pji) * inv_ji;
+                    g += aij - aji;
+                }
+            } else {
+                for (int j = 0; j < L; ++j) {
+                    if (j == i) continue;
+                    const float cj = ys[j];
+                    const float mij = fminf(1.f, fmaxf(yi - cj, 0.f));
+                    const float mji = fminf(1.f, fmaxf(cj - yi, 0.f));
+                    if (mij == 0.f && mji == 0.f) continue;
+                    const float dlt = ps[j] - si;                 // s_j - s_i
+                    const float inv_ij = 1.f / (tpi * tm[j]);
+                    const float inv_ji = 1.f / (tp[j] * tmi);
+                    if (mij != 0.f) {
+                        const float t = mij * softplus_f(dlt);
+                        Tp += t / tm[j];
+                        ls = fmaf(t, inv_ij, ls);
+                        g -= mij * sigmoid_f(dlt) * inv_ij;
+                    }
+                    if (mji != 0.f) {
+                        const float t = mji * softplus_f(-dlt);
+                        Tm += t / tp[j];
+                        g += mji * sigmoid_f(-dlt) * inv_ji;
+                    }
+                }
+            }
+            accp[i] += Tp;
+            accm[i] += Tm;
+            gr[i] = g;
+            loss_acc += ls;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < L; i += blockDim.x)
+            dscores[(size_t)b * L + i] = LAMBDA ? gr[pos[i]] : gr[i];
+    }
+    __syncthreads();
+    const int width = 2 * L + 2;
+    float* mine = partials + (size_t)blockIdx.x * width;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        mine[i] = accp[i];
+        mine[L + i] = accm[i];
+    }
+    const float lsum = block_sum(loss_acc, red);
+    const float isum = block_sum(idcg_acc, red);
+    if (threadIdx.x == 0) {
+        mine[2 * L] = lsum;
+        mine[2 * L + 1] = isum;
+    }
+    if (last_block_ticket(counter, gridDim.x)) reduce_partials(partials, gridDim.x, width, LAMBDA ? width : width - 1, out);
+}
+
+__global__ void em_update_kernel(float* __restrict__ t_plus, float* __restrict__ t_minus,
+                                 const float* __restrict__ out, int L, float em_step, float expo, int safe) {
+    const float Tp0 = out[0], Tm0 = out[L];
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        float rp = safe ? safe_div_f(out[i], Tp0) : out[i] / Tp0;
+        float rm = safe ? safe_div_f(out[L + i], Tm0) : out[L + i] / Tm0;
+        t_plus[i] = (1.f - em_step) * t_plus[i] + em_step * powf(rp, expo);
+        t_minus[i] = (1.f - em_step) * t_minus[i] + em_step * powf(rm, expo);
+    }
+}
+
+}  // namespace ub200
+
+using namespace ub200;
+
+extern "C" UB200_API size_t ub200_loss_workspace_bytes(int B, int L) {
+    (void)B;
+    return loss_ws_bytes(4 + (L > 0 ? L : 0));
+}
+
+extern "C" UB200_API size_t ub200_pair_workspace_bytes(int B, int L) {
+    (void)B;
+    return loss_ws_bytes(2 * (L > 0 ? L : 0) + 2);
+}
+
+static int loss_grid(int B, int lists_per_block) {
+    int g = (B + lists_per_block - 1) / lists_per_block;
+    if (g > kLossBlocks) g = kLossBlocks;
+    return g < 1 ? 1 : g;
+}
+
+extern "C" UB200_API int ub200_softmax_ce(const float* scores, const float* labels, int B, int L, int weight_mode,
+                                const float* table, int table_len, float* dscores, float* sums, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+    UB_CHECK(B > 0 && L > 0, 1, "softmax_ce: bad B=%d L=%d", B, L);
+    UB_CHECK(scores && labels && dscores && sums && workspace, 2, "softmax_ce: null pointer");
+    UB_CHECK(weight_mode == 0 || (weight_mode == 1 && table && table_len > 0), 1, "softmax_ce: bad weight_mode %d",
+             weight_mode);
+    UB_CHECK(workspace_bytes >= loss_ws_bytes(2), 3, "softmax_ce: workspace too small");
+    LossWs w = loss_ws(workspace);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = loss_grid(B, 8);
+    if (weight_mode == 0)
+        softmax_ce_kernel<0><<<grid, 256, 0, st>>>(scores, labels, B, L, nullptr, 0, nullptr, nullptr, dscores, nullptr,
+                                                   sums, w.counter, w.partials);
+    else
+        softmax_ce_kernel<1><<<grid, 256, 0, st>>>(scores, labels, B, L, table, table_len, nullptr, nullptr, dscores,
+                                                   nullptr, sums, w.counter, w.partials);
+    UB_LAUNCH_CHECK("softmax_ce_kernel");
+    return 0;
+}
+
+extern "C" UB200_API int ub200_dla_loss(const float* scores, const float* clicks, int B, int L, const float* prop_w,
+                              const float* prop_b, float* dscores, float* dprop, float* sums, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    UB_CHECK(B > 0 && L > 0, 1, "dla_loss: bad B=%d L=%d", B, L);
+    UB_CHECK(scores && clicks && prop_w && prop_b && dscores && dprop && sums && workspace, 2,
+             "dla_loss: null pointer");
+    UB_CHECK(workspace_bytes >= loss_ws_bytes(4 + L), 3, "dla_loss: workspace too small");
+    LossWs w = loss_ws(workspace);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t smem = sizeof(float) * (size_t)(2 + 8) * L;
+    UB_CHECK(smem <= 200 * 1024, 4, "dla_loss: list length %d too large", L);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(softmax_ce_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int grid = loss_grid(B, 8);
+    softmax_ce_kernel<2><<<grid, 256, smem, st>>>(scores, clicks, B, L, nullptr, 0, prop_w, prop_b, dscores, dprop,
+                                                  sums, w.counter, w.partials);
+    UB_LAUNCH_CHECK("softmax_ce_kernel<dla>");
+    return 0;
+}
+
+template <bool LAMBDA>
+static int launch_pairwise(const float* scores, const float* labels, int B, int L, float sigma, const float* t_plus,
+                           const float* t_minus, float* dscores, float* out, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+    UB_CHECK(B > 0 && L > 0, 1, "pairwise: bad B=%d L=%d", B, L);
+    UB_CHECK(scores && labels && t_plus && t_minus && dscores && out && workspace, 2, "pairwise: null pointer");
+    UB_CHECK(workspace_bytes >= loss_ws_bytes(2 * L + 2), 3, "pairwise: workspace too small");
+    LossWs w = loss_ws(workspace);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t smem = sizeof(float) * 12 * (size_t)L;
+    UB_CHECK(smem <= 200 * 1024, 4, "pairwise: list length %d too large", L);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(pairwise_kernel<LAMBDA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int threads = (L + 31) / 32 * 32;
+    if (threads > 256) threads = 256;
+    const int grid = loss_grid(B, 1);
+    pairwise_kernel<LAMBDA><<<grid, threads, smem, st>>>(scores, labels, B, L, sigma, t_plus, t_minus, dscores, out,
+                                                         w.counter, w.partials);
+    UB_LAUNCH_CHECK("pairwise_kernel");
+    return 0;
+}
+
+extern "C" UB200_API int ub200_lambdarank(const float* scores, const float* labels, int B, int L, float sigma,
+                                const float* t_plus, const float* t_minus, float* dscores, float* out,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    return launch_pairwise<true>(scores, labels, B, L, sigma, t_plus, t_minus, dscores, out, workspace,
+                                 workspace_bytes, stream);
+}
+
+extern "C" UB200_API int ub200_pairdebias(const float* scores, const float* clicks, int B, int L, const float* t_plus,
+                                const float* t_minus, float* dscores, float* out, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+    return launch_pairwise<false>(scores, clicks, B, L, 1.f, t_plus, t_minus, dscores, out, workspace,
+                                  workspace_bytes, stream);
+}
+
+extern "C" UB200_API int ub200_em_update(float* t_plus, float* t_minus, const float* out, int L, float em_step, float reg_p,
+                               int safe_div, void* stream) {
+    UB_CHECK(L > 0 && t_plus && t_minus && out, 1, "em_update: bad arguments");
+    em_update_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(t_plus, t_minus, out, L, em_step,
+                                                                      1.f / (reg_p + 1.f), safe_div);
+    UB_LAUNCH_CHECK("em_update_kernel");
+    return 0;
+}

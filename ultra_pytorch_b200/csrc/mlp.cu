@@ -1,0 +1,542 @@
+// K1 - DNN ranker forward / backward for sm_100a (fp32, CUDA-core path).
+//
+// Replaces (reference paths): the host gather base_algorithm.py:148-152, cat+cast DNN.py:72-73, the
+// [LayerNorm -> Linear -> ELU] x n + LayerNorm -> Linear(1) stack DNN.py:43-55,77 and its autograd backward.
+//
+// Structure per linear layer j (K_j -> N_j), rows M = L*B in position-major order:
+//   forward : stats_j = rowwise (mean, rstd) of X_j ; Y_j = ELU( LN(X_j) W_j^T + c_j )   (LN fused into the A-operand load)
+//   final   : one warp per row: stats + dot product with the [1,K] weight, scattered to scores[B,L]
+//   backward: G_j  = dZ_j^T [xhat_j | 1]      (split over row chunks, deterministic two-stage reduction)
+//             dW_j = gamma (.) G + beta (x) db, dgamma = sum_n W (.) G, dbeta = sum_n W db   (LayerNorm affine grads
+//             derived from the weight-gradient GEMM, so no gradient w.r.t. the features is ever formed)
+//             dXhat_j = dZ_j (W_j (.) gamma) ; dZ_{j-1} = LNbwd(dXhat_j) (.) ELU'(Y_{j-1})
+#include "common.cuh"
+
+namespace ub200 {
+
+// ------------------------------------------------------------------------------------------------
+// workspace carving
+// ------------------------------------------------------------------------------------------------
+struct MlpWorkspace {
+    float2* stats[UB200_MAX_LAYERS];   // (mean, rstd) of the input of layer j, [M]
+    float* Y[UB200_MAX_LAYERS];        // output of hidden layer j (post-ELU) [M, N_j]
+    float* dz;                         // [M, maxH]
+    float* dxh;                        // [M, maxH]
+    float* partials;                   // split-M partial weight gradients
+    size_t partial_floats;
+    size_t total_bytes;
+};
+
+constexpr int kFinalBlocks = 2 * kNumSMs;   // blocks of the final-layer backward (column partial sums)
+
+static int wgrad_splits(int M, int N, int K1) {
+    int tiles = ((N + 127) / 128) * ((K1 + 127) / 128);
+    int s = (2 * kNumSMs + tiles - 1) / tiles;
+    int max_s = (M + 255) / 256;
+    if (s > max_s) s = max_s;
+    if (s < 1) s = 1;
+    return s;
+}
+
+static void carve(const LayerDims& d, int M, int training, char* base, MlpWorkspace* w) {
+    size_t off = 0;
+    int maxH = 1;
+    for (int j = 0; j + 1 < d.n_layers; ++j) maxH = d.N[j] > maxH ? d.N[j] : maxH;
+    for (int j = 0; j < d.n_layers; ++j) {
+        w->stats[j] = reinterpret_cast<float2*>(base + off);
+        off = align_up(off + sizeof(float2) * (size_t)M, 256);
+    }
+    if (training) {
+        for (int j = 0; j + 1 < d.n_layers; ++j) {
+            w->Y[j] = reinterpret_cast<float*>(base + off);
+            off = align_up(off + sizeof(float) * (size_t)M * d.N[j], 256);
+        }
+        w->dz = reinterpret_cast<float*>(base + off);
+        off = align_up(off + sizeof(float) * (size_t)M * maxH, 256);
+        w->dxh = reinterpret_cast<float*>(base + off);
+        off = align_up(off + sizeof(float) * (size_t)M * maxH, 256);
+        size_t pf = (size_t)kFinalBlocks * (d.K[d.n_layers - 1] + 1);
+        for (int j = 0; j + 1 < d.n_layers; ++j) {
+            size_t need = (size_t)wgrad_splits(M, d.N[j], d.K[j] + 1) * d.N[j] * (d.K[j] + 1);
+            pf = need > pf ? need : pf;
+        }
+        w->partials = reinterpret_cast<float*>(base + off);
+        w->partial_floats = pf;
+        off = align_up(off + sizeof(float) * pf, 256);
+    } else {
+        // inference: ping-pong two activation buffers
+        float* a = reinterpret_cast<float*>(base + off);
+        off = align_up(off + sizeof(float) * (size_t)M * maxH, 256);
+        float* b = reinterpret_cast<float*>(base + off);
+        off = align_up(off + sizeof(float) * (size_t)M * maxH, 256);
+        for (int j = 0; j + 1 < d.n_layers; ++j) w->Y[j] = (j & 1) ? b : a;
+        w->dz = w->dxh = w->partials = nullptr;
+        w->partial_floats = 0;
+    }
+    w->total_bytes = off;
+}
+
+// ------------------------------------------------------------------------------------------------
+// row-wise kernels (one warp per row)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ const float* row_ptr(const float* X, const int32_t* docid, int r, int ld) {
+    return X + (size_t)(docid ? docid[r] : r) * ld;
+}
+
+__device__ __forceinline__ float2 warp_row_stats(const float* __restrict__ x, int K, int lane) {
+    float s = 0.f;
+    for (int k = lane; k < K; k += kWarp) s += x[k];
+    float mean = warp_sum(s) / (float)K;
+    float v = 0.f;
+    for (int k = lane; k < K; k += kWarp) {
+        float dlt = x[k] - mean;
+        v += dlt * dlt;
+    }
+    float var = warp_sum(v) / (float)K;
+    return make_float2(mean, 1.0f / sqrtf(var + kLnEps));
+}
+
+__global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict__ X, const int32_t* __restrict__ docid,
+                                                         int M, int K, float2* __restrict__ stats) {
+    int lane = threadIdx.x & 31;
+    int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= M) return;
+    const float* x = row_ptr(X, docid, r, K);
+    float2 st = warp_row_stats(x, K, lane);
+    if (lane == 0) stats[r] = st;
+}
+
+// final layer forward: score = LN(x) . w + c, written to scores[b*L + l] for row r = l*B + b
+__global__ void __launch_bounds__(256) final_fwd_kernel(const float* __restrict__ X, const int32_t* __restrict__ docid,
+                                                         int M, int K, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, const float* __restrict__ w,
+                                                         const float* __restrict__ c, float2* __restrict__ stats,
+                                                         float* __restrict__ scores, int L, int B) {
+    int lane = threadIdx.x & 31;
+    int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= M) return;
+    const float* x = row_ptr(X, docid, r, K);
+    float2 st = warp_row_stats(x, K, lane);
+    float acc = 0.f;
+    for (int k = lane; k < K; k += kWarp) {
+        float a = (x[k] - st.x) * st.y * gamma[k] + beta[k];
+        acc = fmaf(a, w[k], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        if (stats) stats[r] = st;
+        int l = r / B, b = r - l * B;
+        scores[(size_t)b * L + l] = acc + c[0];
+    }
+}
+
+// final layer backward: dZ_prev[r,:] = LNbwd(ds_r * w (.) gamma) (.) ELU'(x) and per-block column partials of
+// G[k] = sum_r ds_r xhat_rk, G[K] = sum_r ds_r.
+__global__ void __launch_bounds__(256) final_bwd_kernel(const float* __restrict__ X, const int32_t* __restrict__ docid,
+                                                         const float2* __restrict__ stats, int M, int K,
+                                                         const float* __restrict__ gamma, const float* __restrict__ w,
+                                                         const float* __restrict__ dscores, int L, int B,
+                                                         float* __restrict__ dz_prev, float* __restrict__ colpart) {
+    extern __shared__ float sm[];   // [8][K+1]
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    float* acc = sm + (size_t)wid * (K + 1);
+    for (int k = lane; k <= K; k += kWarp) acc[k] = 0.f;
+    __syncwarp();
+    for (int r = blockIdx.x * nw + wid; r < M; r += gridDim.x * nw) {
+        const float* x = row_ptr(X, docid, r, K);
+        float2 st = stats[r];
+        int l = r / B, b = r - l * B;
+        float ds = dscores[(size_t)b * L + l];
+        float s1 = 0.f, s2 = 0.f;
+        for (int k = lane; k < K; k += kWarp) {
+            float xh = (x[k] - st.x) * st.y;
+            float dxh = ds * w[k] * gamma[k];
+            s1 += dxh;
+            s2 = fmaf(dxh, xh, s2);
+            acc[k] = fmaf(ds, xh, acc[k]);
+        }
+        if (lane == 0) acc[K] += ds;
+        if (dz_prev) {
+            s1 = warp_sum(s1) / (float)K;
+            s2 = warp_sum(s2) / (float)K;
+            for (int k = lane; k < K; k += kWarp) {
+                float xv = x[k];
+                float xh = (xv - st.x) * st.y;
+                float dxh = ds * w[k] * gamma[k];
+                float dx = st.y * (dxh - s1 - xh * s2);
+                dz_prev[(size_t)r * K + k] = dx * elu_grad_from_out(xv);
+            }
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k <= K; k += blockDim.x) {
+        float s = 0.f;
+        for (int q = 0; q < nw; ++q) s += sm[(size_t)q * (K + 1) + k];
+        colpart[(size_t)blockIdx.x * (K + 1) + k] = s;
+    }
+}
+
+// dZ_{j-1}[r,:] = LNbwd(dXhat[r,:]) (.) ELU'(X[r,:])   (X = Y_{j-1} is both the LN input and the ELU output)
+__global__ void __launch_bounds__(256) ln_bwd_elu_kernel(const float* __restrict__ dxh, const float* __restrict__ X,
+                                                          const float2* __restrict__ stats, int M, int K,
+                                                          float* __restrict__ dz_prev) {
+    int lane = threadIdx.x & 31;
+    int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= M) return;
+    const float* x = X + (size_t)r * K;
+    const float* g = dxh + (size_t)r * K;
+    float2 st = stats[r];
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = lane; k < K; k += kWarp) {
+        float xh = (x[k] - st.x) * st.y;
+        float d = g[k];
+        s1 += d;
+        s2 = fmaf(d, xh, s2);
+    }
+    s1 = warp_sum(s1) / (float)K;
+    s2 = warp_sum(s2) / (float)K;
+    for (int k = lane; k < K; k += kWarp) {
+        float xv = x[k];
+        float xh = (xv - st.x) * st.y;
+        float dx = st.y * (g[k] - s1 - xh * s2);
+        dz_prev[(size_t)r * K + k] = dx * elu_grad_from_out(xv);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic fp32 tiled GEMM  C[i,j] = sum_c A(i,c) * B(j,c)  with mode-specific operand loads / epilogues
+// ------------------------------------------------------------------------------------------------
+enum { MODE_FWD = 0, MODE_DGRAD = 1, MODE_WGRAD = 2 };
+
+struct GemmArgs {
+    int I, J, C;                 // output rows, output cols, contraction length
+    const float* X;              // layer input rows [M,K] (FWD / WGRAD)
+    const int32_t* docid;        // gather indices for layer 0 (or nullptr)
+    const float2* stats;         // [M] (mean, rstd) of X rows
+    const float* gamma;          // [K]
+    const float* beta;           // [K]
+    const float* W;              // [N,K]
+    const float* bias;           // [N]
+    const float* dZ;             // [M,N]
+    float* out;
+    int K, N;                    // layer dims
+    int act;                     // FWD: apply ELU
+    int rows_per_split;          // WGRAD
+};
+
+template <int MODE>
+__device__ __forceinline__ float elem_a(const GemmArgs& a, int i, int c) {
+    if (MODE == MODE_FWD) {          // i = m, c = k
+        const float* x = row_ptr(a.X, a.docid, i, a.K);
+        float2 st = a.stats[i];
+        return (x[c] - st.x) * st.y * a.gamma[c] + a.beta[c];
+    } else if (MODE == MODE_DGRAD) { // i = m, c = n
+        return a.dZ[(size_t)i * a.N + c];
+    } else {                         // WGRAD: i = n, c = m
+        return a.dZ[(size_t)c * a.N + i];
+    }
+}
+template <int MODE>
+__device__ __forceinline__ float elem_b(const GemmArgs& a, int j, int c) {
+    if (MODE == MODE_FWD) {          // j = n, c = k
+        return a.W[(size_t)j * a.K + c];
+    } else if (MODE == MODE_DGRAD) { // j = k, c = n
+        return a.W[(size_t)c * a.K + j] * a.gamma[j];
+    } else {                         // WGRAD: j = k (k == K -> ones column for the bias gradient), c = m
+        if (j == a.K) return 1.f;
+        const float* x = row_ptr(a.X, a.docid, c, a.K);
+        float2 st = a.stats[c];
+        return (x[j] - st.x) * st.y;
+    }
+}
+
+template <int MODE, int BN>
+__global__ void __launch_bounds__(256) gemm_kernel(GemmArgs a) {
+    constexpr int BM = 128, BK = 16, TM = 8, TN = BN / 16;
+    constexpr bool A_CC = (MODE != MODE_WGRAD);   // A contiguous in memory along the contraction index
+    constexpr bool B_CC = (MODE == MODE_FWD);
+    constexpr int A_PER = BM * BK / 256, B_PER = BN * BK / 256;
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+    int c_begin = 0, c_end = a.C;
+    if (MODE == MODE_WGRAD) {
+        c_begin = blockIdx.z * a.rows_per_split;
+        c_end = min(a.C, c_begin + a.rows_per_split);
+    }
+    float acc[TM][TN];
+#pragma unroll
+    for (int p = 0; p < TM; ++p)
+#pragma unroll
+        for (int q = 0; q < TN; ++q) acc[p][q] = 0.f;
+    float ra[A_PER], rb[B_PER];
+
+    auto load_tiles = [&](int c0) {
+#pragma unroll
+        for (int e = 0; e < A_PER; ++e) {
+            int idx = tid + e * 256;
+            int i = A_CC ? idx / BK : idx % BM;
+            int c = A_CC ? idx % BK : idx / BM;
+            ra[e] = (i0 + i < a.I && c0 + c < c_end) ? elem_a<MODE>(a, i0 + i, c0 + c) : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < B_PER; ++e) {
+            int idx = tid + e * 256;
+            int j = B_CC ? idx / BK : idx % BN;
+            int c = B_CC ? idx % BK : idx / BN;
+            rb[e] = (j0 + j < a.J && c0 + c < c_end) ? elem_b<MODE>(a, j0 + j, c0 + c) : 0.f;
+        }
+    };
+    auto store_tiles = [&]() {
+#pragma unroll
+        for (int e = 0; e < A_PER; ++e) {
+            int idx = tid + e * 256;
+            int i = A_CC ? idx / BK : idx % BM;
+            int c = A_CC ? idx % BK : idx / BM;
+            As[c][i] = ra[e];
+        }
+#pragma unroll
+        for (int e = 0; e < B_PER; ++e) {
+            int idx = tid + e * 256;
+            int j = B_CC ? idx / BK : idx % BN;
+            int c = B_CC ? idx % BK : idx / BN;
+            Bs[c][j] = rb[e];
+        }
+    };
+
+    if (c_begin < c_end) load_tiles(c_begin);
+    for (int c0 = c_begin; c0 < c_end; c0 += BK) {
+        store_tiles();
+        __syncthreads();
+        if (c0 + BK < c_end) load_tiles(c0 + BK);
+#pragma unroll
+        for (int c = 0; c < BK; ++c) {
+            float av[TM], bv[TN];
+#pragma unroll
+            for (int p = 0; p < TM; p += 4) {
+                float4 t = *reinterpret_cast<const float4*>(&As[c][ty * TM + p]);
+                av[p] = t.x; av[p + 1] = t.y; av[p + 2] = t.z; av[p + 3] = t.w;
+            }
+#pragma unroll
+            for (int q = 0; q < TN; q += 4) {
+                float4 t = *reinterpret_cast<const float4*>(&Bs[c][tx * TN + q]);
+                bv[q] = t.x; bv[q + 1] = t.y; bv[q + 2] = t.z; bv[q + 3] = t.w;
+            }
+#pragma unroll
+            for (int p = 0; p < TM; ++p)
+#pragma unroll
+                for (int q = 0; q < TN; ++q) acc[p][q] = fmaf(av[p], bv[q], acc[p][q]);
+        }
+        __syncthreads();
+    }
+
+    // epilogue
+    float* out = a.out;
+    if (MODE == MODE_WGRAD) out += (size_t)blockIdx.z * a.I * a.J;
+#pragma unroll
+    for (int p = 0; p < TM; ++p) {
+        int i = i0 + ty * TM + p;
+        if (i >= a.I) continue;
+#pragma unroll
+        for (int q = 0; q < TN; ++q) {
+            int j = j0 + tx * TN + q;
+            if (j >= a.J) continue;
+            float v = acc[p][q];
+            if (MODE == MODE_FWD) {
+                v += a.bias[j];
+                if (a.act) v = elu_f(v);
+            }
+            out[(size_t)i * a.J + j] = v;
+        }
+    }
+}
+
+// reduce the split-M partials G[s][n][k] (k == K holds db) and derive all parameter gradients of the layer:
+//   dW[n,k] = gamma_k G[n,k] + beta_k db[n];  db[n];  dgamma_k = sum_n W[n,k] G[n,k];  dbeta_k = sum_n W[n,k] db[n]
+__global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __restrict__ part, int S, int N, int K,
+                                                              const float* __restrict__ W,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float* __restrict__ dW,
+                                                              float* __restrict__ db, float* __restrict__ dgamma,
+                                                              float* __restrict__ dbeta) {
+    __shared__ float sg[8][33], sb[8][33];
+    const int kx = threadIdx.x & 31, ny = threadIdx.x >> 5;
+    const int k = blockIdx.x * 32 + kx;
+    const int K1 = K + 1;
+    const size_t plane = (size_t)N * K1;
+    float ag = 0.f, ab = 0.f;
+    float gk = (k < K) ? gamma[k] : 0.f, bk = (k < K) ? beta[k] : 0.f;
+    for (int n = ny; n < N; n += 8) {
+        float dbn = 0.f, g = 0.f;
+        for (int s = 0; s < S; ++s) dbn += part[s * plane + (size_t)n * K1 + K];
+        if (k < K) {
+            for (int s = 0; s < S; ++s) g += part[s * plane + (size_t)n * K1 + k];
+            float wv = W[(size_t)n * K + k];
+            dW[(size_t)n * K + k] = fmaf(gk, g, bk * dbn);
+            ag = fmaf(wv, g, ag);
+            ab = fmaf(wv, dbn, ab);
+        }
+        if (blockIdx.x == 0 && kx == 0) db[n] = dbn;
+    }
+    sg[ny][kx] = ag;
+    sb[ny][kx] = ab;
+    __syncthreads();
+    if (ny == 0 && k < K) {
+        float tg = 0.f, tb = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            tg += sg[q][kx];
+            tb += sb[q][kx];
+        }
+        dgamma[k] = tg;
+        dbeta[k] = tb;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+static void launch_gemm(const GemmArgs& a, int splits, cudaStream_t st) {
+    if (a.J <= 64) {
+        dim3 grid((a.J + 63) / 64, (a.I + 127) / 128, splits);
+        gemm_kernel<MODE, 64><<<grid, 256, 0, st>>>(a);
+    } else {
+        dim3 grid((a.J + 127) / 128, (a.I + 127) / 128, splits);
+        gemm_kernel<MODE, 128><<<grid, 256, 0, st>>>(a);
+    }
+}
+
+}  // namespace ub200
+
+using namespace ub200;
+
+extern "C" UB200_API size_t ub200_mlp_param_count(int F, const int* hidden, int n_hidden) {
+    LayerDims d;
+    if (make_dims(F, hidden, n_hidden, &d)) return 0;
+    return d.n_params;
+}
+
+extern "C" UB200_API size_t ub200_mlp_workspace_bytes(int L, int B, int F, const int* hidden, int n_hidden, int training) {
+    LayerDims d;
+    if (make_dims(F, hidden, n_hidden, &d) || L <= 0 || B <= 0) return 0;
+    MlpWorkspace w;
+    carve(d, L * B, training, nullptr, &w);
+    return w.total_bytes;
+}
+
+extern "C" UB200_API int ub200_mlp_forward(const float* feats, const int32_t* docid, int L, int B, int F, const int* hidden,
+                                 int n_hidden, const float* params, float* scores, void* workspace,
+                                 size_t workspace_bytes, int training, void* stream) {
+    LayerDims d;
+    UB_CHECK(make_dims(F, hidden, n_hidden, &d) == 0, 1, "mlp_forward: bad layer spec");
+    UB_CHECK(L > 0 && B > 0, 1, "mlp_forward: bad L=%d B=%d", L, B);
+    UB_CHECK(feats && params && scores && workspace, 2, "mlp_forward: null pointer");
+    const int M = L * B;
+    MlpWorkspace w;
+    carve(d, M, training, static_cast<char*>(workspace), &w);
+    UB_CHECK(w.total_bytes <= workspace_bytes, 3, "mlp_forward: workspace too small (%zu < %zu)", workspace_bytes,
+             w.total_bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int row_blocks = (M + 7) / 8;
+    const float* X = feats;
+    const int32_t* idx = docid;
+    for (int j = 0; j < d.n_layers; ++j) {
+        const int K = d.K[j], N = d.N[j];
+        const float* g = params + d.off_g[j];
+        const float* bt = params + d.off_b[j];
+        const float* W = params + d.off_w[j];
+        const float* c = params + d.off_c[j];
+        if (j == d.n_layers - 1) {
+            final_fwd_kernel<<<row_blocks, 256, 0, st>>>(X, idx, M, K, g, bt, W, c, w.stats[j], scores, L, B);
+            UB_LAUNCH_CHECK("final_fwd_kernel");
+        } else {
+            row_stats_kernel<<<row_blocks, 256, 0, st>>>(X, idx, M, K, w.stats[j]);
+            UB_LAUNCH_CHECK("row_stats_kernel");
+            GemmArgs a{};
+            a.I = M; a.J = N; a.C = K;
+            a.X = X; a.docid = idx; a.stats = w.stats[j]; a.gamma = g; a.beta = bt; a.W = W; a.bias = c;
+            a.out = w.Y[j]; a.K = K; a.N = N; a.act = 1;
+            launch_gemm<MODE_FWD>(a, 1, st);
+            UB_LAUNCH_CHECK("gemm_kernel<FWD>");
+            X = w.Y[j];
+            idx = nullptr;
+        }
+    }
+    return 0;
+}
+
+extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* docid, int L, int B, int F, const int* hidden,
+                                  int n_hidden, const float* params, const float* dscores, float* grads,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+    LayerDims d;
+    UB_CHECK(make_dims(F, hidden, n_hidden, &d) == 0, 1, "mlp_backward: bad layer spec");
+    UB_CHECK(L > 0 && B > 0, 1, "mlp_backward: bad L=%d B=%d", L, B);
+    UB_CHECK(feats && params && dscores && grads && workspace, 2, "mlp_backward: null pointer");
+    const int M = L * B;
+    MlpWorkspace w;
+    carve(d, M, 1, static_cast<char*>(workspace), &w);
+    UB_CHECK(w.total_bytes <= workspace_bytes, 3, "mlp_backward: workspace too small (%zu < %zu)", workspace_bytes,
+             w.total_bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int row_blocks = (M + 7) / 8;
+    const int nl = d.n_layers;
+
+    // final layer (N = 1)
+    {
+        const int j = nl - 1, K = d.K[j];
+        const float* X = (j == 0) ? feats : w.Y[j - 1];
+        const int32_t* idx = (j == 0) ? docid : nullptr;
+        int blocks = kFinalBlocks;
+        if (blocks > row_blocks) blocks = row_blocks;
+        size_t smem = sizeof(float) * 8 * (size_t)(K + 1);
+        UB_CHECK(smem <= 200 * 1024, 4, "mlp_backward: final-layer width %d too large", K);
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(final_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        final_bwd_kernel<<<blocks, 256, smem, st>>>(X, idx, w.stats[j], M, K, params + d.off_g[j],
+                                                    params + d.off_w[j], dscores, L, B, (j == 0) ? nullptr : w.dz,
+                                                    w.partials);
+        UB_LAUNCH_CHECK("final_bwd_kernel");
+        wgrad_finalize_kernel<<<(K + 31) / 32, 256, 0, st>>>(w.partials, blocks, 1, K, params + d.off_w[j],
+                                                             params + d.off_g[j], params + d.off_b[j],
+                                                             grads + d.off_w[j], grads + d.off_c[j],
+                                                             grads + d.off_g[j], grads + d.off_b[j]);
+        UB_LAUNCH_CHECK("wgrad_finalize_kernel(final)");
+    }
+    // hidden layers, last to first; w.dz holds dZ_j [M, N_j]
+    for (int j = nl - 2; j >= 0; --j) {
+        const int K = d.K[j], N = d.N[j];
+        const float* X = (j == 0) ? feats : w.Y[j - 1];
+        const int32_t* idx = (j == 0) ? docid : nullptr;
+        const float* g = params + d.off_g[j];
+        const float* bt = params + d.off_b[j];
+        const float* W = params + d.off_w[j];
+        // weight gradient GEMM: G[n, k] (k == K -> db)
+        const int S = wgrad_splits(M, N, K + 1);
+        int rps = (M + S - 1) / S;
+        rps = (rps + 15) / 16 * 16;
+        GemmArgs a{};
+        a.I = N; a.J = K + 1; a.C = M;
+        a.X = X; a.docid = idx; a.stats = w.stats[j]; a.dZ = w.dz; a.out = w.partials;
+        a.K = K; a.N = N; a.rows_per_split = rps;
+        const int S_eff = (M + rps - 1) / rps;
+        launch_gemm<MODE_WGRAD>(a, S_eff, st);
+        UB_LAUNCH_CHECK("gemm_kernel<WGRAD>");
+        wgrad_finalize_kernel<<<(K + 31) / 32, 256, 0, st>>>(w.partials, S_eff, N, K, W, g, bt, grads + d.off_w[j],
+                                                             grads + d.off_c[j], grads + d.off_g[j],
+                                                             grads + d.off_b[j]);
+        UB_LAUNCH_CHECK("wgrad_finalize_kernel");
+        if (j > 0) {
+            GemmArgs b{};
+            b.I = M; b.J = K; b.C = N;
+            b.dZ = w.dz; b.W = W; b.gamma = g; b.out = w.dxh; b.K = K; b.N = N;
+            launch_gemm<MODE_DGRAD>(b, 1, st);
+            UB_LAUNCH_CHECK("gemm_kernel<DGRAD>");
+            ln_bwd_elu_kernel<<<row_blocks, 256, 0, st>>>(w.dxh, X, w.stats[j], M, K, w.dz);
+            UB_LAUNCH_CHECK("ln_bwd_elu_kernel");
+        }
+    }
+    return 0;
+}

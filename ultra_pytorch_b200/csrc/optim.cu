@@ -1,0 +1,123 @@
+// clip_grad_norm_ + Adagrad / SGD on a flat fp32 parameter buffer (sm_100a).
+// Replaces BaseAlgorithm.opt_step (base_algorithm.py:208-226) and DLA.separate_gradient_update (dla.py:141-166).
+// Two launches: (1) deterministic global L2 norm of the (loss-normalised) gradient, (2) clip + update.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace ub200 {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+constexpr int kOptBlocks = 2 * kNumSMs;
+// workspace: [counter | norm (float at +64B)] [partials kOptBlocks]
+static size_t opt_ws_bytes() { return 256 + sizeof(float) * kOptBlocks; }
+
+__device__ __forceinline__ float grad_scale(const float* den, float scale_const) {
+    return den ? scale_const / den[0] : scale_const;
+}
+
+__global__ void __launch_bounds__(256) grad_norm_kernel(const float* __restrict__ g, size_t n,
+                                                         const float* __restrict__ den, float scale_const,
+                                                         unsigned int* counter, float* __restrict__ norm_slot,
+                                                         float* __restrict__ partials, float* __restrict__ norm_out) {
+    __shared__ float red[8];
+    const float sc = grad_scale(den, scale_const);
+    float s = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float v = g[i] * sc;
+        s = fmaf(v, v, s);
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) t += red[q];
+        partials[blockIdx.x] = t;
+    }
+    if (last_block_ticket(counter, gridDim.x)) {
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int b = 0; b < (int)gridDim.x; ++b) t += partials[b];
+            float nrm = sqrtf(t);
+            norm_slot[0] = nrm;
+            if (norm_out) norm_out[0] = nrm;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) clip_update_kernel(float* __restrict__ p, float* __restrict__ g,
+                                                           float* __restrict__ state, size_t n,
+                                                           const float* __restrict__ den, float scale_const,
+                                                           float max_norm, float lr, int mode,
+                                                           const float* __restrict__ norm_slot) {
+    float sc = grad_scale(den, scale_const);
+    if (max_norm > 0.f) {
+        float coef = max_norm / (norm_slot[0] + 1e-6f);     // torch.nn.utils.clip_grad_norm_
+        sc *= fminf(coef, 1.f);
+    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float gi = g[i] * sc;
+        g[i] = gi;
+        float pi = p[i];
+        if (mode == 2) {
+            pi -= lr * gi;
+        } else {
+            float ss = gi * gi;
+            if (mode == 0) {
+                ss += state[i];
+                state[i] = ss;
+            }
+            pi -= lr * gi / (sqrtf(ss) + 1e-10f);              // torch.optim.Adagrad, eps = 1e-10
+        }
+        p[i] = pi;
+    }
+}
+
+}  // namespace ub200
+
+using namespace ub200;
+
+extern "C" UB200_API const char* ub200_last_error(void) { return g_err; }
+extern "C" UB200_API int ub200_abi_version(void) { return 1; }
+extern "C" UB200_API unsigned long long ub200_launch_count(void) { return g_launches.load(); }
+
+extern "C" UB200_API size_t ub200_opt_workspace_bytes(size_t n) {
+    (void)n;
+    return opt_ws_bytes();
+}
+
+extern "C" UB200_API int ub200_clip_update(float* params, float* grads, float* state_sum, size_t n, const float* den,
+                                 float scale_const, float max_norm, float lr, int mode, float* norm_out,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+    UB_CHECK(params && grads && workspace && n > 0, 2, "clip_update: null pointer / empty buffer");
+    UB_CHECK(mode == 1 || mode == 2 || (mode == 0 && state_sum), 1, "clip_update: bad mode %d", mode);
+    UB_CHECK(workspace_bytes >= opt_ws_bytes(), 3, "clip_update: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned int* counter = static_cast<unsigned int*>(workspace);
+    float* norm_slot = reinterpret_cast<float*>(static_cast<char*>(workspace) + 64);
+    float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
+    int grid = (int)((n + 256 * 4 - 1) / (256 * 4));
+    if (grid > kOptBlocks) grid = kOptBlocks;
+    if (grid < 1) grid = 1;
+    if (max_norm > 0.f || norm_out) {
+        grad_norm_kernel<<<grid, 256, 0, st>>>(grads, n, den, scale_const, counter, norm_slot, partials, norm_out);
+        UB_LAUNCH_CHECK("grad_norm_kernel");
+    }
+    clip_update_kernel<<<grid, 256, 0, st>>>(params, grads, state_sum, n, den, scale_const, max_norm, lr, mode,
+                                             norm_slot);
+    UB_LAUNCH_CHECK("clip_update_kernel");
+    return 0;
+}

@@ -1,0 +1,207 @@
+"""Device-side state and launch plumbing for the hot path (PyTorch is used for device memory and streams only).
+
+`RankerEngine` owns, for one DNN ranker on one GPU:
+  - the flat fp32 parameter / gradient / Adagrad-accumulator buffers (layout of include/ultra_b200.h),
+  - the kernel workspaces (zeroed once; the kernels keep their ticket counters at zero),
+  - a pinned host staging buffer + its device mirror for one step's input_feed.
+Every compute call goes through the C ABI (ultra_pytorch_b200._capi); there is no eager fallback.
+"""
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import check, int_array, lib
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Staged(object):
+    """Device views of one staged input_feed."""
+    __slots__ = ("feats", "docid", "labels", "B", "L", "n_docs", "h2d_bytes")
+
+
+class RankerEngine(object):
+    def __init__(self, feature_size, hidden, device=None, extra_floats=0):
+        if not torch.cuda.is_available():
+            raise _capi.UltraB200Error("ultra_pytorch_b200 needs a CUDA device (B200, sm_100a); no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.F = int(feature_size)
+        self.hidden = [int(h) for h in hidden]
+        self._hidden_c = int_array(self.hidden)
+        self.n_hidden = len(self.hidden)
+        self.P = int(lib.ub200_mlp_param_count(self.F, self._hidden_c, self.n_hidden))
+        if self.P == 0:
+            raise _capi.UltraB200Error("bad ranker spec F=%d hidden=%s" % (self.F, self.hidden))
+        self.E = int(extra_floats)
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.params = torch.zeros(self.P, **f32)
+        # gradient buffer with E trailing floats for the loss normalisers / EM partials, so that data-parallel
+        # ranks need ONE all-reduce per step
+        self.gradbuf = torch.zeros(self.P + self.E, **f32)
+        self.grads = self.gradbuf[:self.P]
+        self.extra = self.gradbuf[self.P:]
+        self.state_sum = torch.zeros(self.P, **f32)
+        self.norm = torch.zeros(1, **f32)
+        self._ws = {}
+        self._opt_ws = torch.zeros(int(lib.ub200_opt_workspace_bytes(self.P)), dtype=torch.uint8, device=self.device)
+        self._loss_ws = None
+        self._pin = None
+        self._dev = None
+        self._scores = {}
+        self._dscores = {}
+
+    # ---- parameter views -------------------------------------------------------------------------
+    def layer_slices(self):
+        """[(name, offset, shape)] in the flat layout == the reference's state_dict order (DNN.py:43-55)."""
+        out, off, k = [], 0, self.F
+        for j, n in enumerate(self.hidden + [1]):
+            for name, shape in (("layer_norm%d.weight" % j, (k,)), ("layer_norm%d.bias" % j, (k,)),
+                                ("linear%d.weight" % j, (n, k)), ("linear%d.bias" % j, (n,))):
+                cnt = int(np.prod(shape))
+                out.append((name, off, shape))
+                off += cnt
+            k = n
+        assert off == self.P
+        return out
+
+    # ---- workspaces ------------------------------------------------------------------------------
+    def _mlp_ws(self, L, B, training):
+        key = (L, B, int(bool(training)))
+        ws = self._ws.get(key)
+        if ws is None:
+            n = int(lib.ub200_mlp_workspace_bytes(L, B, self.F, self._hidden_c, self.n_hidden, key[2]))
+            ws = torch.zeros(max(n, 256), dtype=torch.uint8, device=self.device)
+            if len(self._ws) > 8:
+                self._ws.clear()
+            self._ws[key] = ws
+        return ws
+
+    def loss_ws(self, B, L):
+        n = max(int(lib.ub200_loss_workspace_bytes(B, L)), int(lib.ub200_pair_workspace_bytes(B, L)))
+        if self._loss_ws is None or self._loss_ws.numel() < n:
+            self._loss_ws = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        return self._loss_ws
+
+    def scores_buf(self, B, L):
+        key = (B, L)
+        t = self._scores.get(key)
+        if t is None:
+            if len(self._scores) > 8:
+                self._scores.clear()
+                self._dscores.clear()
+            t = torch.empty(B, L, dtype=torch.float32, device=self.device)
+            self._scores[key] = t
+            self._dscores[key] = torch.empty(B, L, dtype=torch.float32, device=self.device)
+        return t
+
+    def dscores_buf(self, B, L):
+        self.scores_buf(B, L)
+        return self._dscores[(B, L)]
+
+    # ---- staging: host input_feed -> device ---------------------------------------------------------
+    def stage(self, letor_features, docid_arrays, label_arrays):
+        """One pinned-memory pack + ONE async H2D copy of a step's inputs.
+
+        letor_features: np [n_docs, F] (f64 in the reference feeds, cast like DNN.py:73);
+        docid_arrays / label_arrays: L arrays of [B] (f32 in the feeds, base_algorithm.py:176-186).
+        Device layout: docid i32 [L, B] (position-major) | labels f32 [B, L] |
+                       feats f32 [n_docs+1, F] (last row = zero PAD, base_algorithm.py:148-149)."""
+        feats = np.asarray(letor_features)
+        n_docs = feats.shape[0] if feats.ndim == 2 else 0
+        L = len(docid_arrays)
+        B = len(docid_arrays[0])
+        nf = (n_docs + 1) * self.F
+        # fixed offsets for a given (L, B): docid | labels | feats (so captured CUDA graphs keep valid pointers)
+        off_l = 4 * L * B
+        off_f = (8 * L * B + 255) // 256 * 256
+        total = off_f + 4 * nf
+        if self._pin is None or self._pin.numel() < total:
+            cap = int(total * 1.5) + 1024
+            self._pin = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+            self._dev = torch.empty(cap, dtype=torch.uint8, device=self.device)
+            self._pin_np = self._pin.numpy()
+        buf = self._pin_np
+        hd = buf[:off_l].view(np.int32).reshape(L, B)
+        hl = buf[off_l:2 * off_l].view(np.float32).reshape(B, L)
+        hf = buf[off_f:total].view(np.float32).reshape(n_docs + 1, self.F)
+        if n_docs:
+            np.copyto(hf[:n_docs], feats, casting="same_kind")
+        hf[n_docs] = 0.0
+        for l in range(L):
+            np.copyto(hd[l], docid_arrays[l], casting="unsafe")
+            hl[:, l] = label_arrays[l]
+        # the pinned buffer is reused next step: callers sync once per step (loss read-back) before re-staging
+        self._dev[:total].copy_(self._pin[:total], non_blocking=True)
+        return self.staged_views(self._dev, L, B, n_docs)
+
+    def staged_views(self, dev, L, B, n_docs):
+        off_l = 4 * L * B
+        off_f = (8 * L * B + 255) // 256 * 256
+        total = off_f + 4 * (n_docs + 1) * self.F
+        st = Staged()
+        st.docid = dev[:off_l].view(torch.int32).view(L, B)
+        st.labels = dev[off_l:2 * off_l].view(torch.float32).view(B, L)
+        st.feats = dev[off_f:total].view(torch.float32).view(n_docs + 1, self.F)
+        st.B, st.L, st.n_docs, st.h2d_bytes = B, L, n_docs, total
+        return st
+
+    # ---- K1 ---------------------------------------------------------------------------------------
+    def forward(self, feats, docid, L, B, training, scores=None):
+        """feats f32 [rows, F] cuda, docid i32 [L*B] cuda or None (identity) -> scores [B, L]."""
+        if scores is None:
+            scores = self.scores_buf(B, L)
+        ws = self._mlp_ws(L, B, training)
+        check(lib.ub200_mlp_forward(_ptr(feats), _ptr(docid), L, B, self.F, self._hidden_c, self.n_hidden,
+                                    _ptr(self.params), _ptr(scores), _ptr(ws), ws.numel(), int(bool(training)),
+                                    _stream()), "ub200_mlp_forward")
+        return scores
+
+    def backward(self, feats, docid, L, B, dscores):
+        ws = self._mlp_ws(L, B, True)
+        check(lib.ub200_mlp_backward(_ptr(feats), _ptr(docid), L, B, self.F, self._hidden_c, self.n_hidden,
+                                     _ptr(self.params), _ptr(dscores), _ptr(self.grads), _ptr(ws), ws.numel(),
+                                     _stream()), "ub200_mlp_backward")
+        return self.grads
+
+    # ---- K2 / K3 -----------------------------------------------------------------------------------
+    def softmax_ce(self, scores, labels, weight_mode, table, dscores, sums):
+        B, L = scores.shape
+        ws = self.loss_ws(B, L)
+        check(lib.ub200_softmax_ce(_ptr(scores), _ptr(labels), B, L, weight_mode, _ptr(table),
+                                   0 if table is None else table.numel(), _ptr(dscores), _ptr(sums), _ptr(ws),
+                                   ws.numel(), _stream()), "ub200_softmax_ce")
+
+    def dla_loss(self, scores, clicks, prop_w, prop_b, dscores, dprop, sums):
+        B, L = scores.shape
+        ws = self.loss_ws(B, L)
+        check(lib.ub200_dla_loss(_ptr(scores), _ptr(clicks), B, L, _ptr(prop_w), _ptr(prop_b), _ptr(dscores),
+                                 _ptr(dprop), _ptr(sums), _ptr(ws), ws.numel(), _stream()), "ub200_dla_loss")
+
+    def lambdarank(self, scores, labels, sigma, t_plus, t_minus, dscores, out):
+        B, L = scores.shape
+        ws = self.loss_ws(B, L)
+        check(lib.ub200_lambdarank(_ptr(scores), _ptr(labels), B, L, float(sigma), _ptr(t_plus), _ptr(t_minus),
+                                   _ptr(dscores), _ptr(out), _ptr(ws), ws.numel(), _stream()), "ub200_lambdarank")
+
+    def pairdebias(self, scores, clicks, t_plus, t_minus, dscores, out):
+        B, L = scores.shape
+        ws = self.loss_ws(B, L)
+        check(lib.ub200_pairdebias(_ptr(scores), _ptr(clicks), B, L, _ptr(t_plus), _ptr(t_minus), _ptr(dscores),
+                                   _ptr(out), _ptr(ws), ws.numel(), _stream()), "ub200_pairdebias")
+
+    def em_update(self, t_plus, t_minus, out, em_step, reg_p, safe_div):
+        check(lib.ub200_em_update(_ptr(t_plus), _ptr(t_minus), _ptr(out), t_plus.numel(), float(em_step),
+                                  float(reg_p), int(bool(safe_div)), _stream()), "ub200_em_update")
+
+    # ---- optimizer ------------------------------------------------------------------------------------
+    def clip_update(self, params, grads, state_sum, den, scale_const, max_norm, lr, mode, norm_out=None):
+        n = params.numel()
+        check(lib.ub200_clip_update(_ptr(params), _ptr(grads), _ptr(state_sum), n, _ptr(den), float(scale_const),
+                                    float(max_norm), float(lr), int(mode), _ptr(norm_out), _ptr(self._opt_ws),
+                                    self._opt_ws.numel(), _stream()), "ub200_clip_update")

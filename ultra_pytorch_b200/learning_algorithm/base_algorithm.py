@@ -1,0 +1,169 @@
+"""Shared host logic of the B200-native learning algorithms.
+
+Mirrors `ultra.learning_algorithm.BaseAlgorithm` (reference: ultra/learning_algorithm/base_algorithm.py:32-333):
+same constructor `(data_set, exp_settings)`, same `train(input_feed)` / `validation(input_feed,
+is_online_simulation=False)` contract, same public attributes (`model`, `global_step`, `learning_rate`,
+`rank_list_size`, `max_candidate_num`, `feature_size`, `letor_features_name`, `docid_inputs_name`, `labels_name`,
+`hparams`, `is_cuda_avail`, `exp_settings`), so the reference's unmodified main.py and input feeds drive it.
+
+What changed underneath: `create_input_feed` + `get_ranking_scores` (host gather, base_algorithm.py:134-186) become
+one pinned-memory pack + one H2D copy, and ranking_model -> loss -> backward -> clip -> optimizer all run as
+hand-written sm_100a kernels through the C ABI on the current CUDA stream.  One D2H read of the loss scalars per
+step remains, as in the reference (`loss.item()`).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+from .. import metrics as b200_metrics
+from ..engine import RankerEngine  # noqa: F401  (re-exported for subclasses)
+from ..hparams import HParams  # noqa: F401
+
+
+def _reference_base():
+    """Subclass the reference's BaseAlgorithm when it is importable so `list_available()` sees the plugin
+    (ultra/learning_algorithm/__init__.py:17-20); stand alone otherwise."""
+    mod = sys.modules.get("ultra.learning_algorithm.base_algorithm")
+    if mod is not None and hasattr(mod, "BaseAlgorithm"):
+        return mod.BaseAlgorithm
+    return object
+
+
+def find_class(class_str):
+    """ultra/utils/sys_tools.py:7-21."""
+    mod_str, _, cls_str = class_str.rpartition('.')
+    __import__(mod_str)
+    return getattr(sys.modules[mod_str], cls_str)
+
+
+_RANKER_ALIASES = {
+    # the reference class path is accepted and mapped to the B200 implementation, so a settings JSON only has to
+    # switch the learning algorithm to move the whole hot path onto the GPU kernels
+    "ultra.ranking_model.DNN": "ultra_pytorch_b200.ranking_model.DNN",
+}
+
+
+class B200Algorithm(_reference_base()):
+    PADDING_SCORE = -100000                      # base_algorithm.py:37
+    VERBOSE = os.environ.get("UB200_QUIET", "0") != "1"
+
+    # ---- construction helpers ---------------------------------------------------------------------
+    def _init_common(self, data_set, exp_settings, extra_floats):
+        self.is_cuda_avail = True                # online feeds call .cpu() on the scores when this is set
+        self.cuda = torch.device('cuda')
+        self.train_summary = {}
+        self.eval_summary = {}
+        self.is_training = "is_train"
+        self.exp_settings = exp_settings
+        if 'selection_bias_cutoff' in self.exp_settings.keys():
+            self.rank_list_size = self.exp_settings['selection_bias_cutoff']
+        self.max_candidate_num = exp_settings['max_candidate_num']
+        self.feature_size = data_set.feature_size
+        self.letor_features_name = "letor_features"
+        self.letor_features = None
+        self.docid_inputs_name = []
+        self.labels_name = []
+        self.docid_inputs = []
+        self.labels = []
+        for i in range(self.max_candidate_num):
+            self.docid_inputs_name.append("docid_input{0}".format(i))
+            self.labels_name.append("label{0}".format(i))
+        self.global_step = 0
+        self._extra_floats = extra_floats
+        self.last_h2d_bytes = 0
+        self.last_d2h_bytes = 0
+
+    def create_model(self, feature_size):
+        """base_algorithm.py:156-167 (class resolved from exp_settings['ranking_model'])."""
+        cls_path = self.exp_settings['ranking_model']
+        cls_path = _RANKER_ALIASES.get(cls_path, cls_path)
+        cls = find_class(cls_path)
+        model = cls(self.exp_settings['ranking_model_hparams'], feature_size, extra_floats=self._extra_floats)
+        if not hasattr(model, "engine"):
+            raise TypeError("%s is not a B200 ranking model (no .engine): the B200 learning algorithms drive the "
+                            "fused kernels directly and have no fallback path" % cls_path)
+        return model
+
+    @property
+    def engine(self):
+        return self.model.engine
+
+    # ---- data-parallel plumbing ---------------------------------------------------------------------
+    @staticmethod
+    def world_size():
+        import torch.distributed as dist
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def _allreduce_gradbuf(self):
+        """ONE all-reduce per step over [DNN grads | loss normalisers | EM / DenoisingNet partials]."""
+        if self.world_size() > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.engine.gradbuf, op=dist.ReduceOp.SUM)
+
+    # ---- input staging --------------------------------------------------------------------------------
+    def _stage(self, input_feed, list_size):
+        docids = [input_feed[self.docid_inputs_name[i]] for i in range(list_size)]
+        labels = [input_feed[self.labels_name[i]] for i in range(list_size)]
+        self.letor_features = input_feed[self.letor_features_name]
+        st = self.engine.stage(self.letor_features, docids, labels)
+        self.last_h2d_bytes = st.h2d_bytes
+        return st
+
+    def _read_scalars(self, t):
+        """The one D2H sync of a step (the reference's loss.item())."""
+        host = t.detach().to("cpu", non_blocking=False)
+        self.last_d2h_bytes = host.numel() * 4
+        return host.numpy()
+
+    # ---- validation (identical text in all five reference algorithms, e.g. ipw_rank.py:184-211) ----------
+    def validation(self, input_feed, is_online_simulation=False):
+        self.model.eval()
+        L = self.max_candidate_num
+        st = self._stage(input_feed, L)
+        eng = self.engine
+        with torch.no_grad():
+            scores = eng.forward(st.feats, st.docid.view(-1), L, st.B, training=False)
+            self.output = scores.clone()
+        if not is_online_simulation:
+            out_host = self.output.cpu()
+            self.last_d2h_bytes = out_host.numel() * 4
+            docid_bl = np.stack([np.asarray(input_feed[self.docid_inputs_name[i]]) for i in range(L)], axis=1)
+            # same memory layout as the reference (a TRANSPOSED view of the [L, B] stack, base_algorithm.py:181-182):
+            # torch reduces strided tensors in a layout-dependent order, and the metrics must be bit-identical
+            self.labels = torch.from_numpy(np.transpose(
+                np.asarray([np.asarray(input_feed[self.labels_name[i]], dtype=np.float32) for i in range(L)])))
+            pad_removed = self.remove_padding_for_metric_eval(torch.from_numpy(docid_bl), out_host)
+            for metric in self.exp_settings['metrics']:
+                topn = self.exp_settings['metrics_topn']
+                metric_values = b200_metrics.make_ranking_metric_fn(metric, topn)(self.labels, pad_removed, None)
+                for n, metric_value in zip(topn, metric_values):
+                    self.create_summary('%s_%d' % (metric, n), '%s_%d' % (metric, n), metric_value.item(), False)
+        return None, self.output, self.eval_summary
+
+    def remove_padding_for_metric_eval(self, docid_bl, model_output):
+        """base_algorithm.py:88-116: documents whose id == n_docs (the PAD row) score PADDING_SCORE."""
+        n_docs = self.letor_features.shape[0]
+        valid = docid_bl.to(torch.int64) != n_docs
+        return torch.where(valid, model_output, torch.ones_like(model_output) * self.PADDING_SCORE)
+
+    def create_summary(self, scalar_name, summarize_name, value, is_training):
+        if is_training:
+            self.train_summary[summarize_name] = value
+        else:
+            self.eval_summary[summarize_name] = value
+
+    def _say(self, loss):
+        if self.VERBOSE:
+            print(" Loss %f at Global Step %d: " % (loss, self.global_step))
+
+    # ---- optimizer selection (ipw_rank.py:96-99) ---------------------------------------------------------
+    def _opt_mode(self, fresh=False):
+        if self.hparams.grad_strategy == 'sgd':
+            return 2
+        return 1 if fresh else 0
+
+    def _check_l2(self):
+        if getattr(self.hparams, "l2_loss", 0.0) > 0:
+            raise NotImplementedError("l2_loss > 0 is not implemented in the B200 path (reference default is 0.0)")
