@@ -191,6 +191,7 @@ def test_softmax_ce_vs_oracle(B, L, mode):
     s = (2.0 * rs.randn(B, L)).astype(np.float32)
     if mode == "ipw":
         y = (rs.rand(B, L) < 0.2).astype(np.float32)
+        y[0, 0] = 1.0                       # at least one click in the batch (sum w == 0 is 0/0 in the reference too)
         if B > 2:
             y[1] = 0.0                      # a list without clicks: W_b = 0 -> nan_to_num path
         table = np.linspace(1.0, 11.0, 40)
