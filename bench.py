@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py - queries/sec of the ULTRA training hot path on B200 (contract: see the task statement / DESIGN.md).
+
+    python bench.py --gpus 1 --steps 200 --warmup 20                     # the B200 arm (this repo's kernels)
+    python bench.py --impl reference --gpus 1 --steps 10 --warmup 3      # the reference's own CPU path
+    torchrun --nproc-per-node N ... bench.py --gpus N ...                # data-parallel, one rank per GPU
+
+A "step" = one `train()` of the workload's learning algorithm on one batch of B ranked lists (queries):
+DNN forward + loss + backward + clip_grad_norm + Adagrad.  Workload at N=1: BASELINE.json configs[1]
+(IPW + DNN[256,128,64], 136 features, list length 40, B = 256, PBM clicks) - `--workload` selects the others.
+
+  value : whole-job queries/s with the input batches already resident in HBM (a ring of distinct resident batches
+          larger than the 126 MB L2), timed with CUDA events, max over ranks.
+  e2e   : the same metric through the plugin's public `train(input_feed)` with HOST numpy feeds: pinned pack +
+          H2D copy of the batch + kernels + D2H read of the loss inside the timed region.
+  roofline : the DNN forward+backward kernels (K1) timed alone with CUDA events; algorithmic FLOPs per SURVEY 8(d).
+  cpu_baseline : the reference's CPU path (oracle/_ref, else the numpy oracle port) on the host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "queries/sec (IPW+DNN, MSLR-30K 136-feat, list_len 40) at 1/2/4/8 B200 vs CPU ref"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2_ipw_mslr10k")
+    ap.add_argument("--batch", type=int, default=0, help="override the batch size B (default: workload's, 256)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=0, help="timed steps of the cpu_baseline sample (0 = auto)")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm (reference / oracle port) - always a child process with CUDA hidden
+# ----------------------------------------------------------------------------------------------------------
+def run_cpu_arm(workload, batch, steps, warmup, timeout=900):
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "time_ref_cpu.py"), "--workload", workload,
+           "--steps", str(steps), "--warmup", str(warmup)]
+    if batch:
+        cmd += ["--batch", str(batch)]
+    env = dict(os.environ)
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    env["PYTHONDONTWRITEBYTECODE"] = "1"
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+        for line in reversed(out.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        return {"error": (out.stderr or out.stdout)[-400:]}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
+
+
+def cpu_steps_for(workload):
+    # ~10-30 s of CPU work per sample (survey-time probes)
+    return {"c2_ipw_mslr10k": 40, "c3_dla_yahoo": 20, "c4_lambdarank_mslr30k": 6, "c4_pairdebias_mslr30k": 1,
+            "c5_dla_istella": 10, "c1_na_toy": 40}.get(workload, 10)
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from ultra_pytorch_b200 import synth
+    w = dict(synth.WORKLOADS[args.workload])
+    if args.batch:
+        w["B"] = args.batch
+    r = run_cpu_arm(args.workload, args.batch, args.steps, args.warmup, timeout=3000)
+    if "error" in r:
+        print(json.dumps({"impl": "reference", "unavailable": r["error"].replace("\n", " ")[-300:]}))
+        return
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["queries_per_s"], "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "algo": w["algo"], "features": w["F"], "list_len": w["L"],
+                   "batch_queries": w["B"], "hidden": w["hidden"], "device": "host CPU"},
+        "cpu_baseline": {"value": r["queries_per_s"], "unit": "queries/s", "cores": r["cores"], "kind": r["kind"],
+                         "sample": r["sample"]},
+        "e2e": {"value": r["queries_per_s"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------------
+def main_b200(args):
+    import types
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from ultra_pytorch_b200 import _capi, synth
+    import ultra_pytorch_b200.learning_algorithm as la
+
+    la.B200Algorithm.VERBOSE = False
+    if args.no_graph:
+        la.B200Algorithm.USE_GRAPH = False
+    w = dict(synth.WORKLOADS[args.workload])
+    if args.batch:
+        w["B"] = args.batch
+    F, L, B, hidden = w["F"], w["L"], w["B"], w["hidden"]
+    torch.manual_seed(0)
+    settings = synth.exp_settings(args.workload)
+    model = getattr(la, w["algo"])(types.SimpleNamespace(feature_size=F), settings)
+    eng = model.engine
+
+    # ---- synthetic batches (rank-specific seeds: every rank trains on its own shard of queries) ----
+    n_host = 8
+    feeds = [synth.make_feed(1000 * rank + i, F, L, B, w["labels"]) for i in range(n_host)]
+    step_bytes = eng.stage(feeds[0]["letor_features"], [feeds[0]["docid_input%d" % l] for l in range(L)],
+                           [feeds[0]["label%d" % l] for l in range(L)]).h2d_bytes
+    ring_n = max(4, int(1.25 * L2_BYTES / step_bytes) + 1)
+    ring = []
+    for i in range(ring_n):
+        f = feeds[i % n_host]
+        st = eng.stage(f["letor_features"], [f["docid_input%d" % l] for l in range(L)],
+                       [f["label%d" % l] for l in range(L)])
+        torch.cuda.synchronize()
+        own = eng._dev[:st.h2d_bytes].clone()
+        ring.append(eng.staged_views(own, L, B, st.n_docs))
+    use_graph = la.B200Algorithm.USE_GRAPH and world == 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value leg: device-resident batches ----
+    for i in range(max(args.warmup, 3)):
+        model.run_step(ring[i % ring_n])
+    if use_graph:                       # make sure every ring slot has its graph before timing
+        for i in range(3 * ring_n):
+            model.run_step(ring[i % ring_n])
+    barrier()
+    launches0 = _capi.lib.ub200_launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        model.run_step(ring[k % ring_n])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    eager_launches = _capi.lib.ub200_launch_count() - launches0
+    t = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms / 1e3)
+
+    # kernels per step (graph replays launch the captured kernels without passing through the library counter)
+    model.USE_GRAPH_saved = la.B200Algorithm.USE_GRAPH
+    la.B200Algorithm.USE_GRAPH = False
+    c0 = _capi.lib.ub200_launch_count()
+    model.run_step(ring[0])
+    per_step = _capi.lib.ub200_launch_count() - c0
+    la.B200Algorithm.USE_GRAPH = model.USE_GRAPH_saved
+    gpu_launches = per_step * args.steps if use_graph else eager_launches
+
+    # ---- roofline leg: K1 (DNN forward + backward kernels) timed alone, graph-replayed ----
+    st0 = ring[0]
+    docid0 = st0.docid.view(-1)
+    dsc = eng.dscores_buf(B, L)
+    torch.cuda.synchronize()
+    g_f, g_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_f):
+        eng.forward(st0.feats, docid0, L, B, training=True)
+    with torch.cuda.graph(g_b):
+        eng.backward(st0.feats, docid0, L, B, dsc)
+    flush = torch.empty(L2_BYTES * 2 // 4, dtype=torch.float32, device="cuda")
+    n_rf = 20
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_rf)]
+    for it in range(n_rf + 3):
+        flush.zero_()                                        # flush L2 between timed iterations
+        ev = evs[max(it - 3, 0)]
+        ev[0].record(); g_f.replay(); ev[1].record()
+        ev[2].record(); g_b.replay(); ev[3].record()
+    torch.cuda.synchronize()
+    k1_ms = sum(e[0].elapsed_time(e[1]) + e[2].elapsed_time(e[3]) for e in evs) / n_rf
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / n_rf
+    flops = synth.train_flops_per_query(F, L, hidden) * B
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+    achieved_tf = flops / (k1_ms / 1e3) / 1e12
+    roofline = {"bound": "tensor", "achieved": round(achieved_tf, 3), "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": round(achieved_tf / peak_tf, 5), "traffic": None,
+                "kernel": "K1 DNN forward+backward (all launches of ub200_mlp_forward + ub200_mlp_backward)",
+                "ms_per_launch_group": round(k1_ms, 4), "fwd_ms": round(fwd_ms, 4),
+                "algorithmic_flops": flops, "peak_source": "MEASURED_PEAKS.json bf16 burst" if peaks else "fallback",
+                "fp32_ffma_peak_tflops": 72.0, "frac_of_fp32_ffma_peak": round(achieved_tf / 72.0, 4)}
+
+    # ---- e2e leg: public train(input_feed) with host feeds ----
+    for i in range(6):
+        model.train(feeds[i % n_host])
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        model.train(feeds[k % n_host])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e = {"value": round(world * B * args.steps / e2e_s, 1), "unit": "queries/s",
+           "h2d_bytes_per_step": int(model.last_h2d_bytes), "d2h_bytes_per_step": int(model.last_d2h_bytes),
+           "ms_per_step": round(1e3 * e2e_s / args.steps, 4)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "algo": w["algo"], "features": F, "list_len": L,
+                       "batch_queries": B, "hidden": hidden, "parallelism": "dp%d" % world,
+                       "cuda_graph": bool(use_graph),
+                       "l2": "ring of %d distinct resident batches (%.0f MB) > 126 MB L2" %
+                             (ring_n, ring_n * step_bytes / 1e6)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "kernels_per_step": int(per_step),
+            "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            n = args.cpu_steps or cpu_steps_for(args.workload)
+            r = run_cpu_arm(args.workload, args.batch, n, 3)
+            if "error" in r:
+                line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": None, "kind": "unavailable",
+                                        "sample": r["error"][-200:]}
+            else:
+                line["cpu_baseline"] = {"value": r["queries_per_s"], "unit": "queries/s", "cores": r["cores"],
+                                        "kind": r["kind"], "sample": r["sample"]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_b200(a)

@@ -102,7 +102,7 @@ class DLA(B200Algorithm):
         self.rank_list_size = self.exp_settings['selection_bias_cutoff']
         self.model.train()
         st = self._stage(input_feed, self.rank_list_size)
-        s = self._read_scalars(self.device_step(st))
+        s = self._read_scalars(self.run_step(st))
         mg = self.hparams.max_gradient_norm
         self.rank_loss = float(s[0] / s[1])
         self.exam_loss = float(s[2] / s[3])

@@ -52,7 +52,7 @@ class NavieAlgorithm(B200Algorithm):
         self.global_step += 1
         self.model.train()
         st = self._stage(input_feed, self.rank_list_size)
-        s = self._read_scalars(self.device_step(st))
+        s = self._read_scalars(self.run_step(st))
         self.loss = float(s[0] / s[1])
         self._say(self.loss)
         return self.loss, None, self.train_summary

@@ -65,7 +65,7 @@ class PairDebias(B200Algorithm):
         """pairwise_debias.py:106-174."""
         self.model.train()
         st = self._stage(input_feed, self.rank_list_size)
-        s = self._read_scalars(self.device_step(st))
+        s = self._read_scalars(self.run_step(st))
         self.loss = float(s[0]) * self._b_global
         if self.VERBOSE:
             print(" Loss %f at Global Step %d" % (self.loss, self.global_step))
