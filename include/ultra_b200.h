@@ -45,6 +45,11 @@ UB200_API const char* ub200_last_error(void);
 UB200_API int ub200_abi_version(void);
 /* number of kernel launches issued through this library since it was loaded (bench.py's gpu_launches) */
 UB200_API unsigned long long ub200_launch_count(void);
+/* K1 GEMM engine, a bit mask: 1 = forward, 2 = data-gradient, 4 = weight-gradient GEMMs of the hidden layers whose
+ * shapes qualify (K % 4 == 0, N % 64 == 0) run on the tcgen05 tensor cores with 3xTF32 error compensation; cleared
+ * bits use the CUDA-core fp32 kernels.  Default 7 (env UB200_TC overrides).  Both engines meet the same parity bound;
+ * the switch exists for A/B tests and profiling.  Returns the previous mask. */
+UB200_API int ub200_set_tc_mode(int mode);
 /* number of parameters of the DNN ranker for (F, hidden[]) in the flat layout above */
 UB200_API size_t ub200_mlp_param_count(int F, const int* hidden, int n_hidden);
 

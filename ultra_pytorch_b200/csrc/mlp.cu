@@ -10,9 +10,26 @@
 //             dW_j = gamma (.) G + beta (x) db, dgamma = sum_n W (.) G, dbeta = sum_n W db   (LayerNorm affine grads
 //             derived from the weight-gradient GEMM, so no gradient w.r.t. the features is ever formed)
 //             dXhat_j = dZ_j (W_j (.) gamma) ; dZ_{j-1} = LNbwd(dXhat_j) (.) ELU'(Y_{j-1})
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "mlp_tc.cuh"
 
 namespace ub200 {
+
+// Bit mask: which GEMMs of the tensor-core friendly hidden layers run on tcgen05 (3xTF32): 1 = forward,
+// 2 = data gradient, 4 = weight gradient; 0 = CUDA-core fp32 kernels everywhere.  Default 7 (env UB200_TC overrides).
+enum { TC_FWD = 1, TC_DGRAD = 2, TC_WGRAD = 4 };
+static int g_tc_mode = -1;
+static int tc_mode() {
+    if (g_tc_mode < 0) {
+        const char* e = getenv("UB200_TC");
+        g_tc_mode = e ? atoi(e) & 7 : 7;
+    }
+    return g_tc_mode;
+}
+static bool use_tc(int j, int K, int N, int what = 7) { return (tc_mode() & what) != 0 && tc_layer_ok(j, K, N); }
+
 
 // ------------------------------------------------------------------------------------------------
 // workspace carving
@@ -24,8 +41,16 @@ struct MlpWorkspace {
     float* dxh;                        // [M, maxH]
     float* partials;                   // split-M partial weight gradients
     size_t partial_floats;
+    float* fin_scratch;                // wgrad_finalize: per-block partial dgamma / dbeta
+    unsigned int* fin_counters;        // wgrad_finalize: one ticket per k-tile (zero between launches)
+    float* wf_hi[UB200_MAX_LAYERS];    // tensor-core path: pre-split weights (forward operand [N][Kpad])
+    float* wf_lo[UB200_MAX_LAYERS];
+    float* wd_hi[UB200_MAX_LAYERS];    // data-gradient operand [K][Npad] = (W * gamma)^T
+    float* wd_lo[UB200_MAX_LAYERS];
     size_t total_bytes;
 };
+
+static int round_up(int x, int a) { return (x + a - 1) / a * a; }
 
 constexpr int kFinalBlocks = 2 * kNumSMs;   // blocks of the final-layer backward (column partial sums)
 
@@ -59,10 +84,23 @@ static void carve(const LayerDims& d, int M, int training, char* base, MlpWorksp
         for (int j = 0; j + 1 < d.n_layers; ++j) {
             size_t need = (size_t)wgrad_splits(M, d.N[j], d.K[j] + 1) * d.N[j] * (d.K[j] + 1);
             pf = need > pf ? need : pf;
+            size_t need_tc = (size_t)tc_wgrad_splits(M, d.N[j], d.K[j]) * d.N[j] * round_up(d.K[j] + 1, 4);
+            pf = need_tc > pf ? need_tc : pf;
         }
         w->partials = reinterpret_cast<float*>(base + off);
         w->partial_floats = pf;
         off = align_up(off + sizeof(float) * pf, 256);
+        size_t sf = 0;
+        int maxK = 0;
+        for (int j = 0; j < d.n_layers; ++j) {
+            const size_t need = (size_t)((d.N[j] + 7) / 8) * 2 * d.K[j];
+            sf = need > sf ? need : sf;
+            maxK = d.K[j] > maxK ? d.K[j] : maxK;
+        }
+        w->fin_scratch = reinterpret_cast<float*>(base + off);
+        off = align_up(off + sizeof(float) * sf, 256);
+        w->fin_counters = reinterpret_cast<unsigned int*>(base + off);
+        off = align_up(off + sizeof(unsigned int) * ((maxK + 31) / 32), 256);
     } else {
         // inference: ping-pong two activation buffers
         float* a = reinterpret_cast<float*>(base + off);
@@ -72,8 +110,49 @@ static void carve(const LayerDims& d, int M, int training, char* base, MlpWorksp
         for (int j = 0; j + 1 < d.n_layers; ++j) w->Y[j] = (j & 1) ? b : a;
         w->dz = w->dxh = w->partials = nullptr;
         w->partial_floats = 0;
+        w->fin_scratch = nullptr;
+        w->fin_counters = nullptr;
+    }
+    for (int j = 0; j < UB200_MAX_LAYERS; ++j) w->wf_hi[j] = w->wf_lo[j] = w->wd_hi[j] = w->wd_lo[j] = nullptr;
+    for (int j = 0; j + 1 < d.n_layers; ++j) {
+        if (!tc_layer_ok(j, d.K[j], d.N[j])) continue;
+        const size_t nf = (size_t)d.N[j] * round_up(d.K[j], 32);
+        w->wf_hi[j] = reinterpret_cast<float*>(base + off);
+        off = align_up(off + sizeof(float) * nf, 256);
+        w->wf_lo[j] = reinterpret_cast<float*>(base + off);
+        off = align_up(off + sizeof(float) * nf, 256);
+        if (training && j > 0) {
+            const size_t nd = (size_t)d.K[j] * round_up(d.N[j], 32);
+            w->wd_hi[j] = reinterpret_cast<float*>(base + off);
+            off = align_up(off + sizeof(float) * nd, 256);
+            w->wd_lo[j] = reinterpret_cast<float*>(base + off);
+            off = align_up(off + sizeof(float) * nd, 256);
+        }
     }
     w->total_bytes = off;
+}
+
+// split the weights of the tensor-core layers into (hi, lo) TF32 operands for this step
+static int prep_tc_weights(const LayerDims& d, const MlpWorkspace& w, const float* params, int training,
+                           cudaStream_t st) {
+    tc::PrepTable t;
+    t.n = 0;
+    int max_elems = 0;
+    for (int j = 0; j + 1 < d.n_layers; ++j) {
+        if (!use_tc(j, d.K[j], d.N[j])) continue;
+        const int q = t.n++;
+        t.W[q] = params + d.off_w[j];
+        t.gamma[q] = params + d.off_g[j];
+        t.wf_hi[q] = w.wf_hi[j]; t.wf_lo[q] = w.wf_lo[j];
+        t.wd_hi[q] = training ? w.wd_hi[j] : nullptr;
+        t.wd_lo[q] = training ? w.wd_lo[j] : nullptr;
+        t.K[q] = d.K[j]; t.N[q] = d.N[j];
+        t.Kpad[q] = round_up(d.K[j], 32); t.Npad[q] = round_up(d.N[j], 32);
+        const int e = d.N[j] * t.Kpad[q] + (t.wd_hi[q] ? d.K[j] * t.Npad[q] : 0);
+        max_elems = e > max_elems ? e : max_elems;
+    }
+    if (t.n == 0) return 0;
+    return tc_prep(t, max_elems, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -353,33 +432,57 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs a) {
     }
 }
 
-// reduce the split-M partials G[s][n][k] (k == K holds db) and derive all parameter gradients of the layer:
+// reduce the split-M partials G[s][n][k] (k == K holds db; K1 = row stride of a partial plane) and derive all parameter
+// gradients of the layer:
 //   dW[n,k] = gamma_k G[n,k] + beta_k db[n];  db[n];  dgamma_k = sum_n W[n,k] G[n,k];  dbeta_k = sum_n W[n,k] db[n]
+// grid (ceil(K/32), ceil(N/8)), block 32 k x 8 n.  The sums over n cross blocks: per-block partials go to `scratch`
+// and the last block of each k-tile (ticket) adds them in block order, so the result is deterministic.
 __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __restrict__ part, int S, int N, int K,
-                                                              const float* __restrict__ W,
+                                                              int K1, const float* __restrict__ W,
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, float* __restrict__ dW,
                                                               float* __restrict__ db, float* __restrict__ dgamma,
-                                                              float* __restrict__ dbeta) {
+                                                              float* __restrict__ dbeta, float* __restrict__ scratch,
+                                                              unsigned int* __restrict__ counters) {
     __shared__ float sg[8][33], sb[8][33];
+    __shared__ bool is_last;
     const int kx = threadIdx.x & 31, ny = threadIdx.x >> 5;
-    const int k = blockIdx.x * 32 + kx;
-    const int K1 = K + 1;
+    const int k = blockIdx.x * 32 + kx, n = blockIdx.y * 8 + ny;
     const size_t plane = (size_t)N * K1;
-    float ag = 0.f, ab = 0.f;
-    float gk = (k < K) ? gamma[k] : 0.f, bk = (k < K) ? beta[k] : 0.f;
-    for (int n = ny; n < N; n += 8) {
-        float dbn = 0.f, g = 0.f;
-        for (int s = 0; s < S; ++s) dbn += part[s * plane + (size_t)n * K1 + K];
-        if (k < K) {
-            for (int s = 0; s < S; ++s) g += part[s * plane + (size_t)n * K1 + k];
-            float wv = W[(size_t)n * K + k];
-            dW[(size_t)n * K + k] = fmaf(gk, g, bk * dbn);
-            ag = fmaf(wv, g, ag);
-            ab = fmaf(wv, dbn, ab);
+    float g = 0.f, dbn = 0.f;
+    if (n < N) {
+        const float* pn = part + (size_t)n * K1;
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+        int s = 0;
+        for (; s + 3 < S; s += 4) {
+            d0 += pn[(size_t)s * plane + K];
+            d1 += pn[(size_t)(s + 1) * plane + K];
+            d2 += pn[(size_t)(s + 2) * plane + K];
+            d3 += pn[(size_t)(s + 3) * plane + K];
         }
-        if (blockIdx.x == 0 && kx == 0) db[n] = dbn;
+        for (; s < S; ++s) d0 += pn[(size_t)s * plane + K];
+        dbn = (d0 + d1) + (d2 + d3);
+        if (k < K) {
+            float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+            s = 0;
+            for (; s + 3 < S; s += 4) {
+                g0 += pn[(size_t)s * plane + k];
+                g1 += pn[(size_t)(s + 1) * plane + k];
+                g2 += pn[(size_t)(s + 2) * plane + k];
+                g3 += pn[(size_t)(s + 3) * plane + k];
+            }
+            for (; s < S; ++s) g0 += pn[(size_t)s * plane + k];
+            g = (g0 + g1) + (g2 + g3);
+        }
     }
+    float ag = 0.f, ab = 0.f;
+    if (n < N && k < K) {
+        const float wv = W[(size_t)n * K + k];
+        dW[(size_t)n * K + k] = fmaf(gamma[k], g, beta[k] * dbn);
+        ag = wv * g;
+        ab = wv * dbn;
+    }
+    if (n < N && blockIdx.x == 0 && kx == 0) db[n] = dbn;
     sg[ny][kx] = ag;
     sb[ny][kx] = ab;
     __syncthreads();
@@ -390,8 +493,28 @@ __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __rest
             tg += sg[q][kx];
             tb += sb[q][kx];
         }
-        dgamma[k] = tg;
-        dbeta[k] = tb;
+        scratch[((size_t)blockIdx.y * 2 + 0) * K + k] = tg;
+        scratch[((size_t)blockIdx.y * 2 + 1) * K + k] = tb;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(&counters[blockIdx.x], 1u);
+        is_last = (t == gridDim.y - 1);
+        if (is_last) counters[blockIdx.x] = 0u;
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        if (ny == 0 && k < K) {
+            float tg = 0.f, tb = 0.f;
+            for (unsigned int q = 0; q < gridDim.y; ++q) {
+                tg += scratch[((size_t)q * 2 + 0) * K + k];
+                tb += scratch[((size_t)q * 2 + 1) * K + k];
+            }
+            dgamma[k] = tg;
+            dbeta[k] = tb;
+        }
     }
 }
 
@@ -412,6 +535,12 @@ static void launch_gemm(const GemmArgs& a, int splits, cudaStream_t st) {
 }  // namespace ub200
 
 using namespace ub200;
+
+extern "C" UB200_API int ub200_set_tc_mode(int mode) {
+    const int old = tc_mode();
+    g_tc_mode = mode & 7;
+    return old;
+}
 
 extern "C" UB200_API size_t ub200_mlp_param_count(int F, const int* hidden, int n_hidden) {
     LayerDims d;
@@ -443,6 +572,7 @@ extern "C" UB200_API int ub200_mlp_forward(const float* feats, const int32_t* do
     const int row_blocks = (M + 7) / 8;
     const float* X = feats;
     const int32_t* idx = docid;
+    if (int rc = prep_tc_weights(d, w, params, training, st)) return rc;
     for (int j = 0; j < d.n_layers; ++j) {
         const int K = d.K[j], N = d.N[j];
         const float* g = params + d.off_g[j];
@@ -455,12 +585,20 @@ extern "C" UB200_API int ub200_mlp_forward(const float* feats, const int32_t* do
         } else {
             row_stats_kernel<<<row_blocks, 256, 0, st>>>(X, idx, M, K, w.stats[j]);
             UB_LAUNCH_CHECK("row_stats_kernel");
-            GemmArgs a{};
-            a.I = M; a.J = N; a.C = K;
-            a.X = X; a.docid = idx; a.stats = w.stats[j]; a.gamma = g; a.beta = bt; a.W = W; a.bias = c;
-            a.out = w.Y[j]; a.K = K; a.N = N; a.act = 1;
-            launch_gemm<MODE_FWD>(a, 1, st);
-            UB_LAUNCH_CHECK("gemm_kernel<FWD>");
+            if (use_tc(j, K, N, TC_FWD)) {
+                tc::TcArgs t{};
+                t.M = M; t.K = K; t.N = N; t.X = X; t.docid = idx; t.stats = w.stats[j]; t.gamma = g; t.beta = bt;
+                t.Bhi = w.wf_hi[j]; t.Blo = w.wf_lo[j]; t.ldb = round_up(K, 32); t.bias = c;
+                t.out = w.Y[j]; t.ldo = N;
+                if (int rc = tc_forward_layer(t, st)) return rc;
+            } else {
+                GemmArgs a{};
+                a.I = M; a.J = N; a.C = K;
+                a.X = X; a.docid = idx; a.stats = w.stats[j]; a.gamma = g; a.beta = bt; a.W = W; a.bias = c;
+                a.out = w.Y[j]; a.K = K; a.N = N; a.act = 1;
+                launch_gemm<MODE_FWD>(a, 1, st);
+                UB_LAUNCH_CHECK("gemm_kernel<FWD>");
+            }
             X = w.Y[j];
             idx = nullptr;
         }
@@ -499,10 +637,10 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
                                                     params + d.off_w[j], dscores, L, B, (j == 0) ? nullptr : w.dz,
                                                     w.partials);
         UB_LAUNCH_CHECK("final_bwd_kernel");
-        wgrad_finalize_kernel<<<(K + 31) / 32, 256, 0, st>>>(w.partials, blocks, 1, K, params + d.off_w[j],
-                                                             params + d.off_g[j], params + d.off_b[j],
-                                                             grads + d.off_w[j], grads + d.off_c[j],
-                                                             grads + d.off_g[j], grads + d.off_b[j]);
+        wgrad_finalize_kernel<<<dim3((K + 31) / 32, 1), 256, 0, st>>>(
+            w.partials, blocks, 1, K, K + 1, params + d.off_w[j], params + d.off_g[j], params + d.off_b[j],
+            grads + d.off_w[j], grads + d.off_c[j], grads + d.off_g[j], grads + d.off_b[j], w.fin_scratch,
+            w.fin_counters);
         UB_LAUNCH_CHECK("wgrad_finalize_kernel(final)");
     }
     // hidden layers, last to first; w.dz holds dZ_j [M, N_j]
@@ -513,27 +651,48 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
         const float* g = params + d.off_g[j];
         const float* bt = params + d.off_b[j];
         const float* W = params + d.off_w[j];
-        // weight gradient GEMM: G[n, k] (k == K -> db)
-        const int S = wgrad_splits(M, N, K + 1);
-        int rps = (M + S - 1) / S;
-        rps = (rps + 15) / 16 * 16;
-        GemmArgs a{};
-        a.I = N; a.J = K + 1; a.C = M;
-        a.X = X; a.docid = idx; a.stats = w.stats[j]; a.dZ = w.dz; a.out = w.partials;
-        a.K = K; a.N = N; a.rows_per_split = rps;
-        const int S_eff = (M + rps - 1) / rps;
-        launch_gemm<MODE_WGRAD>(a, S_eff, st);
-        UB_LAUNCH_CHECK("gemm_kernel<WGRAD>");
-        wgrad_finalize_kernel<<<(K + 31) / 32, 256, 0, st>>>(w.partials, S_eff, N, K, W, g, bt, grads + d.off_w[j],
-                                                             grads + d.off_c[j], grads + d.off_g[j],
-                                                             grads + d.off_b[j]);
+        // weight gradient GEMM: G[n, k] (k == K -> db), split over row chunks
+        int S_eff, ldp;
+        if (use_tc(j, K, N, TC_WGRAD)) {
+            const int S = tc_wgrad_splits(M, N, K);
+            int rps = (M + S - 1) / S;
+            rps = (rps + 31) / 32 * 32;
+            S_eff = (M + rps - 1) / rps;
+            ldp = round_up(K + 1, 4);
+            tc::TcArgs t{};
+            t.M = M; t.K = K; t.N = N; t.X = X; t.docid = idx; t.stats = w.stats[j]; t.dZ = w.dz;
+            t.out = w.partials; t.ldo = ldp; t.rows_per_split = rps;
+            if (int rc = tc_wgrad_layer(t, S_eff, st)) return rc;
+        } else {
+            const int S = wgrad_splits(M, N, K + 1);
+            int rps = (M + S - 1) / S;
+            rps = (rps + 15) / 16 * 16;
+            S_eff = (M + rps - 1) / rps;
+            ldp = K + 1;
+            GemmArgs a{};
+            a.I = N; a.J = K + 1; a.C = M;
+            a.X = X; a.docid = idx; a.stats = w.stats[j]; a.dZ = w.dz; a.out = w.partials;
+            a.K = K; a.N = N; a.rows_per_split = rps;
+            launch_gemm<MODE_WGRAD>(a, S_eff, st);
+            UB_LAUNCH_CHECK("gemm_kernel<WGRAD>");
+        }
+        wgrad_finalize_kernel<<<dim3((K + 31) / 32, (N + 7) / 8), 256, 0, st>>>(
+            w.partials, S_eff, N, K, ldp, W, g, bt, grads + d.off_w[j], grads + d.off_c[j], grads + d.off_g[j],
+            grads + d.off_b[j], w.fin_scratch, w.fin_counters);
         UB_LAUNCH_CHECK("wgrad_finalize_kernel");
         if (j > 0) {
-            GemmArgs b{};
-            b.I = M; b.J = K; b.C = N;
-            b.dZ = w.dz; b.W = W; b.gamma = g; b.out = w.dxh; b.K = K; b.N = N;
-            launch_gemm<MODE_DGRAD>(b, 1, st);
-            UB_LAUNCH_CHECK("gemm_kernel<DGRAD>");
+            if (use_tc(j, K, N, TC_DGRAD)) {
+                tc::TcArgs t{};
+                t.M = M; t.K = K; t.N = N; t.dZ = w.dz; t.Bhi = w.wd_hi[j]; t.Blo = w.wd_lo[j];
+                t.ldb = round_up(N, 32); t.out = w.dxh; t.ldo = K;
+                if (int rc = tc_dgrad_layer(t, st)) return rc;
+            } else {
+                GemmArgs b{};
+                b.I = M; b.J = K; b.C = N;
+                b.dZ = w.dz; b.W = W; b.gamma = g; b.out = w.dxh; b.K = K; b.N = N;
+                launch_gemm<MODE_DGRAD>(b, 1, st);
+                UB_LAUNCH_CHECK("gemm_kernel<DGRAD>");
+            }
             ln_bwd_elu_kernel<<<row_blocks, 256, 0, st>>>(w.dxh, X, w.stats[j], M, K, w.dz);
             UB_LAUNCH_CHECK("ln_bwd_elu_kernel");
         }

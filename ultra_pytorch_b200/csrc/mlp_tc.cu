@@ -1,0 +1,390 @@
+// K1 on the 5th-generation tensor cores (tcgen05 + TMEM), fp32-accurate through 3xTF32 error compensation.
+//
+// Every dense contraction of the DNN ranker (forward  Y = LN(X) W^T,  data gradient  dXhat = dZ (W.gamma),
+// weight gradient  G = dZ^T [xhat | 1]) runs through ONE warp-specialised kernel template:
+//
+//   warps 0-7 : operand producers. They read the fp32 activations / weights from global memory (L2), apply the
+//               fused prologue (LayerNorm of the A operand for the forward pass, normalisation for the weight
+//               gradient), split every value into a TF32-exact high part and an fp32 remainder
+//               (x = hi + lo) and store both into 128B-swizzled shared-memory tiles of a multi-stage ring.
+//   warp 8    : one elected thread issues  hi*hi + lo*hi + hi*lo  as three tcgen05.mma.kind::tf32 per K=8 step,
+//               accumulating in fp32 in tensor memory; tcgen05.commit releases the ring slots / signals the epilogue.
+//   warps 0-3 : epilogue: tcgen05.ld of the accumulator tile (thread = row), bias + ELU (forward) and the store.
+//
+// The dropped lo*lo term is O(2^-22) relative, the same order as fp32 rounding, so the results stay
+// inside the 1e-5 parity bound where plain TF32 (2^-11) does not.
+#include "common.cuh"
+#include "mlp_tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace ub200 {
+namespace tc {
+
+enum { KIND_FWD = 0, KIND_DGRAD = 1, KIND_WGRAD = 2 };
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;                 // fp32 elements per 128-byte swizzle row
+constexpr int NPROD = 256;                  // producer threads (warps 0-7)
+constexpr int NTHREADS = NPROD + 32;        // + the MMA warp
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;   // 16 KB
+
+__host__ __device__ constexpr int stage_bytes(int block_n) { return 2 * A_TILE_BYTES + 2 * block_n * BLOCK_K * 4; }
+__host__ __device__ constexpr int num_stages(int block_n) {
+    return (220 * 1024) / stage_bytes(block_n) > 4 ? 4 : (220 * 1024) / stage_bytes(block_n);
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st_split(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, float4 v) {
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x);
+    split_tf32(v.y, h.y, l.y);
+    split_tf32(v.z, h.z, l.z);
+    split_tf32(v.w, h.w, l.w);
+    *reinterpret_cast<float4*>(hi_base + off) = h;
+    *reinterpret_cast<float4*>(lo_base + off) = l;
+}
+
+template <int KIND, int BLOCK_N>
+__global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
+    constexpr int STAGES = num_stages(BLOCK_N);
+    constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 4;
+    constexpr int STAGE_BYTES = stage_bytes(BLOCK_N);
+    constexpr int NB = BLOCK_N / 32;                         // 32-column blocks of the B operand (MN-major case)
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int i0 = blockIdx.x * BLOCK_M;        // first row of the MMA "M" dimension (m, or n for WGRAD)
+    const int j0 = blockIdx.y * BLOCK_N;        // first row of the MMA "N" dimension (n / k / k)
+    int c_begin = 0, c_end;
+    if (KIND == KIND_FWD) c_end = a.K;
+    else if (KIND == KIND_DGRAD) c_end = a.N;
+    else {
+        c_begin = blockIdx.z * a.rows_per_split;
+        c_end = min(a.M, c_begin + a.rows_per_split);
+    }
+    const int n_chunks = (c_end - c_begin + BLOCK_K - 1) / BLOCK_K;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], NPROD);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_mbar_init();
+    }
+    // two fp32 accumulators in tensor memory: [0, BLOCK_N) main = hi*hi, [BLOCK_N, 2*BLOCK_N) correction = lo*hi + hi*lo.
+    // The tensor core truncates when it accumulates, a one-sided error proportional to the accumulator magnitude and
+    // the number of accumulation steps; keeping the 2^-12-times-smaller correction terms out of the main accumulator
+    // cuts its accumulation count by 3 (measured at K = 700: 1.1e-5 -> see DESIGN.md).
+    if (warp == 8) tmem_alloc(tmem_slot, 2 * BLOCK_N);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        // =========================== producers ===========================
+        for (int it = 0; it < n_chunks; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+            mbar_wait(&empty_bar[s], ph ^ 1u);
+            uint8_t* a_hi = smem + s * STAGE_BYTES;
+            uint8_t* a_lo = a_hi + A_TILE_BYTES;
+            uint8_t* b_hi = a_lo + A_TILE_BYTES;
+            uint8_t* b_lo = b_hi + B_TILE_BYTES;
+            const int c0 = c_begin + it * BLOCK_K;
+            if (KIND != KIND_WGRAD) {
+                // ---- A, K-major: 128 rows (m) x 8 chunks of 4 contraction elements ----
+#pragma unroll
+                for (int e = 0; e < BLOCK_M * 8 / NPROD; ++e) {
+                    const int idx = tid + e * NPROD;
+                    const int r = idx >> 3, c = idx & 7;
+                    const int m = i0 + r, cc = c0 + c * 4;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (m < a.M && cc < c_end) {
+                        if (KIND == KIND_FWD) {
+                            const float* x = a.X + (size_t)(a.docid ? a.docid[m] : m) * a.K;
+                            const float4 xv = ld4(x + cc), g = ld4(a.gamma + cc), b = ld4(a.beta + cc);
+                            const float2 st = a.stats[m];
+                            v.x = (xv.x - st.x) * st.y * g.x + b.x;
+                            v.y = (xv.y - st.x) * st.y * g.y + b.y;
+                            v.z = (xv.z - st.x) * st.y * g.z + b.z;
+                            v.w = (xv.w - st.x) * st.y * g.w + b.w;
+                        } else {
+                            v = ld4(a.dZ + (size_t)m * a.N + cc);
+                        }
+                    }
+                    st_split(a_hi, a_lo, swz128(r, c), v);
+                }
+                // ---- B, K-major: BLOCK_N rows x 8 chunks, already split + zero padded in global memory ----
+#pragma unroll
+                for (int e = 0; e < BLOCK_N * 8 / NPROD; ++e) {
+                    const int idx = tid + e * NPROD;
+                    const int r = idx >> 3, c = idx & 7;
+                    const size_t g = (size_t)(j0 + r) * a.ldb + c0 + c * 4;
+                    const uint32_t off = swz128(r, c);
+                    *reinterpret_cast<float4*>(b_hi + off) = ld4(a.Bhi + g);
+                    *reinterpret_cast<float4*>(b_lo + off) = ld4(a.Blo + g);
+                }
+            } else {
+                // ---- A, MN-major: dZ^T. 32 contraction rows (m) x 4 blocks of 32 n x 8 chunks ----
+#pragma unroll
+                for (int e = 0; e < 32 * 4 * 8 / NPROD; ++e) {
+                    const int idx = tid + e * NPROD;
+                    const int c = idx & 7, blk = (idx >> 3) & 3, ml = idx >> 5;
+                    const int m = c0 + ml, n = i0 + blk * 32 + c * 4;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (m < c_end && n < a.N) v = ld4(a.dZ + (size_t)m * a.N + n);
+                    st_split(a_hi, a_lo, swz_mn32(ml, blk, c, 4), v);
+                }
+                // ---- B, MN-major: [xhat | 1]^T. 32 contraction rows (m) x NB blocks of 32 k x 8 chunks ----
+#pragma unroll
+                for (int e = 0; e < 32 * NB * 8 / NPROD; ++e) {
+                    const int idx = tid + e * NPROD;
+                    const int c = idx & 7, blk = (idx >> 3) % NB, ml = idx / (8 * NB);
+                    const int m = c0 + ml, kk = j0 + blk * 32 + c * 4;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (m < c_end && kk <= a.K) {
+                        const float* x = a.X + (size_t)(a.docid ? a.docid[m] : m) * a.K;
+                        const float2 st = a.stats[m];
+                        if (kk + 3 < a.K) {
+                            const float4 xv = ld4(x + kk);
+                            v.x = (xv.x - st.x) * st.y;
+                            v.y = (xv.y - st.x) * st.y;
+                            v.z = (xv.z - st.x) * st.y;
+                            v.w = (xv.w - st.x) * st.y;
+                        } else {
+                            float t[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int k = kk + q;
+                                t[q] = (k < a.K) ? (x[k] - st.x) * st.y : (k == a.K ? 1.f : 0.f);   // ones column -> db
+                            }
+                            v = make_float4(t[0], t[1], t[2], t[3]);
+                        }
+                    }
+                    st_split(b_hi, b_lo, swz_mn32(ml, blk, c, NB), v);
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(&full_bar[s]);
+        }
+    } else if (lane == 0) {
+        // =========================== MMA issuer (one thread) ===========================
+        constexpr uint32_t idesc =
+            make_idesc_tf32(BLOCK_N, KIND == KIND_WGRAD ? 1 : 0, KIND == KIND_WGRAD ? 1 : 0);
+        for (int it = 0; it < n_chunks; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
+            const uint32_t a_lo = a_hi + A_TILE_BYTES;
+            const uint32_t b_hi = a_lo + A_TILE_BYTES;
+            const uint32_t b_lo = b_hi + B_TILE_BYTES;
+            const int rem = c_end - (c_begin + it * BLOCK_K);
+            const int nk8 = rem >= BLOCK_K ? 4 : (rem + 7) / 8;
+            for (int k8 = 0; k8 < nk8; ++k8) {
+                uint64_t da_hi, da_lo, db_hi, db_lo;
+                if (KIND != KIND_WGRAD) {
+                    // K-major, 128B swizzle: 8-row groups 1024 B apart; one K=8 step = 32 bytes along the row
+                    da_hi = make_smem_desc(a_hi + k8 * 32, 16, 1024);
+                    da_lo = make_smem_desc(a_lo + k8 * 32, 16, 1024);
+                    db_hi = make_smem_desc(b_hi + k8 * 32, 16, 1024);
+                    db_lo = make_smem_desc(b_lo + k8 * 32, 16, 1024);
+                } else {
+                    // MN-major tf32: 128B swizzle with 32B base; 32-element MN blocks 512 B apart (LBO), 4-row K groups
+                    // nblk*512 B apart (SBO); one K=8 step = two K groups
+                    da_hi = make_smem_desc(a_hi + k8 * 4 * 1024, 512, 4 * 512, kSwizzle128B_Base32B);
+                    da_lo = make_smem_desc(a_lo + k8 * 4 * 1024, 512, 4 * 512, kSwizzle128B_Base32B);
+                    db_hi = make_smem_desc(b_hi + k8 * NB * 1024, 512, NB * 512, kSwizzle128B_Base32B);
+                    db_lo = make_smem_desc(b_lo + k8 * NB * 1024, 512, NB * 512, kSwizzle128B_Base32B);
+                }
+                const uint32_t acc = (it | k8) != 0 ? 1u : 0u;
+                mma_tf32(tmem_base + BLOCK_N, da_lo, db_hi, idesc, acc);
+                mma_tf32(tmem_base + BLOCK_N, da_hi, db_lo, idesc, 1u);
+                mma_tf32(tmem_base, da_hi, db_hi, idesc, acc);
+            }
+            mma_commit(&empty_bar[s]);       // ring slot reusable once these MMAs have read it
+        }
+        mma_commit(accum_bar);               // accumulator complete
+    }
+
+    __syncwarp();
+    if (warp < 4) {
+        // =========================== epilogue ===========================
+        mbar_wait(accum_bar, 0);
+        __syncwarp();
+        tc_fence_after();
+        const int row = i0 + warp * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        int row_limit, col_limit;
+        float* dst;
+        if (KIND == KIND_FWD) {
+            row_limit = a.M; col_limit = a.N;
+            dst = a.out + (size_t)row * a.ldo;
+        } else if (KIND == KIND_DGRAD) {
+            row_limit = a.M; col_limit = a.K;
+            dst = a.out + (size_t)row * a.ldo;
+        } else {
+            row_limit = a.N; col_limit = a.ldo;
+            dst = a.out + ((size_t)blockIdx.z * a.N + row) * a.ldo;
+        }
+#pragma unroll 1
+        for (int cb = 0; cb < BLOCK_N / 32; ++cb) {
+            float v[32], corr[32];
+            tmem_ld32(taddr + cb * 32, v);
+            tmem_ld32(taddr + BLOCK_N + cb * 32, corr);
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] += corr[q];
+            const int col0 = j0 + cb * 32;
+            if (row < row_limit) {
+#pragma unroll
+                for (int q = 0; q < 32; q += 4) {
+                    if (col0 + q < col_limit) {       // limits are multiples of 4
+                        float4 o = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+                        if (KIND == KIND_FWD) {
+                            const float4 b = ld4(a.bias + col0 + q);
+                            o.x = elu_f(o.x + b.x);
+                            o.y = elu_f(o.y + b.y);
+                            o.z = elu_f(o.z + b.z);
+                            o.w = elu_f(o.w + b.w);
+                        }
+                        *reinterpret_cast<float4*>(dst + col0 + q) = o;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * BLOCK_N);
+    }
+}
+
+// Pre-split the weights once per step: forward operand Wf[n][Kpad] = W[n][k] and data-gradient operand
+// Wd[k][Npad] = W[n][k] * gamma[k] (transposed), each as (hi, lo) with zero padding to a multiple of 32.
+__global__ void __launch_bounds__(256) prep_weights_kernel(PrepTable t) {
+    const int j = blockIdx.y;
+    const int K = t.K[j], N = t.N[j], Kpad = t.Kpad[j], Npad = t.Npad[j];
+    const float* W = t.W[j];
+    const size_t nf = (size_t)N * Kpad;
+    const size_t nd = t.wd_hi[j] ? (size_t)K * Npad : 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nf + nd; i += (size_t)gridDim.x * blockDim.x) {
+        float w, *hi, *lo;
+        size_t o;
+        if (i < nf) {
+            const int n = (int)(i / Kpad), k = (int)(i % Kpad);
+            w = k < K ? W[(size_t)n * K + k] : 0.f;
+            hi = t.wf_hi[j]; lo = t.wf_lo[j]; o = i;
+        } else {
+            o = i - nf;
+            const int k = (int)(o / Npad), n = (int)(o % Npad);
+            w = n < N ? W[(size_t)n * K + k] * t.gamma[j][k] : 0.f;
+            hi = t.wd_hi[j]; lo = t.wd_lo[j];
+        }
+        float h, l;
+        split_tf32(w, h, l);
+        hi[o] = h;
+        lo[o] = l;
+    }
+}
+
+template <int KIND, int BLOCK_N>
+static cudaError_t launch_one(const TcArgs& a, dim3 grid, cudaStream_t st) {
+    constexpr int smem = num_stages(BLOCK_N) * stage_bytes(BLOCK_N) + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<KIND, BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    tc_gemm_kernel<KIND, BLOCK_N><<<grid, NTHREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int KIND>
+static cudaError_t launch_kind(const TcArgs& a, int block_n, dim3 grid, cudaStream_t st) {
+    if (block_n == 64) return launch_one<KIND, 64>(a, grid, st);
+    if (block_n == 128) return launch_one<KIND, 128>(a, grid, st);
+    return launch_one<KIND, 256>(a, grid, st);
+}
+
+// widest tile (dividing `cols`, a multiple of 64) that still gives at least one wave of CTAs
+static int pick_block_n(int cols, int row_tiles) {
+    const int cands[3] = {256, 128, 64};
+    for (int i = 0; i < 3; ++i) {
+        const int bn = cands[i];
+        if (cols % bn != 0) continue;
+        if (row_tiles * (cols / bn) >= kNumSMs) return bn;
+    }
+    return 64;
+}
+
+}  // namespace tc
+
+// ---- entry points used by mlp.cu -------------------------------------------------------------------------
+bool tc_layer_ok(int j, int K, int N) {
+    return (K % 4 == 0) && (N % 64 == 0) && (j == 0 || K % 64 == 0);
+}
+
+int tc_prep(const tc::PrepTable& t, int max_elems, cudaStream_t st) {
+    int bx = (max_elems + 256 * 4 - 1) / (256 * 4);
+    if (bx > 4 * kNumSMs) bx = 4 * kNumSMs;
+    if (bx < 1) bx = 1;
+    tc::prep_weights_kernel<<<dim3(bx, t.n), 256, 0, st>>>(t);
+    UB_LAUNCH_CHECK("prep_weights_kernel");
+    return 0;
+}
+
+int tc_forward_layer(const tc::TcArgs& a, cudaStream_t st) {
+    const int row_tiles = (a.M + tc::BLOCK_M - 1) / tc::BLOCK_M;
+    const int bn = tc::pick_block_n(a.N, row_tiles);
+    cudaError_t e = tc::launch_kind<tc::KIND_FWD>(a, bn, dim3(row_tiles, a.N / bn, 1), st);
+    count_launch();
+    UB_CHECK(e == cudaSuccess, 100, "tc_gemm_kernel<FWD> launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int tc_dgrad_layer(const tc::TcArgs& a, cudaStream_t st) {
+    const int row_tiles = (a.M + tc::BLOCK_M - 1) / tc::BLOCK_M;
+    const int bn = tc::pick_block_n(a.K, row_tiles);
+    cudaError_t e = tc::launch_kind<tc::KIND_DGRAD>(a, bn, dim3(row_tiles, a.K / bn, 1), st);
+    count_launch();
+    UB_CHECK(e == cudaSuccess, 100, "tc_gemm_kernel<DGRAD> launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+static int wgrad_block_n(int cols) { return cols > 128 ? 256 : (cols > 64 ? 128 : 64); }
+
+// split count of the weight-gradient contraction over the M rows (each split >= 256 rows)
+int tc_wgrad_splits(int M, int N, int K) {
+    const int cols = K + 1, bn = wgrad_block_n(cols);
+    const int tiles = ((N + tc::BLOCK_M - 1) / tc::BLOCK_M) * ((cols + bn - 1) / bn);
+    int s = (2 * kNumSMs + tiles - 1) / tiles;
+    const int max_s = (M + 255) / 256;
+    if (s > max_s) s = max_s;
+    return s < 1 ? 1 : s;
+}
+
+int tc_wgrad_layer(const tc::TcArgs& a, int splits, cudaStream_t st) {
+    const int row_tiles = (a.N + tc::BLOCK_M - 1) / tc::BLOCK_M;
+    const int cols = a.K + 1;
+    const int bn = wgrad_block_n(cols);
+    cudaError_t e = tc::launch_kind<tc::KIND_WGRAD>(a, bn, dim3(row_tiles, (cols + bn - 1) / bn, splits), st);
+    count_launch();
+    UB_CHECK(e == cudaSuccess, 100, "tc_gemm_kernel<WGRAD> launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+}  // namespace ub200

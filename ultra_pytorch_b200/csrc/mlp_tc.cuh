@@ -1,0 +1,41 @@
+// Host-side entry points of the tensor-core (tcgen05) GEMM path, shared between mlp.cu and mlp_tc.cu.
+#pragma once
+#include "common.cuh"
+
+namespace ub200 {
+namespace tc {
+struct TcArgs {
+    int M, K, N;
+    const float* X;
+    const int32_t* docid;
+    const float2* stats;
+    const float* gamma;
+    const float* beta;
+    const float* dZ;
+    const float* Bhi;
+    const float* Blo;
+    int ldb;
+    const float* bias;
+    float* out;
+    int ldo;
+    int rows_per_split;
+};
+struct PrepTable {
+    int n;
+    const float* W[UB200_MAX_LAYERS];
+    const float* gamma[UB200_MAX_LAYERS];
+    float* wf_hi[UB200_MAX_LAYERS];
+    float* wf_lo[UB200_MAX_LAYERS];
+    float* wd_hi[UB200_MAX_LAYERS];   // nullptr: not needed
+    float* wd_lo[UB200_MAX_LAYERS];
+    int K[UB200_MAX_LAYERS], N[UB200_MAX_LAYERS], Kpad[UB200_MAX_LAYERS], Npad[UB200_MAX_LAYERS];
+};
+}  // namespace tc
+
+bool tc_layer_ok(int j, int K, int N);
+int tc_prep(const tc::PrepTable& t, int max_elems, cudaStream_t st);
+int tc_forward_layer(const tc::TcArgs& a, cudaStream_t st);
+int tc_dgrad_layer(const tc::TcArgs& a, cudaStream_t st);
+int tc_wgrad_splits(int M, int N, int K);
+int tc_wgrad_layer(const tc::TcArgs& a, int splits, cudaStream_t st);
+}  // namespace ub200
