@@ -518,6 +518,42 @@ __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __rest
     }
 }
 
+// N == 1 variant for the final layer: the S per-block column partials [S][K+1] of final_bwd_kernel are reduced with
+// the 8 thread rows splitting S (fixed assignment + fixed-order combine => deterministic).
+__global__ void __launch_bounds__(256) final_finalize_kernel(const float* __restrict__ part, int S, int K,
+                                                              const float* __restrict__ w,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float* __restrict__ dW,
+                                                              float* __restrict__ db, float* __restrict__ dgamma,
+                                                              float* __restrict__ dbeta) {
+    __shared__ float sg[8][33], sd[8];
+    const int kx = threadIdx.x & 31, ny = threadIdx.x >> 5;
+    const int k = blockIdx.x * 32 + kx;
+    const int K1 = K + 1;
+    float g = 0.f, d = 0.f;
+    for (int s = ny; s < S; s += 8) {
+        if (k < K) g += part[(size_t)s * K1 + k];
+        if (kx == 0) d += part[(size_t)s * K1 + K];
+    }
+    sg[ny][kx] = g;
+    if (kx == 0) sd[ny] = d;
+    __syncthreads();
+    if (ny == 0) {
+        float G = 0.f, dbn = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            G += sg[q][kx];
+            dbn += sd[q];
+        }
+        if (k < K) {
+            dW[k] = fmaf(gamma[k], G, beta[k] * dbn);
+            dgamma[k] = w[k] * G;
+            dbeta[k] = w[k] * dbn;
+        }
+        if (blockIdx.x == 0 && kx == 0) db[0] = dbn;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
@@ -588,7 +624,7 @@ extern "C" UB200_API int ub200_mlp_forward(const float* feats, const int32_t* do
             if (use_tc(j, K, N, TC_FWD)) {
                 tc::TcArgs t{};
                 t.M = M; t.K = K; t.N = N; t.X = X; t.docid = idx; t.stats = w.stats[j]; t.gamma = g; t.beta = bt;
-                t.Bhi = w.wf_hi[j]; t.Blo = w.wf_lo[j]; t.ldb = round_up(K, 32); t.bias = c;
+                t.Bhi = w.wf_hi[j]; t.Blo = w.wf_lo[j]; t.ldb = N; t.bias = c;
                 t.out = w.Y[j]; t.ldo = N;
                 if (int rc = tc_forward_layer(t, st)) return rc;
             } else {
@@ -637,10 +673,10 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
                                                     params + d.off_w[j], dscores, L, B, (j == 0) ? nullptr : w.dz,
                                                     w.partials);
         UB_LAUNCH_CHECK("final_bwd_kernel");
-        wgrad_finalize_kernel<<<dim3((K + 31) / 32, 1), 256, 0, st>>>(
-            w.partials, blocks, 1, K, K + 1, params + d.off_w[j], params + d.off_g[j], params + d.off_b[j],
-            grads + d.off_w[j], grads + d.off_c[j], grads + d.off_g[j], grads + d.off_b[j], w.fin_scratch,
-            w.fin_counters);
+        final_finalize_kernel<<<(K + 31) / 32, 256, 0, st>>>(w.partials, blocks, K, params + d.off_w[j],
+                                                             params + d.off_g[j], params + d.off_b[j],
+                                                             grads + d.off_w[j], grads + d.off_c[j],
+                                                             grads + d.off_g[j], grads + d.off_b[j]);
         UB_LAUNCH_CHECK("wgrad_finalize_kernel(final)");
     }
     // hidden layers, last to first; w.dz holds dZ_j [M, N_j]
@@ -684,7 +720,7 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
             if (use_tc(j, K, N, TC_DGRAD)) {
                 tc::TcArgs t{};
                 t.M = M; t.K = K; t.N = N; t.dZ = w.dz; t.Bhi = w.wd_hi[j]; t.Blo = w.wd_lo[j];
-                t.ldb = round_up(N, 32); t.out = w.dxh; t.ldo = K;
+                t.ldb = K; t.out = w.dxh; t.ldo = K;
                 if (int rc = tc_dgrad_layer(t, st)) return rc;
             } else {
                 GemmArgs b{};

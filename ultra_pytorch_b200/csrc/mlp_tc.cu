@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], NPROD);
+            mbar_init(&full_bar[s], KIND == KIND_WGRAD ? NPROD : NPROD + 1);
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(accum_bar, 1);
@@ -90,90 +90,143 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
 
     if (warp < 8) {
         // =========================== producers ===========================
-        for (int it = 0; it < n_chunks; ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-            mbar_wait(&empty_bar[s], ph ^ 1u);
-            uint8_t* a_hi = smem + s * STAGE_BYTES;
-            uint8_t* a_lo = a_hi + A_TILE_BYTES;
-            uint8_t* b_hi = a_lo + A_TILE_BYTES;
-            uint8_t* b_lo = b_hi + B_TILE_BYTES;
-            const int c0 = c_begin + it * BLOCK_K;
-            if (KIND != KIND_WGRAD) {
-                // ---- A, K-major: 128 rows (m) x 8 chunks of 4 contraction elements ----
+        if (KIND != KIND_WGRAD) {
+            // A, K-major: 128 rows (m) x 8 chunks of 4 contraction elements; thread -> chunk c = tid & 7 of the four
+            // rows (tid >> 3) + 32 e.  Row pointers / LayerNorm statistics are loop invariant; the global loads of
+            // chunk it+1 are issued before chunk it is stored (register double buffering), so the L2 latency overlaps
+            // the MMAs.  B (pre-split, pre-swizzled weight images) arrives through the TMA engine (cp.async.bulk).
+            constexpr int RPT = BLOCK_M * 8 / NPROD;    // rows per thread = 4
+            const int c = tid & 7;
+            const float* xrow[RPT];
+            float2 st[RPT];
 #pragma unroll
-                for (int e = 0; e < BLOCK_M * 8 / NPROD; ++e) {
-                    const int idx = tid + e * NPROD;
-                    const int r = idx >> 3, c = idx & 7;
-                    const int m = i0 + r, cc = c0 + c * 4;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (m < a.M && cc < c_end) {
-                        if (KIND == KIND_FWD) {
-                            const float* x = a.X + (size_t)(a.docid ? a.docid[m] : m) * a.K;
-                            const float4 xv = ld4(x + cc), g = ld4(a.gamma + cc), b = ld4(a.beta + cc);
-                            const float2 st = a.stats[m];
-                            v.x = (xv.x - st.x) * st.y * g.x + b.x;
-                            v.y = (xv.y - st.x) * st.y * g.y + b.y;
-                            v.z = (xv.z - st.x) * st.y * g.z + b.z;
-                            v.w = (xv.w - st.x) * st.y * g.w + b.w;
-                        } else {
-                            v = ld4(a.dZ + (size_t)m * a.N + cc);
-                        }
+            for (int e = 0; e < RPT; ++e) {
+                const int m = i0 + (tid >> 3) + e * 32;
+                xrow[e] = nullptr;
+                st[e] = make_float2(0.f, 1.f);
+                if (m < a.M) {
+                    if (KIND == KIND_FWD) {
+                        xrow[e] = a.X + (size_t)(a.docid ? a.docid[m] : m) * a.K;
+                        st[e] = a.stats[m];
+                    } else {
+                        xrow[e] = a.dZ + (size_t)m * a.N;
                     }
-                    st_split(a_hi, a_lo, swz128(r, c), v);
                 }
-                // ---- B, K-major: BLOCK_N rows x 8 chunks, already split + zero padded in global memory ----
+            }
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 cur[RPT], nxt[RPT], g_cur = zero4, b_cur = zero4, g_nxt = zero4, b_nxt = zero4;
+            auto load_chunk = [&](int it, float4* xv, float4& g, float4& b) {
+                const int cc = c_begin + it * BLOCK_K + c * 4;
+                const bool kv = cc < c_end;
 #pragma unroll
-                for (int e = 0; e < BLOCK_N * 8 / NPROD; ++e) {
-                    const int idx = tid + e * NPROD;
-                    const int r = idx >> 3, c = idx & 7;
-                    const size_t g = (size_t)(j0 + r) * a.ldb + c0 + c * 4;
-                    const uint32_t off = swz128(r, c);
-                    *reinterpret_cast<float4*>(b_hi + off) = ld4(a.Bhi + g);
-                    *reinterpret_cast<float4*>(b_lo + off) = ld4(a.Blo + g);
+                for (int e = 0; e < RPT; ++e) xv[e] = (kv && xrow[e]) ? ld4(xrow[e] + cc) : zero4;
+                if (KIND == KIND_FWD) {
+                    g = kv ? ld4(a.gamma + cc) : zero4;
+                    b = kv ? ld4(a.beta + cc) : zero4;
                 }
-            } else {
+            };
+            if (n_chunks > 0) load_chunk(0, cur, g_cur, b_cur);
+            for (int it = 0; it < n_chunks; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                if (it + 1 < n_chunks) load_chunk(it + 1, nxt, g_nxt, b_nxt);
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                uint8_t* a_hi = smem + s * STAGE_BYTES;
+                uint8_t* a_lo = a_hi + A_TILE_BYTES;
+                uint8_t* b_hi = a_lo + A_TILE_BYTES;
+                uint8_t* b_lo = b_hi + B_TILE_BYTES;
+                if (tid == 0) {
+                    // weight image: [chunk][rows x 128 B, swizzled]; this tile = rows j0 .. j0+BLOCK_N of chunk `it`
+                    const size_t goff = ((size_t)it * a.ldb + j0) * BLOCK_K;
+                    mbar_arrive_expect_tx(&full_bar[s], 2 * B_TILE_BYTES);
+                    bulk_g2s(b_hi, a.Bhi + goff, B_TILE_BYTES, &full_bar[s]);
+                    bulk_g2s(b_lo, a.Blo + goff, B_TILE_BYTES, &full_bar[s]);
+                }
+#pragma unroll
+                for (int e = 0; e < RPT; ++e) {
+                    float4 v = cur[e];
+                    if (KIND == KIND_FWD) {
+                        v.x = (v.x - st[e].x) * st[e].y * g_cur.x + b_cur.x;
+                        v.y = (v.y - st[e].x) * st[e].y * g_cur.y + b_cur.y;
+                        v.z = (v.z - st[e].x) * st[e].y * g_cur.z + b_cur.z;
+                        v.w = (v.w - st[e].x) * st[e].y * g_cur.w + b_cur.w;
+                        if (!xrow[e]) v = zero4;
+                    }
+                    st_split(a_hi, a_lo, swz128((tid >> 3) + e * 32, c), v);
+                }
+                fence_proxy_async();
+                mbar_arrive(&full_bar[s]);
+#pragma unroll
+                for (int e = 0; e < RPT; ++e) cur[e] = nxt[e];
+                g_cur = g_nxt;
+                b_cur = b_nxt;
+            }
+        } else {
+            for (int it = 0; it < n_chunks; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                uint8_t* a_hi = smem + s * STAGE_BYTES;
+                uint8_t* a_lo = a_hi + A_TILE_BYTES;
+                uint8_t* b_hi = a_lo + A_TILE_BYTES;
+                uint8_t* b_lo = b_hi + B_TILE_BYTES;
+                const int c0 = c_begin + it * BLOCK_K;
+                // all global loads of the chunk are issued before the first shared-memory store
+                constexpr int NA = 32 * 4 * 8 / NPROD, NBV = 32 * NB * 8 / NPROD;
+                float4 av[NA], bv[NBV];
+                float2 bst[NBV];
                 // ---- A, MN-major: dZ^T. 32 contraction rows (m) x 4 blocks of 32 n x 8 chunks ----
 #pragma unroll
-                for (int e = 0; e < 32 * 4 * 8 / NPROD; ++e) {
+                for (int e = 0; e < NA; ++e) {
                     const int idx = tid + e * NPROD;
                     const int c = idx & 7, blk = (idx >> 3) & 3, ml = idx >> 5;
                     const int m = c0 + ml, n = i0 + blk * 32 + c * 4;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (m < c_end && n < a.N) v = ld4(a.dZ + (size_t)m * a.N + n);
-                    st_split(a_hi, a_lo, swz_mn32(ml, blk, c, 4), v);
+                    av[e] = (m < c_end && n < a.N) ? ld4(a.dZ + (size_t)m * a.N + n) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 // ---- B, MN-major: [xhat | 1]^T. 32 contraction rows (m) x NB blocks of 32 k x 8 chunks ----
 #pragma unroll
-                for (int e = 0; e < 32 * NB * 8 / NPROD; ++e) {
+                for (int e = 0; e < NBV; ++e) {
                     const int idx = tid + e * NPROD;
                     const int c = idx & 7, blk = (idx >> 3) % NB, ml = idx / (8 * NB);
                     const int m = c0 + ml, kk = j0 + blk * 32 + c * 4;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    bst[e] = make_float2(0.f, 0.f);
                     if (m < c_end && kk <= a.K) {
                         const float* x = a.X + (size_t)(a.docid ? a.docid[m] : m) * a.K;
-                        const float2 st = a.stats[m];
+                        bst[e] = a.stats[m];
                         if (kk + 3 < a.K) {
-                            const float4 xv = ld4(x + kk);
-                            v.x = (xv.x - st.x) * st.y;
-                            v.y = (xv.y - st.x) * st.y;
-                            v.z = (xv.z - st.x) * st.y;
-                            v.w = (xv.w - st.x) * st.y;
+                            v = ld4(x + kk);
                         } else {
+                            // tail of the row: pre-bias so that (v - mean) * rstd gives xhat, 1 (ones column) or 0
                             float t[4];
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 const int k = kk + q;
-                                t[q] = (k < a.K) ? (x[k] - st.x) * st.y : (k == a.K ? 1.f : 0.f);   // ones column -> db
+                                t[q] = (k < a.K) ? x[k] : bst[e].x + (k == a.K ? 1.f / bst[e].y : 0.f);
                             }
                             v = make_float4(t[0], t[1], t[2], t[3]);
                         }
                     }
-                    st_split(b_hi, b_lo, swz_mn32(ml, blk, c, NB), v);
+                    bv[e] = v;
                 }
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+#pragma unroll
+                for (int e = 0; e < NA; ++e) {
+                    const int idx = tid + e * NPROD;
+                    st_split(a_hi, a_lo, swz_mn32(idx >> 5, (idx >> 3) & 3, idx & 7, 4), av[e]);
+                }
+#pragma unroll
+                for (int e = 0; e < NBV; ++e) {
+                    const int idx = tid + e * NPROD;
+                    float4 v = bv[e];
+                    v.x = (v.x - bst[e].x) * bst[e].y;
+                    v.y = (v.y - bst[e].x) * bst[e].y;
+                    v.z = (v.z - bst[e].x) * bst[e].y;
+                    v.w = (v.w - bst[e].x) * bst[e].y;
+                    st_split(b_hi, b_lo, swz_mn32(idx / (8 * NB), (idx >> 3) % NB, idx & 7, NB), v);
+                }
+                fence_proxy_async();
+                mbar_arrive(&full_bar[s]);
             }
-            fence_proxy_async();
-            mbar_arrive(&full_bar[s]);
         }
     } else if (lane == 0) {
         // =========================== MMA issuer (one thread) ===========================
@@ -274,6 +327,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
 // Pre-split the weights once per step: forward operand Wf[n][Kpad] = W[n][k] and data-gradient operand
 // Wd[k][Npad] = W[n][k] * gamma[k] (transposed), each as (hi, lo) with zero padding to a multiple of 32.
 __global__ void __launch_bounds__(256) prep_weights_kernel(PrepTable t) {
+    // Output "images": for every 32-wide contraction chunk, [rows x 128 B] in the exact 128B-swizzled shared-memory
+    // order, so that a tile (any multiple-of-8 row range of one chunk) is ONE contiguous cp.async.bulk copy.
+    //   forward operand   rows = n (N),  contraction = k: value W[n][k]
+    //   data-grad operand rows = k (K),  contraction = n: value W[n][k] * gamma[k]
     const int j = blockIdx.y;
     const int K = t.K[j], N = t.N[j], Kpad = t.Kpad[j], Npad = t.Npad[j];
     const float* W = t.W[j];
@@ -283,14 +340,16 @@ __global__ void __launch_bounds__(256) prep_weights_kernel(PrepTable t) {
         float w, *hi, *lo;
         size_t o;
         if (i < nf) {
-            const int n = (int)(i / Kpad), k = (int)(i % Kpad);
+            const int n = (int)(i / Kpad), k = (int)(i % Kpad);      // coalesced read of W along k
             w = k < K ? W[(size_t)n * K + k] : 0.f;
-            hi = t.wf_hi[j]; lo = t.wf_lo[j]; o = i;
+            hi = t.wf_hi[j]; lo = t.wf_lo[j];
+            o = (size_t)(k >> 5) * N * 32 + (swz128(n, (k & 31) >> 2) >> 2) + (k & 3);
         } else {
-            o = i - nf;
-            const int k = (int)(o / Npad), n = (int)(o % Npad);
+            const size_t q = i - nf;
+            const int n = (int)(q / K), k = (int)(q % K);            // n < Npad; coalesced read of W along k
             w = n < N ? W[(size_t)n * K + k] * t.gamma[j][k] : 0.f;
             hi = t.wd_hi[j]; lo = t.wd_lo[j];
+            o = (size_t)(n >> 5) * K * 32 + (swz128(k, (n & 31) >> 2) >> 2) + (n & 3);
         }
         float h, l;
         split_tf32(w, h, l);

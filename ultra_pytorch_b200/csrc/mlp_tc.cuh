@@ -12,9 +12,9 @@ struct TcArgs {
     const float* gamma;
     const float* beta;
     const float* dZ;
-    const float* Bhi;
+    const float* Bhi;            // pre-split, pre-swizzled weight images [chunk][ldb rows x 32]
     const float* Blo;
-    int ldb;
+    int ldb;                     // rows of the image (N for the forward operand, K for the data-gradient operand)
     const float* bias;
     float* out;
     int ldo;
