@@ -53,6 +53,18 @@ UB200_API int ub200_set_tc_mode(int mode);
 /* number of parameters of the DNN ranker for (F, hidden[]) in the flat layout above */
 UB200_API size_t ub200_mlp_param_count(int F, const int* hidden, int n_hidden);
 
+/* ---- host side of the boundary: pack one input_feed into a (pinned) staging buffer ---------------------------
+ * Replaces the numpy work of create_input_feed / get_ranking_scores (base_algorithm.py:148-152, 176-186) and the
+ * f64 -> f32 cast (DNN.py:72-73).  HOST pointers.  Layout written to dst (and expected on the device after ONE
+ * H2D copy of ub200_feed_bytes bytes):
+ *     docid int32 [L, B] (position-major) | labels f32 [B, L] | pad to 256 B | feats f32 [n_docs + 1, F] (PAD row = 0)
+ * feats_host: f64 [n_docs, F] row-major; docid_cols_host / label_cols_host: L pointers to f32 [B] (the feed's
+ * "docid_input{l}" / "label{l}" arrays).  Multi-threaded with OpenMP (n_threads). */
+UB200_API size_t ub200_feed_bytes(int n_docs, int F, int L, int B);
+UB200_API int ub200_pack_feed_host(const double* feats_host, int n_docs, int F, const float* const* docid_cols_host,
+                         const float* const* label_cols_host, int L, int B, void* dst_host, size_t dst_bytes,
+                         int n_threads);
+
 /* ---- K1: DNN ranker forward / backward ----------------------------------------------------------------
  * Replaces: host gather base_algorithm.py:148-152, cat + f64->f32 cast DNN.py:72-73, the nn.Sequential of
  * [LayerNorm -> Linear -> ELU] x n_hidden + LayerNorm -> Linear(1) DNN.py:43-55,77, split/cat DNN.py:87-88 +

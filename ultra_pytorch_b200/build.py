@@ -17,7 +17,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libultra_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--cudart", "static"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-fopenmp", "--cudart", "static"]
 FLAGS = [f for f in FLAGS if f != "--use_fast_math=false"]
 
 
@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
         cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         subprocess.check_call(cmd)
         objs.append(obj)
-    cmd = [NVCC, "-shared", "-o", LIBPATH] + objs + ["--cudart", "static", "-lcuda"]
+    cmd = [NVCC, "-shared", "-o", LIBPATH] + objs + ["--cudart", "static", "-lcuda", "-Xcompiler", "-fopenmp"]
     subprocess.check_call(cmd)
     with open(stamp, "w") as f:
         f.write(fp)

@@ -6,6 +6,9 @@
   - a pinned host staging buffer + its device mirror for one step's input_feed.
 Every compute call goes through the C ABI (ultra_pytorch_b200._capi); there is no eager fallback.
 """
+import ctypes
+import os
+
 import numpy as np
 import torch
 
@@ -53,6 +56,7 @@ class RankerEngine(object):
         self._loss_ws = None
         self._pin = None
         self._dev = None
+        self._pack_threads = int(os.environ.get("UB200_PACK_THREADS", str(min(8, os.cpu_count() or 1))))
         self._scores = {}
         self._dscores = {}
 
@@ -126,16 +130,29 @@ class RankerEngine(object):
             self._pin = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
             self._dev = torch.empty(cap, dtype=torch.uint8, device=self.device)
             self._pin_np = self._pin.numpy()
-        buf = self._pin_np
-        hd = buf[:off_l].view(np.int32).reshape(L, B)
-        hl = buf[off_l:2 * off_l].view(np.float32).reshape(B, L)
-        hf = buf[off_f:total].view(np.float32).reshape(n_docs + 1, self.F)
-        if n_docs:
-            np.copyto(hf[:n_docs], feats, casting="same_kind")
-        hf[n_docs] = 0.0
-        for l in range(L):
-            np.copyto(hd[l], docid_arrays[l], casting="unsafe")
-            hl[:, l] = label_arrays[l]
+        fast = (feats.dtype == np.float64 and feats.flags.c_contiguous and n_docs > 0 and
+                all(isinstance(x, np.ndarray) and x.dtype == np.float32 and x.flags.c_contiguous and len(x) == B
+                    for x in docid_arrays) and
+                all(isinstance(x, np.ndarray) and x.dtype == np.float32 and x.flags.c_contiguous and len(x) == B
+                    for x in label_arrays))
+        if fast:
+            # multi-threaded C packer (f64 -> f32 cast, docid -> int32, label transpose) straight into pinned memory
+            PtrArr = ctypes.c_void_p * L
+            dptr = PtrArr(*[x.ctypes.data for x in docid_arrays])
+            lptr = PtrArr(*[x.ctypes.data for x in label_arrays])
+            check(lib.ub200_pack_feed_host(feats.ctypes.data, n_docs, self.F, dptr, lptr, L, B, self._pin.data_ptr(),
+                                           self._pin.numel(), self._pack_threads), "ub200_pack_feed_host")
+        else:
+            buf = self._pin_np
+            hd = buf[:off_l].view(np.int32).reshape(L, B)
+            hl = buf[off_l:2 * off_l].view(np.float32).reshape(B, L)
+            hf = buf[off_f:total].view(np.float32).reshape(n_docs + 1, self.F)
+            if n_docs:
+                np.copyto(hf[:n_docs], feats, casting="same_kind")
+            hf[n_docs] = 0.0
+            for l in range(L):
+                np.copyto(hd[l], docid_arrays[l], casting="unsafe")
+                hl[:, l] = label_arrays[l]
         # the pinned buffer is reused next step: callers sync once per step (loss read-back) before re-staging
         self._dev[:total].copy_(self._pin[:total], non_blocking=True)
         return self.staged_views(self._dev, L, B, n_docs)
