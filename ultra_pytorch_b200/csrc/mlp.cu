@@ -32,17 +32,54 @@ static bool use_tc(int j, int K, int N, int what = 7) { return (tc_mode() & what
 
 
 // ------------------------------------------------------------------------------------------------
+// side streams: the weight-gradient branch of every layer (wgrad GEMM + finalize) is independent of the data-gradient
+// chain once dZ_j exists, so it is forked onto one of two side streams and joined before the launcher returns.
+// Under stream capture the fork/join events become edges of the CUDA graph (parallel branches).
+// ------------------------------------------------------------------------------------------------
+struct SideStreams {
+    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaEvent_t fork_ev[UB200_MAX_LAYERS + 1] = {};
+    cudaEvent_t done_ev[UB200_MAX_LAYERS + 1] = {};
+    int device = -1;
+    bool ok = false;
+};
+static SideStreams* side_streams() {
+    static SideStreams per_dev[16];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    SideStreams* ss = &per_dev[dev];
+    if (!ss->ok) {
+        for (int q = 0; q < 2; ++q)
+            if (cudaStreamCreateWithFlags(&ss->s[q], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (int q = 0; q <= UB200_MAX_LAYERS; ++q) {
+            if (cudaEventCreateWithFlags(&ss->fork_ev[q], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&ss->done_ev[q], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        ss->device = dev;
+        ss->ok = true;
+    }
+    return ss;
+}
+static int g_side = -1;   // env UB200_SIDE_STREAMS=0 keeps the whole backward pass on the caller's stream
+static bool use_side_streams() {
+    if (g_side < 0) {
+        const char* e = getenv("UB200_SIDE_STREAMS");
+        g_side = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_side == 1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // workspace carving
 // ------------------------------------------------------------------------------------------------
 struct MlpWorkspace {
     float2* stats[UB200_MAX_LAYERS];   // (mean, rstd) of the input of layer j, [M]
     float* Y[UB200_MAX_LAYERS];        // output of hidden layer j (post-ELU) [M, N_j]
-    float* dz;                         // [M, maxH]
+    float* dz[2];                      // dZ_j ping-pong, [M, maxH] each (layer j reads dz[j & 1], writes dz[(j-1) & 1])
     float* dxh;                        // [M, maxH]
-    float* partials;                   // split-M partial weight gradients
-    size_t partial_floats;
-    float* fin_scratch;                // wgrad_finalize: per-block partial dgamma / dbeta
-    unsigned int* fin_counters;        // wgrad_finalize: one ticket per k-tile (zero between launches)
+    float* partials[UB200_MAX_LAYERS];     // per layer: split-M partial weight gradients (layers run concurrently)
+    float* fin_scratch[UB200_MAX_LAYERS];  // wgrad_finalize: per-block partial dgamma / dbeta
+    unsigned int* fin_counters[UB200_MAX_LAYERS];   // wgrad_finalize: one ticket per k-tile (zero between launches)
     float* wf_hi[UB200_MAX_LAYERS];    // tensor-core path: pre-split weights (forward operand [N][Kpad])
     float* wf_lo[UB200_MAX_LAYERS];
     float* wd_hi[UB200_MAX_LAYERS];    // data-gradient operand [K][Npad] = (W * gamma)^T
@@ -76,31 +113,28 @@ static void carve(const LayerDims& d, int M, int training, char* base, MlpWorksp
             w->Y[j] = reinterpret_cast<float*>(base + off);
             off = align_up(off + sizeof(float) * (size_t)M * d.N[j], 256);
         }
-        w->dz = reinterpret_cast<float*>(base + off);
-        off = align_up(off + sizeof(float) * (size_t)M * maxH, 256);
+        for (int q = 0; q < 2; ++q) {
+            w->dz[q] = reinterpret_cast<float*>(base + off);
+            off = align_up(off + sizeof(float) * (size_t)M * maxH, 256);
+        }
         w->dxh = reinterpret_cast<float*>(base + off);
         off = align_up(off + sizeof(float) * (size_t)M * maxH, 256);
-        size_t pf = (size_t)kFinalBlocks * (d.K[d.n_layers - 1] + 1);
-        for (int j = 0; j + 1 < d.n_layers; ++j) {
-            size_t need = (size_t)wgrad_splits(M, d.N[j], d.K[j] + 1) * d.N[j] * (d.K[j] + 1);
-            pf = need > pf ? need : pf;
-            size_t need_tc = (size_t)tc_wgrad_splits(M, d.N[j], d.K[j]) * d.N[j] * round_up(d.K[j] + 1, 4);
-            pf = need_tc > pf ? need_tc : pf;
-        }
-        w->partials = reinterpret_cast<float*>(base + off);
-        w->partial_floats = pf;
-        off = align_up(off + sizeof(float) * pf, 256);
-        size_t sf = 0;
-        int maxK = 0;
         for (int j = 0; j < d.n_layers; ++j) {
-            const size_t need = (size_t)((d.N[j] + 7) / 8) * 2 * d.K[j];
-            sf = need > sf ? need : sf;
-            maxK = d.K[j] > maxK ? d.K[j] : maxK;
+            size_t pf;
+            if (j == d.n_layers - 1) {
+                pf = (size_t)kFinalBlocks * (d.K[j] + 1);
+            } else {
+                pf = (size_t)wgrad_splits(M, d.N[j], d.K[j] + 1) * d.N[j] * (d.K[j] + 1);
+                const size_t need_tc = (size_t)tc_wgrad_splits(M, d.N[j], d.K[j]) * d.N[j] * round_up(d.K[j] + 1, 4);
+                pf = need_tc > pf ? need_tc : pf;
+            }
+            w->partials[j] = reinterpret_cast<float*>(base + off);
+            off = align_up(off + sizeof(float) * pf, 256);
+            w->fin_scratch[j] = reinterpret_cast<float*>(base + off);
+            off = align_up(off + sizeof(float) * (size_t)((d.N[j] + 7) / 8) * 2 * d.K[j], 256);
+            w->fin_counters[j] = reinterpret_cast<unsigned int*>(base + off);
+            off = align_up(off + sizeof(unsigned int) * ((d.K[j] + 31) / 32), 256);
         }
-        w->fin_scratch = reinterpret_cast<float*>(base + off);
-        off = align_up(off + sizeof(float) * sf, 256);
-        w->fin_counters = reinterpret_cast<unsigned int*>(base + off);
-        off = align_up(off + sizeof(unsigned int) * ((maxK + 31) / 32), 256);
     } else {
         // inference: ping-pong two activation buffers
         float* a = reinterpret_cast<float*>(base + off);
@@ -108,10 +142,11 @@ static void carve(const LayerDims& d, int M, int training, char* base, MlpWorksp
         float* b = reinterpret_cast<float*>(base + off);
         off = align_up(off + sizeof(float) * (size_t)M * maxH, 256);
         for (int j = 0; j + 1 < d.n_layers; ++j) w->Y[j] = (j & 1) ? b : a;
-        w->dz = w->dxh = w->partials = nullptr;
-        w->partial_floats = 0;
-        w->fin_scratch = nullptr;
-        w->fin_counters = nullptr;
+        w->dz[0] = w->dz[1] = w->dxh = nullptr;
+        for (int j = 0; j < UB200_MAX_LAYERS; ++j) {
+            w->partials[j] = w->fin_scratch[j] = nullptr;
+            w->fin_counters[j] = nullptr;
+        }
     }
     for (int j = 0; j < UB200_MAX_LAYERS; ++j) w->wf_hi[j] = w->wf_lo[j] = w->wd_hi[j] = w->wd_lo[j] = nullptr;
     for (int j = 0; j + 1 < d.n_layers; ++j) {
@@ -450,29 +485,24 @@ __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __rest
     const int k = blockIdx.x * 32 + kx, n = blockIdx.y * 8 + ny;
     const size_t plane = (size_t)N * K1;
     float g = 0.f, dbn = 0.f;
-    if (n < N) {
-        const float* pn = part + (size_t)n * K1;
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-        int s = 0;
-        for (; s + 3 < S; s += 4) {
-            d0 += pn[(size_t)s * plane + K];
-            d1 += pn[(size_t)(s + 1) * plane + K];
-            d2 += pn[(size_t)(s + 2) * plane + K];
-            d3 += pn[(size_t)(s + 3) * plane + K];
-        }
-        for (; s < S; ++s) d0 += pn[(size_t)s * plane + K];
-        dbn = (d0 + d1) + (d2 + d3);
-        if (k < K) {
-            float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
-            s = 0;
-            for (; s + 3 < S; s += 4) {
-                g0 += pn[(size_t)s * plane + k];
-                g1 += pn[(size_t)(s + 1) * plane + k];
-                g2 += pn[(size_t)(s + 2) * plane + k];
-                g3 += pn[(size_t)(s + 3) * plane + k];
+    {
+        // db[n]: the 32 lanes of the warp (same n) split the S planes, then a butterfly sum (fixed order)
+        const float* pn = part + (size_t)(n < N ? n : 0) * K1;
+        float dpart = 0.f;
+        if (n < N)
+            for (int s = kx; s < S; s += 32) dpart += pn[(size_t)s * plane + K];
+        dbn = warp_sum(dpart);
+        if (n < N && k < K) {
+            float acc[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+            int s = 0;
+            for (; s + 7 < S; s += 8) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] += pn[(size_t)(s + q) * plane + k];
             }
-            for (; s < S; ++s) g0 += pn[(size_t)s * plane + k];
-            g = (g0 + g1) + (g2 + g3);
+            for (; s < S; ++s) acc[0] += pn[(size_t)s * plane + k];
+            g = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
         }
     }
     float ag = 0.f, ab = 0.f;
@@ -658,7 +688,22 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
     const int row_blocks = (M + 7) / 8;
     const int nl = d.n_layers;
 
-    // final layer (N = 1)
+    SideStreams* ss = use_side_streams() ? side_streams() : nullptr;
+    // stream of the weight-gradient branch of layer j, forked from `st` at the current point
+    auto fork = [&](int j) -> cudaStream_t {
+        if (!ss) return st;
+        cudaEventRecord(ss->fork_ev[j], st);
+        cudaStreamWaitEvent(ss->s[j & 1], ss->fork_ev[j], 0);
+        return ss->s[j & 1];
+    };
+    auto branch_done = [&](int j) {
+        if (ss) cudaEventRecord(ss->done_ev[j], ss->s[j & 1]);
+    };
+    auto wait_branch = [&](int j) {
+        if (ss) cudaStreamWaitEvent(st, ss->done_ev[j], 0);
+    };
+
+    // final layer (N = 1): dZ_{nl-2} goes to dz[(nl-2) & 1]
     {
         const int j = nl - 1, K = d.K[j];
         const float* X = (j == 0) ? feats : w.Y[j - 1];
@@ -670,16 +715,18 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(final_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         final_bwd_kernel<<<blocks, 256, smem, st>>>(X, idx, w.stats[j], M, K, params + d.off_g[j],
-                                                    params + d.off_w[j], dscores, L, B, (j == 0) ? nullptr : w.dz,
-                                                    w.partials);
+                                                    params + d.off_w[j], dscores, L, B,
+                                                    (j == 0) ? nullptr : w.dz[(j - 1) & 1], w.partials[j]);
         UB_LAUNCH_CHECK("final_bwd_kernel");
-        final_finalize_kernel<<<(K + 31) / 32, 256, 0, st>>>(w.partials, blocks, K, params + d.off_w[j],
+        cudaStream_t sb = fork(j);
+        final_finalize_kernel<<<(K + 31) / 32, 256, 0, sb>>>(w.partials[j], blocks, K, params + d.off_w[j],
                                                              params + d.off_g[j], params + d.off_b[j],
                                                              grads + d.off_w[j], grads + d.off_c[j],
                                                              grads + d.off_g[j], grads + d.off_b[j]);
-        UB_LAUNCH_CHECK("wgrad_finalize_kernel(final)");
+        UB_LAUNCH_CHECK("final_finalize_kernel");
+        branch_done(j);
     }
-    // hidden layers, last to first; w.dz holds dZ_j [M, N_j]
+    // hidden layers, last to first; dz[j & 1] holds dZ_j [M, N_j]
     for (int j = nl - 2; j >= 0; --j) {
         const int K = d.K[j], N = d.N[j];
         const float* X = (j == 0) ? feats : w.Y[j - 1];
@@ -687,7 +734,9 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
         const float* g = params + d.off_g[j];
         const float* bt = params + d.off_b[j];
         const float* W = params + d.off_w[j];
-        // weight gradient GEMM: G[n, k] (k == K -> db), split over row chunks
+        const float* dz = w.dz[j & 1];
+        // ---- weight-gradient branch (side stream): G[n, k] (k == K -> db) split over row chunks, then finalize ----
+        cudaStream_t sb = fork(j);
         int S_eff, ldp;
         if (use_tc(j, K, N, TC_WGRAD)) {
             const int S = tc_wgrad_splits(M, N, K);
@@ -696,9 +745,9 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
             S_eff = (M + rps - 1) / rps;
             ldp = round_up(K + 1, 4);
             tc::TcArgs t{};
-            t.M = M; t.K = K; t.N = N; t.X = X; t.docid = idx; t.stats = w.stats[j]; t.dZ = w.dz;
-            t.out = w.partials; t.ldo = ldp; t.rows_per_split = rps;
-            if (int rc = tc_wgrad_layer(t, S_eff, st)) return rc;
+            t.M = M; t.K = K; t.N = N; t.X = X; t.docid = idx; t.stats = w.stats[j]; t.dZ = dz;
+            t.out = w.partials[j]; t.ldo = ldp; t.rows_per_split = rps;
+            if (int rc = tc_wgrad_layer(t, S_eff, sb)) return rc;
         } else {
             const int S = wgrad_splits(M, N, K + 1);
             int rps = (M + S - 1) / S;
@@ -707,31 +756,36 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
             ldp = K + 1;
             GemmArgs a{};
             a.I = N; a.J = K + 1; a.C = M;
-            a.X = X; a.docid = idx; a.stats = w.stats[j]; a.dZ = w.dz; a.out = w.partials;
+            a.X = X; a.docid = idx; a.stats = w.stats[j]; a.dZ = dz; a.out = w.partials[j];
             a.K = K; a.N = N; a.rows_per_split = rps;
-            launch_gemm<MODE_WGRAD>(a, S_eff, st);
+            launch_gemm<MODE_WGRAD>(a, S_eff, sb);
             UB_LAUNCH_CHECK("gemm_kernel<WGRAD>");
         }
-        wgrad_finalize_kernel<<<dim3((K + 31) / 32, (N + 7) / 8), 256, 0, st>>>(
-            w.partials, S_eff, N, K, ldp, W, g, bt, grads + d.off_w[j], grads + d.off_c[j], grads + d.off_g[j],
-            grads + d.off_b[j], w.fin_scratch, w.fin_counters);
+        wgrad_finalize_kernel<<<dim3((K + 31) / 32, (N + 7) / 8), 256, 0, sb>>>(
+            w.partials[j], S_eff, N, K, ldp, W, g, bt, grads + d.off_w[j], grads + d.off_c[j], grads + d.off_g[j],
+            grads + d.off_b[j], w.fin_scratch[j], w.fin_counters[j]);
         UB_LAUNCH_CHECK("wgrad_finalize_kernel");
+        branch_done(j);
+        // ---- data-gradient chain (caller's stream) ----
         if (j > 0) {
             if (use_tc(j, K, N, TC_DGRAD)) {
                 tc::TcArgs t{};
-                t.M = M; t.K = K; t.N = N; t.dZ = w.dz; t.Bhi = w.wd_hi[j]; t.Blo = w.wd_lo[j];
+                t.M = M; t.K = K; t.N = N; t.dZ = dz; t.Bhi = w.wd_hi[j]; t.Blo = w.wd_lo[j];
                 t.ldb = K; t.out = w.dxh; t.ldo = K;
                 if (int rc = tc_dgrad_layer(t, st)) return rc;
             } else {
                 GemmArgs b{};
                 b.I = M; b.J = K; b.C = N;
-                b.dZ = w.dz; b.W = W; b.gamma = g; b.out = w.dxh; b.K = K; b.N = N;
+                b.dZ = dz; b.W = W; b.gamma = g; b.out = w.dxh; b.K = K; b.N = N;
                 launch_gemm<MODE_DGRAD>(b, 1, st);
                 UB_LAUNCH_CHECK("gemm_kernel<DGRAD>");
             }
-            ln_bwd_elu_kernel<<<row_blocks, 256, 0, st>>>(w.dxh, X, w.stats[j], M, K, w.dz);
+            // dZ_{j-1} overwrites the buffer dZ_{j+1} lived in: its weight-gradient branch must have finished
+            if (j + 1 <= nl - 2) wait_branch(j + 1);
+            ln_bwd_elu_kernel<<<row_blocks, 256, 0, st>>>(w.dxh, X, w.stats[j], M, K, w.dz[(j - 1) & 1]);
             UB_LAUNCH_CHECK("ln_bwd_elu_kernel");
         }
     }
+    for (int j = 0; j < nl; ++j) wait_branch(j);    // join every branch
     return 0;
 }
