@@ -200,7 +200,7 @@ def main_b200(args):
         torch.cuda.synchronize()
         own = eng._dev[:st.h2d_bytes].clone()
         ring.append(eng.staged_views(own, L, B, st.n_docs))
-    use_graph = la.B200Algorithm.USE_GRAPH and world == 1
+    use_graph = la.B200Algorithm.USE_GRAPH and (world == 1 or la.B200Algorithm.USE_GRAPH_DP)
 
     def barrier():
         if world > 1:

@@ -50,6 +50,9 @@ class B200Algorithm(_reference_base()):
     VERBOSE = os.environ.get("UB200_QUIET", "0") != "1"
     # fixed-shape steps are captured once in a CUDA graph and replayed (one launch per step instead of ~25)
     USE_GRAPH = os.environ.get("UB200_GRAPH", "1") != "0"
+    # data-parallel steps are captured as TWO graphs (compute | update) with the NCCL all-reduce launched eagerly
+    # between them (capturing the collective itself dead-locked when ranks capture at different moments)
+    USE_GRAPH_DP = os.environ.get("UB200_GRAPH_DP", "1") != "0"
 
     # ---- construction helpers ---------------------------------------------------------------------
     def _init_common(self, data_set, exp_settings, extra_floats):
@@ -77,29 +80,48 @@ class B200Algorithm(_reference_base()):
         self.last_h2d_bytes = 0
         self.last_d2h_bytes = 0
         self._graphs = {}
+        self._phase = None       # None: whole step | 'pre': up to the all-reduce | 'post': after it
 
     def run_step(self, st):
-        """device_step(st), replayed from a CUDA graph once the (B, L, buffer) combination has been seen twice."""
-        if not self.USE_GRAPH or self.world_size() > 1:
+        """device_step(st), replayed from CUDA graphs once the (B, L, buffer) combination has been seen twice."""
+        dp = self.world_size() > 1
+        if not self.USE_GRAPH or (dp and not self.USE_GRAPH_DP):
             return self.device_step(st)
         key = (st.B, st.L, st.feats.data_ptr(), st.docid.data_ptr())
         ent = self._graphs.get(key)
         if ent is None:
             if len(self._graphs) > 512:
                 self._graphs.clear()
-            ent = self._graphs[key] = [0, None, None]
+            ent = self._graphs[key] = [0, None, None, None]
         if ent[1] is not None:
             ent[1].replay()
+            if ent[3] is not None:
+                self._allreduce_gradbuf()
+                ent[3].replay()
             return ent[2]
         ent[0] += 1
         if ent[0] <= 2:                      # warm-up: workspaces get allocated outside the capture
             return self.device_step(st)
-        graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
-        with torch.cuda.graph(graph):
+        if not dp:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.device_step(st)
+            ent[1], ent[2] = graph, out
+            graph.replay()
+            return out
+        g_pre, g_post = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        self._phase = "pre"
+        with torch.cuda.graph(g_pre):
+            self.device_step(st)
+        self._phase = "post"
+        with torch.cuda.graph(g_post):
             out = self.device_step(st)
-        ent[1], ent[2] = graph, out
-        graph.replay()
+        self._phase = None
+        ent[1], ent[2], ent[3] = g_pre, out, g_post
+        g_pre.replay()
+        self._allreduce_gradbuf()
+        g_post.replay()
         return out
 
     def create_model(self, feature_size):

@@ -78,13 +78,17 @@ class DLA(B200Algorithm):
     def device_step(self, st):
         eng = self.engine
         L, B = st.L, st.B
-        docid = st.docid.view(-1)
-        scores = eng.forward(st.feats, docid, L, B, training=True)
-        dscores = eng.dscores_buf(B, L)
         flat = self.propensity_model.flat
-        eng.dla_loss(scores, st.labels, flat[:L], flat[L:], dscores, self._dprop, self._sums)
-        eng.backward(st.feats, docid, L, B, dscores)
-        self._allreduce_gradbuf()
+        if self._phase != "post":
+            docid = st.docid.view(-1)
+            scores = eng.forward(st.feats, docid, L, B, training=True)
+            dscores = eng.dscores_buf(B, L)
+            eng.dla_loss(scores, st.labels, flat[:L], flat[L:], dscores, self._dprop, self._sums)
+            eng.backward(st.feats, docid, L, B, dscores)
+        if self._phase == "pre":
+            return None
+        if self._phase is None:
+            self._allreduce_gradbuf()
         # fresh optimizers every step (dla.py:153-154): accumulator starts from zero -> mode 1; the two parameter
         # groups are clipped separately (dla.py:161-163)
         mode = self._opt_mode(fresh=True)

@@ -36,13 +36,17 @@ class NavieAlgorithm(B200Algorithm):
         Returns the device tensor holding the loss scalars."""
         eng = self.engine
         L, B = st.L, st.B
-        docid = st.docid.view(-1)
-        scores = eng.forward(st.feats, docid, L, B, training=True)
-        dscores = eng.dscores_buf(B, L)
         sums = eng.extra[:2]
-        eng.softmax_ce(scores, st.labels, self.WEIGHT_MODE, self._table, dscores, sums)
-        eng.backward(st.feats, docid, L, B, dscores)
-        self._allreduce_gradbuf()
+        if self._phase != "post":
+            docid = st.docid.view(-1)
+            scores = eng.forward(st.feats, docid, L, B, training=True)
+            dscores = eng.dscores_buf(B, L)
+            eng.softmax_ce(scores, st.labels, self.WEIGHT_MODE, self._table, dscores, sums)
+            eng.backward(st.feats, docid, L, B, dscores)
+        if self._phase == "pre":
+            return None
+        if self._phase is None:
+            self._allreduce_gradbuf()
         eng.clip_update(eng.params, eng.grads, eng.state_sum, sums[1:2], 1.0, self.hparams.max_gradient_norm,
                         self.learning_rate, self._opt_mode(), eng.norm)
         return sums

@@ -41,13 +41,17 @@ class PairDebias(B200Algorithm):
     def device_step(self, st):
         eng = self.engine
         L, B = st.L, st.B
-        docid = st.docid.view(-1)
-        scores = eng.forward(st.feats, docid, L, B, training=True)
-        dscores = eng.dscores_buf(B, L)
         out = eng.extra[:2 * L + 2]
-        self._pair_kernel(scores, st.labels, dscores, out)
-        eng.backward(st.feats, docid, L, B, dscores)
-        self._allreduce_gradbuf()
+        if self._phase != "post":
+            docid = st.docid.view(-1)
+            scores = eng.forward(st.feats, docid, L, B, training=True)
+            dscores = eng.dscores_buf(B, L)
+            self._pair_kernel(scores, st.labels, dscores, out)
+            eng.backward(st.feats, docid, L, B, dscores)
+        if self._phase == "pre":
+            return None
+        if self._phase is None:
+            self._allreduce_gradbuf()
         self._update(out, L, B)
         self._scal.copy_(out[2 * L:2 * L + 2])          # loss (+ idcg) before anything reuses the buffer
         eng.em_update(self.t_plus, self.t_minus, out, self.hparams.EM_step_size, self.hparams.regulation_p,
