@@ -44,7 +44,7 @@ class UltraB200Error(RuntimeError):
 
 
 def _load():
-    path = _build.LIBPATH
+    path = os.environ.get("UB200_LIB") or _build.LIBPATH     # UB200_LIB: debugging builds (e.g. timeline stamps)
     if not os.path.isfile(path):
         try:
             _build.build()

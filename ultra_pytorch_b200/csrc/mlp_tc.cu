@@ -44,16 +44,22 @@ __device__ __forceinline__ void st_split(uint8_t* hi_base, uint8_t* lo_base, uin
     *reinterpret_cast<float4*>(hi_base + off) = h;
     *reinterpret_cast<float4*>(lo_base + off) = l;
 }
-// ELU for the forward epilogue: expm1 through a degree-6 Taylor polynomial near zero (rel. error < 5e-8 on
-// [-0.25, 0]) and ex2.approx elsewhere (abs. error < 2e-7 on values >= 0.22): ~3x cheaper than expm1f.
+// ELU for the forward epilogue.  Negative side: ex2.approx based exp(z) - 1 (absolute error < 3e-7, i.e. < 1e-6 of
+// the activation scale) with the 2-term series z + z^2/2 below |z| < 2^-7 where the subtraction would cancel.
 __device__ __forceinline__ float elu_fast(float z) {
-    const float zc = fminf(z, 0.f);
-    const float p = zc * (1.f + zc * (0.5f + zc * (0.16666667f + zc * (0.041666668f + zc * (0.0083333338f +
-                                                                                           zc * 0.0013888889f)))));
-    const float e = __expf(zc) - 1.f;
-    const float neg = zc > -0.25f ? p : e;
+    const float e = __expf(z) - 1.f;
+    const float t = fmaf(0.5f * z, z, z);
+    const float neg = z > -0.0078125f ? t : e;
     return z > 0.f ? z : neg;
 }
+
+#ifdef UB200_TC_TIMELINE
+__device__ unsigned long long g_tc_timeline[64];
+#define TC_STAMP(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { unsigned long long t_; \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_tc_timeline[i] = t_; } } while (0)
+#else
+#define TC_STAMP(i) do { } while (0)
+#endif
 
 template <int KIND, int BLOCK_N>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
@@ -67,9 +73,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* accum_bar = empty_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 128);   // [BLOCK_N] bias slice (FWD)
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) TC_STAMP(0);
     const int i0 = blockIdx.x * BLOCK_M;        // first row of the MMA "M" dimension (m, or n for WGRAD)
     const int j0 = blockIdx.y * BLOCK_N;        // first row of the MMA "N" dimension (n / k / k)
     int c_begin = 0, c_end;
@@ -94,11 +102,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
     // the number of accumulation steps; keeping the 2^-12-times-smaller correction terms out of the main accumulator
     // cuts its accumulation count by 3 (measured at K = 700: scores 1.1e-5 -> inside the 1e-5 bound).
     if (warp == MMA_WARP) tmem_alloc(tmem_slot, 2 * BLOCK_N);
+    if (KIND == KIND_FWD && tid < BLOCK_N) sbias[tid] = (j0 + tid < a.N) ? a.bias[j0 + tid] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) TC_STAMP(1);
 
     if (warp < MMA_WARP) {
         // =========================== producers ===========================
@@ -137,12 +147,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
                     b = kv ? ld4(a.beta + cc) : zero4;
                 }
             };
+            if (tid == 0) TC_STAMP(2);
             if (n_chunks > 0) load_chunk(0, cur, g_cur, b_cur);
             for (int it = 0; it < n_chunks; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
                 if (it + 1 < n_chunks) load_chunk(it + 1, nxt, g_nxt, b_nxt);
                 mbar_wait(&empty_bar[s], ph ^ 1u);
+                if (tid == 0 && it < 8) TC_STAMP(8 + 2 * it);
                 uint8_t* a_hi = smem + s * STAGE_BYTES;
                 uint8_t* a_lo = a_hi + A_TILE_BYTES;
                 uint8_t* b_hi = a_lo + A_TILE_BYTES;
@@ -168,6 +180,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
                 }
                 fence_proxy_async();
                 mbar_arrive(&full_bar[s]);
+                if (tid == 0 && it < 8) TC_STAMP(9 + 2 * it);
 #pragma unroll
                 for (int e = 0; e < RPT; ++e) cur[e] = nxt[e];
                 g_cur = g_nxt;
@@ -309,6 +322,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
             mma_commit(&empty_bar[s]);       // ring slot reusable once these MMAs have read it
         }
         mma_commit(accum_bar);               // accumulator complete
+        TC_STAMP(3);
     }
 
     __syncwarp();
@@ -318,47 +332,58 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
         mbar_wait(accum_bar, 0);
         __syncwarp();
         tc_fence_after();
+        if (tid == 0) TC_STAMP(4);
+        // 1) accumulator (main + correction) -> bias/ELU -> shared-memory tile [128][BLOCK_N + 4] (the operand ring is
+        //    free now).  Thread = row in TMEM; the +4 padding keeps the 16-byte row-strided stores conflict free.
+        // 2) coalesced copy-out: consecutive lanes write consecutive 16-byte chunks of a row (a thread-per-row store
+        //    touches 32 cache lines per instruction and made the epilogue half of the kernel time).
+        constexpr int TS = BLOCK_N + 4;                     // tile row stride in floats
+        float* stile = reinterpret_cast<float*>(smem);
         const int q4 = warp & 3;
-        const int row = i0 + q4 * 32 + lane;
+        const int trow = q4 * 32 + lane;
         const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16);
-        int row_limit, col_limit;
-        float* dst;
-        if (KIND == KIND_FWD) {
-            row_limit = a.M; col_limit = a.N;
-            dst = a.out + (size_t)row * a.ldo;
-        } else if (KIND == KIND_DGRAD) {
-            row_limit = a.M; col_limit = a.K;
-            dst = a.out + (size_t)row * a.ldo;
-        } else {
-            row_limit = a.N; col_limit = a.ldo;
-            dst = a.out + ((size_t)blockIdx.z * a.N + row) * a.ldo;
-        }
 #pragma unroll 1
         for (int cb = warp >> 2; cb < BLOCK_N / 32; cb += 4) {
             float v[32], corr[32];
             tmem_ld32(taddr + cb * 32, v);
             tmem_ld32(taddr + BLOCK_N + cb * 32, corr);
+            float* trow_ptr = stile + (size_t)trow * TS + cb * 32;
 #pragma unroll
-            for (int q = 0; q < 32; ++q) v[q] += corr[q];
-            const int col0 = j0 + cb * 32;
-            if (row < row_limit) {
-#pragma unroll
-                for (int q = 0; q < 32; q += 4) {
-                    if (col0 + q < col_limit) {       // limits are multiples of 4
-                        float4 o = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
-                        if (KIND == KIND_FWD) {
-                            const float4 b = ld4(a.bias + col0 + q);
-                            o.x = elu_fast(o.x + b.x);
-                            o.y = elu_fast(o.y + b.y);
-                            o.z = elu_fast(o.z + b.z);
-                            o.w = elu_fast(o.w + b.w);
-                        }
-                        *reinterpret_cast<float4*>(dst + col0 + q) = o;
-                    }
+            for (int q = 0; q < 32; q += 4) {
+                float4 o = make_float4(v[q] + corr[q], v[q + 1] + corr[q + 1], v[q + 2] + corr[q + 2],
+                                       v[q + 3] + corr[q + 3]);
+                if (KIND == KIND_FWD) {
+                    const float4 b = *reinterpret_cast<const float4*>(sbias + cb * 32 + q);
+                    o.x = elu_fast(o.x + b.x);
+                    o.y = elu_fast(o.y + b.y);
+                    o.z = elu_fast(o.z + b.z);
+                    o.w = elu_fast(o.w + b.w);
                 }
+                *reinterpret_cast<float4*>(trow_ptr + q) = o;
             }
         }
+        asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");     // the 16 epilogue warps only
+        int row_limit, col_limit;
+        if (KIND == KIND_FWD) {
+            row_limit = a.M; col_limit = a.N;
+        } else if (KIND == KIND_DGRAD) {
+            row_limit = a.M; col_limit = a.K;
+        } else {
+            row_limit = a.N; col_limit = a.ldo;
+        }
+        float* out_base = a.out;
+        if (KIND == KIND_WGRAD) out_base += (size_t)blockIdx.z * a.N * a.ldo;
+        constexpr int CPR = BLOCK_N / 4;                    // 16-byte chunks per tile row
+#pragma unroll 4
+        for (int idx = tid; idx < BLOCK_M * CPR; idx += NPROD) {
+            const int r = idx / CPR, ch = idx % CPR;
+            const int grow = i0 + r, gcol = j0 + ch * 4;
+            if (grow < row_limit && gcol < col_limit)         // limits are multiples of 4
+                *reinterpret_cast<float4*>(out_base + (size_t)grow * a.ldo + gcol) =
+                    *reinterpret_cast<const float4*>(stile + (size_t)r * TS + ch * 4);
+        }
     }
+    if (tid == 0) TC_STAMP(5);
     __syncwarp();
     tc_fence_before();
     __syncthreads();
@@ -366,6 +391,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 2 * BLOCK_N);
     }
+    if (tid == 0) TC_STAMP(6);
 }
 
 // Pre-split the weights once per step: forward operand Wf[n][Kpad] = W[n][k] and data-gradient operand
@@ -404,7 +430,7 @@ __global__ void __launch_bounds__(256) prep_weights_kernel(PrepTable t) {
 
 template <int KIND, int BLOCK_N>
 static cudaError_t launch_one(const TcArgs& a, dim3 grid, cudaStream_t st) {
-    constexpr int smem = num_stages(BLOCK_N) * stage_bytes(BLOCK_N) + 1024 + 256;
+    constexpr int smem = num_stages(BLOCK_N) * stage_bytes(BLOCK_N) + 1024 + 256 + BLOCK_N * 4;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<KIND, BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -442,6 +468,12 @@ static int pick_block_n(int cols, int row_tiles) {
 }
 
 }  // namespace tc
+
+#ifdef UB200_TC_TIMELINE
+extern "C" UB200_API int ub200_tc_timeline(unsigned long long* out64) {
+    return (int)cudaMemcpyFromSymbol(out64, tc::g_tc_timeline, sizeof(unsigned long long) * 64);
+}
+#endif
 
 // ---- entry points used by mlp.cu -------------------------------------------------------------------------
 bool tc_layer_ok(int j, int K, int N) {
