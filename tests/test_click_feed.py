@@ -1,0 +1,125 @@
+"""CPU tests of the vectorised ClickSimulationFeed drop-in against the reference feed:
+bit-identical on the deterministic paths, equal in distribution on the sampled clicks."""
+import json
+import os
+import random
+import types
+
+import numpy as np
+import pytest
+
+from oracle import ref_shim
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PBM = {"click_prob": [0.1, 0.16, 0.28, 0.52, 1.0], "eta": 1.0,
+       "exam_prob": [0.68, 0.61, 0.48, 0.34, 0.28, 0.2, 0.11, 0.1, 0.08, 0.06], "model_name": "position_biased_model"}
+
+
+class FakeData(object):
+    """Minimal stand-in for ultra.utils.data_utils.Raw_data after pad() (data_utils.py:476-498)."""
+
+    def __init__(self, nq, L, F, seed=0, ragged=True):
+        rs = np.random.RandomState(seed)
+        self.feature_size, self.rank_list_size = F, L
+        self.features, self.initial_list, self.labels = [], [], []
+        doc = 0
+        for _ in range(nq):
+            n = int(rs.randint(max(1, L // 2), L + 1)) if ragged else L
+            self.features.extend(rs.uniform(-1, 1, size=(n, F)).tolist())
+            self.initial_list.append(list(range(doc, doc + n)) + [-1] * (L - n))
+            self.labels.append(rs.randint(0, 5, size=n).astype(float).tolist())
+            doc += n
+        self.features.append([0.0] * F)
+
+
+def _model(L, F):
+    return types.SimpleNamespace(rank_list_size=L, feature_size=F, letor_features_name="letor_features",
+                                 docid_inputs_name=["docid_input%d" % i for i in range(L)],
+                                 labels_name=["label%d" % i for i in range(L)])
+
+
+def _ours(tmp_path, L, F, B, hp=""):
+    from ultra_pytorch_b200.input_layer import ClickSimulationFeed
+    p = os.path.join(str(tmp_path), "pbm.json")
+    with open(p, "w") as f:
+        json.dump(PBM, f)
+    return ClickSimulationFeed(_model(L, F), B, ("click_model_json=%s," % p) + hp), p
+
+
+def test_feed_format_and_pad_convention(tmp_path):
+    L, F, B = 7, 5, 16
+    ds = FakeData(40, L, F)
+    feed, _ = _ours(tmp_path, L, F, B)
+    random.seed(0)
+    f, info = feed.get_batch(ds, check_validation=True)
+    feats = f["letor_features"]
+    n_docs = feats.shape[0]
+    assert feats.dtype == np.float64 and feats.shape[1] == F
+    docid = np.stack([f["docid_input%d" % l] for l in range(L)], axis=1)
+    clicks = np.stack([f["label%d" % l] for l in range(L)], axis=1)
+    assert docid.dtype == np.float32 and clicks.dtype == np.float32 and docid.shape == (B, L)
+    assert (clicks.sum(axis=1) > 0).all()                       # check_validation drops click-less lists
+    real = docid != n_docs
+    assert sorted(docid[real].astype(int).tolist()) == list(range(n_docs))   # every real doc referenced exactly once
+    for b, q in enumerate(info["rank_list_idxs"]):             # features are the data set's rows, in list order
+        ids = [d for d in ds.initial_list[q] if d >= 0]
+        got = feats[docid[b][real[b]].astype(int)]
+        assert np.array_equal(got, np.asarray(ds.features)[ids])
+    assert len(info["input_list"]) == B
+
+
+def test_click_rates_follow_the_position_biased_model(tmp_path):
+    L, F, B = 12, 3, 512
+    ds = FakeData(300, L, F, ragged=False)
+    feed, _ = _ours(tmp_path, L, F, B)
+    feed.rng = np.random.default_rng(1)
+    init, labels, _ = feed._arrays(ds)
+    tot, exp, n = np.zeros(L), np.zeros(L), 0
+    for _ in range(40):
+        f, info = feed.get_batch(ds, check_validation=False)
+        clicks = np.stack([f["label%d" % l] for l in range(L)], axis=1)
+        lab = labels[np.asarray(info["rank_list_idxs"])]
+        exam = np.asarray(PBM["exam_prob"])[np.minimum(np.arange(L), 9)]
+        exp += (exam[None, :] * np.asarray(PBM["click_prob"])[lab.astype(int)]).sum(axis=0)
+        tot += clicks.sum(axis=0)
+        n += B
+    sigma = np.sqrt(np.maximum(exp, 1.0))
+    assert (np.abs(tot - exp) < 5 * sigma).all(), (tot, exp)
+
+
+@pytest.mark.parametrize("oracle_mode", [True, False])
+def test_matches_reference_feed(tmp_path, oracle_mode):
+    if not ref_shim.available():
+        pytest.skip("oracle/_ref not installed")
+    ultra = ref_shim.load()
+    L, F, B = 9, 6, 8
+    ds = FakeData(30, L, F, seed=3)
+    ours, pbm_path = _ours(tmp_path, L, F, B, "oracle_mode=%s" % oracle_mode)
+    ref = ultra.input_layer.ClickSimulationFeed(_model(L, F), B, "click_model_json=%s,oracle_mode=%s"
+                                                % (pbm_path, oracle_mode))
+    if oracle_mode:
+        # deterministic: sequential batches are bit-identical, including the ragged last batch
+        for index in (0, 8, 24):
+            a, ia = ours.get_next_batch(index, ds, check_validation=False)
+            b, ib = ref.get_next_batch(index, ds, check_validation=False)
+            assert sorted(a.keys()) == sorted(b.keys())
+            for k in a:
+                assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), k
+            assert len(ia["input_list"]) == len(ib["input_list"])
+        a, _ = ours.get_data_by_index(ds, 5)
+        b, _ = ref.get_data_by_index(ds, 5)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+    else:
+        # sampled clicks: same per-position click rate as the reference's own sampler (5 sigma)
+        random.seed(7)
+        ours.rng = np.random.default_rng(7)
+        ta, tb, n = np.zeros(L), np.zeros(L), 0
+        for _ in range(150):
+            a, _ = ours.get_next_batch(0, ds, check_validation=False)
+            b, _ = ref.get_next_batch(0, ds, check_validation=False)
+            ta += np.stack([a["label%d" % l] for l in range(L)], axis=1).sum(axis=0)
+            tb += np.stack([b["label%d" % l] for l in range(L)], axis=1).sum(axis=0)
+            n += B
+        sigma = np.sqrt(np.maximum(ta + tb, 1.0))
+        assert (np.abs(ta - tb) < 5 * sigma).all(), (ta, tb)

@@ -18,6 +18,9 @@ SETTINGS = {
     "dla": ("ultra_pytorch_b200.learning_algorithm.DLA", "ultra.input_layer.ClickSimulationFeed"),
     "lambdarank": ("ultra_pytorch_b200.learning_algorithm.LambdaRank", "ultra.input_layer.ClickSimulationFeed"),
     "na": ("ultra_pytorch_b200.learning_algorithm.NavieAlgorithm", "ultra.input_layer.DirectLabelFeed"),
+    # the vectorised feed drop-in together with the B200 algorithm
+    "pairdebias_b200feed": ("ultra_pytorch_b200.learning_algorithm.PairDebias",
+                            "ultra_pytorch_b200.input_layer.ClickSimulationFeed"),
 }
 
 

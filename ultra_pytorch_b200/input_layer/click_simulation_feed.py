@@ -1,0 +1,187 @@
+"""Vectorised drop-in for `ultra.input_layer.ClickSimulationFeed`
+(reference: ultra/input_layer/click_simulation_feed.py:23-294, click model ultra/utils/click_models.py:68-110).
+
+The reference assembles every batch with pure-Python loops (one `sampleClicksForOneList` call per query, one list
+comprehension per (query, position), `np.array` of a list of feature lists): 67 ms per 256-query batch at config 2,
+430 ms at L = 200 - more than the whole reference train() step and ~100x the B200 step.  This class produces the
+SAME `input_feed` (keys, dtypes, shapes, PAD convention, click semantics) with numpy array operations on a cached
+array view of the data set.  Random numbers come from a numpy Generator seeded from Python's `random` module at
+construction (the reference draws from `random` directly), so runs stay reproducible under `random.seed(...)`,
+but the click streams are equal in distribution, not draw for draw.  Deterministic paths (oracle_mode, sequential
+`get_next_batch` with check_validation=False) are bit-identical to the reference (tests/test_click_feed.py).
+"""
+import json
+import random
+
+import numpy as np
+
+from ..hparams import HParams
+
+ORIGINAL_EXAM_PROB = [0.68, 0.61, 0.48, 0.34, 0.28, 0.20, 0.11, 0.10, 0.08, 0.06]   # click_models.py:76-77
+
+
+class _PositionBiasedModel(object):
+    """Array form of PositionBiasedModel (click_models.py:68-110)."""
+
+    def __init__(self, desc):
+        if desc.get('model_name', 'position_biased_model') != 'position_biased_model':
+            raise NotImplementedError("only the position_biased_model click model is vectorised (got %r)"
+                                      % desc.get('model_name'))
+        self.eta = desc['eta']
+        self.click_prob = np.asarray(desc['click_prob'], dtype=np.float64)
+        self.exam_prob = np.asarray(desc['exam_prob'], dtype=np.float64)
+
+    def setExamProb(self, eta):
+        self.eta = eta
+        self.exam_prob = np.power(np.asarray(ORIGINAL_EXAM_PROB, dtype=np.float64), eta)
+
+    def click_probability(self, labels):
+        """labels [n, L] (relevance, pads = 0) -> P(click) [n, L] = exam_prob[min(rank, last)] * click_prob[label]."""
+        L = labels.shape[1]
+        exam = self.exam_prob[np.minimum(np.arange(L), len(self.exam_prob) - 1)]
+        rel = np.where(labels > 0, labels, 0).astype(np.int64)
+        rel = np.where(rel < len(self.click_prob), rel, len(self.click_prob) - 1)
+        return exam[None, :] * self.click_prob[rel]
+
+
+class ClickSimulationFeed(object):
+    MAX_SAMPLE_ROUND_NUM = 100
+
+    @staticmethod
+    def preprocess_data(data_set, hparam_str, exp_settings):
+        return
+
+    def __init__(self, model, batch_size, hparam_str):
+        self.hparams = HParams(
+            click_model_json='./example/ClickModel/pbm_0.1_1.0_4_1.0.json',    # click_simulation_feed.py:40-51
+            oracle_mode=False,
+            dynamic_bias_eta_change=0.0,
+            dynamic_bias_step_interval=1000,
+        )
+        print('Create simluated clicks feed')
+        print(hparam_str)
+        self.hparams.parse(hparam_str)
+        self.click_model = None
+        if not self.hparams.oracle_mode:
+            with open(self.hparams.click_model_json) as fin:
+                self.click_model = _PositionBiasedModel(json.load(fin))
+        self.start_index = 0
+        self.count = 1
+        self.rank_list_size = model.rank_list_size
+        self.feature_size = model.feature_size
+        self.batch_size = batch_size
+        self.model = model
+        self.global_batch_count = 0
+        self.rng = np.random.default_rng(random.getrandbits(63))
+        self._cache_key = None
+
+    # ---- array view of the data set (built once per data set) ------------------------------------------
+    def _arrays(self, data_set):
+        key = (id(data_set), len(data_set.initial_list), len(data_set.features), self.rank_list_size)
+        if self._cache_key != key:
+            L = self.rank_list_size
+            nq = len(data_set.initial_list)
+            init = np.full((nq, L), -1, dtype=np.int64)
+            labels = np.zeros((nq, L), dtype=np.float64)
+            for i in range(nq):
+                row = data_set.initial_list[i]
+                n = min(len(row), L)
+                init[i, :n] = row[:n]
+                lab = data_set.labels[i]
+                m = min(len(lab), n)
+                labels[i, :m] = lab[:m]
+            labels[init < 0] = 0.0                                         # click_simulation_feed.py:75-77
+            self._init = init
+            self._labels = labels
+            self._features = np.asarray(data_set.features, dtype=np.float64)
+            self._cache_key = key
+        return self._init, self._labels, self._features
+
+    def _simulate(self, labels):
+        if self.hparams.oracle_mode:
+            return labels.copy()
+        p = self.click_model.click_probability(labels)
+        return (self.rng.random(labels.shape) < p).astype(np.float64)
+
+    def _assemble(self, idx, clicks):
+        """idx [b] query indices, clicks [b, L] -> (input_feed, info_map) in the reference's format."""
+        init, _, features = self._init, self._labels, self._features
+        L = self.rank_list_size
+        rows = init[idx]                                                   # [b, L]
+        real = rows >= 0
+        n_real = real.sum(axis=1)
+        base = np.concatenate([[0], np.cumsum(n_real)[:-1]])
+        n_docs = int(n_real.sum())
+        letor_features = features[rows[real]]                              # real docs, list by list, in order
+        docid = np.where(real, base[:, None] + np.arange(L)[None, :], n_docs)   # base + x ; PAD id = n_docs
+        input_feed = {self.model.letor_features_name: letor_features}
+        docid_f = np.ascontiguousarray(docid.T.astype(np.float32))         # [L, b]
+        label_f = np.ascontiguousarray(clicks.T.astype(np.float32))
+        for l in range(L):
+            input_feed[self.model.docid_inputs_name[l]] = docid_f[l]
+            input_feed[self.model.labels_name[l]] = label_f[l]
+        return input_feed, docid, n_docs
+
+    def _check_list_size(self, data_set):
+        if len(data_set.initial_list[0]) < self.rank_list_size:
+            raise ValueError("Input ranklist length must be no less than the required list size,"
+                             " %d != %d." % (len(data_set.initial_list[0]), self.rank_list_size))
+
+    # ---- reference API ----------------------------------------------------------------------------------------
+    def get_batch(self, data_set, check_validation=False, data_format="ULTRA"):
+        """Random batch for training (click_simulation_feed.py:101-174): draws queries uniformly with replacement and,
+        with check_validation, keeps only lists with at least one click until batch_size lists are collected."""
+        self._check_list_size(data_set)
+        init, labels, _ = self._arrays(data_set)
+        length = init.shape[0]
+        B = self.batch_size
+        sel_idx, sel_clicks, have = [], [], 0
+        rounds = 0
+        while have < B:
+            n_try = max(8, int((B - have) * 1.5) + 4)
+            cand = (self.rng.random(n_try) * length).astype(np.int64)
+            clicks = self._simulate(labels[cand])
+            keep = clicks.sum(axis=1) > 0 if check_validation else np.ones(n_try, dtype=bool)
+            cand, clicks = cand[keep][:B - have], clicks[keep][:B - have]
+            sel_idx.append(cand)
+            sel_clicks.append(clicks)
+            have += len(cand)
+            rounds += 1
+            if rounds > 10000:
+                raise RuntimeError("could not sample %d lists with clicks" % B)
+        idx = np.concatenate(sel_idx)
+        clicks = np.concatenate(sel_clicks, axis=0)
+        input_feed, docid, _ = self._assemble(idx, clicks)
+        info_map = {
+            'rank_list_idxs': idx.tolist(),
+            'input_list': docid,
+            'click_list': clicks,
+            'letor_features': input_feed[self.model.letor_features_name],
+        }
+        self.global_batch_count += 1
+        if self.hparams.dynamic_bias_eta_change != 0 and not self.hparams.oracle_mode:
+            if self.global_batch_count % self.hparams.dynamic_bias_step_interval == 0:
+                self.click_model.eta += self.hparams.dynamic_bias_eta_change
+                self.click_model.setExamProb(self.click_model.eta)
+                print('Dynamically change bias severity eta to %.3f' % self.click_model.eta)
+        return input_feed, info_map
+
+    def _sequential(self, data_set, indices, check_validation):
+        self._check_list_size(data_set)
+        _, labels, _ = self._arrays(data_set)
+        idx = np.asarray(indices, dtype=np.int64)
+        clicks = self._simulate(labels[idx])
+        if check_validation:
+            keep = clicks.sum(axis=1) > 0
+            idx, clicks = idx[keep], clicks[keep]
+        input_feed, docid, _ = self._assemble(idx, clicks)
+        return input_feed, {'input_list': docid, 'click_list': clicks}
+
+    def get_next_batch(self, index, data_set, check_validation=False, data_format="ULTRA"):
+        """Sequential batch starting at `index` (click_simulation_feed.py:176-241)."""
+        n = min(self.batch_size, len(data_set.initial_list) - index)
+        return self._sequential(data_set, range(index, index + n), check_validation)
+
+    def get_data_by_index(self, data_set, index, check_validation=False):
+        """click_simulation_feed.py:243-294."""
+        return self._sequential(data_set, [index], check_validation)
