@@ -65,6 +65,12 @@ UB200_API int ub200_pack_feed_host(const double* feats_host, int n_docs, int F, 
                          const float* const* label_cols_host, int L, int B, void* dst_host, size_t dst_bytes,
                          int n_threads);
 
+/* the same packing in two pieces, for a pipelined pack (convert a chunk of rows, start its H2D copy, convert the
+ * next chunk): ids/labels part of the layout above, and a plain multi-threaded f64 -> f32 conversion */
+UB200_API int ub200_pack_ids_host(const float* const* docid_cols_host, const float* const* label_cols_host, int L, int B,
+                        void* dst_host, size_t dst_bytes);
+UB200_API int ub200_convert_f64_f32_host(const double* src_host, float* dst_host, size_t n, int n_threads);
+
 /* ---- K1: DNN ranker forward / backward ----------------------------------------------------------------
  * Replaces: host gather base_algorithm.py:148-152, cat + f64->f32 cast DNN.py:72-73, the nn.Sequential of
  * [LayerNorm -> Linear -> ELU] x n_hidden + LayerNorm -> Linear(1) DNN.py:43-55,77, split/cat DNN.py:87-88 +

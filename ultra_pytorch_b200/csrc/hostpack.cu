@@ -48,3 +48,34 @@ extern "C" UB200_API int ub200_pack_feed_host(const double* feats, int n_docs, i
     }
     return 0;
 }
+
+// Pieces of ub200_pack_feed_host for a pipelined pack: the caller converts the feature rows in a few chunks and
+// issues the H2D copy of chunk i while chunk i+1 is being converted.
+extern "C" UB200_API int ub200_pack_ids_host(const float* const* docid_cols, const float* const* label_cols, int L,
+                                             int B, void* dst, size_t dst_bytes) {
+    UB_CHECK(dst && docid_cols && label_cols && L > 0 && B > 0, 2, "pack_ids_host: bad arguments");
+    UB_CHECK(dst_bytes >= (size_t)8 * L * B, 3, "pack_ids_host: destination too small");
+    int32_t* docid = reinterpret_cast<int32_t*>(dst);
+    float* labels = reinterpret_cast<float*>(static_cast<char*>(dst) + (size_t)4 * L * B);
+    for (int l = 0; l < L; ++l) {
+        const float* d = docid_cols[l];
+        const float* y = label_cols[l];
+        for (int b = 0; b < B; ++b) {
+            docid[(size_t)l * B + b] = (int32_t)d[b];
+            labels[(size_t)b * L + l] = y[b];
+        }
+    }
+    return 0;
+}
+
+extern "C" UB200_API int ub200_convert_f64_f32_host(const double* src, float* dst, size_t n, int n_threads) {
+    UB_CHECK((src && dst) || n == 0, 2, "convert_f64_f32_host: null pointer");
+    if (n_threads < 1) n_threads = 1;
+    const long long nn = (long long)n, blk = 16384, nblk = (nn + blk - 1) / blk;
+#pragma omp parallel for num_threads(n_threads) schedule(static)
+    for (long long b = 0; b < nblk; ++b) {
+        const long long lo = b * blk, hi = lo + blk < nn ? lo + blk : nn;
+        for (long long i = lo; i < hi; ++i) dst[i] = (float)src[i];
+    }
+    return 0;
+}

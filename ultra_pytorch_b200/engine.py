@@ -57,6 +57,7 @@ class RankerEngine(object):
         self._pin = None
         self._dev = None
         self._pack_threads = int(os.environ.get("UB200_PACK_THREADS", str(min(8, os.cpu_count() or 1))))
+        self._pack_chunks = int(os.environ.get("UB200_PACK_CHUNKS", "4"))
         self._scores = {}
         self._dscores = {}
 
@@ -130,18 +131,35 @@ class RankerEngine(object):
             self._pin = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
             self._dev = torch.empty(cap, dtype=torch.uint8, device=self.device)
             self._pin_np = self._pin.numpy()
-        fast = (feats.dtype == np.float64 and feats.flags.c_contiguous and n_docs > 0 and
-                all(isinstance(x, np.ndarray) and x.dtype == np.float32 and x.flags.c_contiguous and len(x) == B
-                    for x in docid_arrays) and
-                all(isinstance(x, np.ndarray) and x.dtype == np.float32 and x.flags.c_contiguous and len(x) == B
-                    for x in label_arrays))
+        def _f32_vec(x):
+            return isinstance(x, np.ndarray) and x.dtype == np.float32 and x.flags.c_contiguous and x.shape == (B,)
+        # feeds emit homogeneous per-position arrays (click_simulation_feed.py:141-150): checking the ends is enough
+        fast = (feats.dtype == np.float64 and feats.flags.c_contiguous and n_docs > 0 and feats.shape[1] == self.F and
+                _f32_vec(docid_arrays[0]) and _f32_vec(docid_arrays[-1]) and _f32_vec(label_arrays[0]) and
+                _f32_vec(label_arrays[-1]))
         if fast:
-            # multi-threaded C packer (f64 -> f32 cast, docid -> int32, label transpose) straight into pinned memory
+            # C packer straight into pinned memory, pipelined with the H2D copy: ids/labels first, then the feature rows
+            # in a few chunks (f64 -> f32 on `_pack_threads` host threads); the copy of chunk i overlaps the conversion
+            # of chunk i+1.  All copies are on the current stream, so the kernels that follow see complete data.
             PtrArr = ctypes.c_void_p * L
             dptr = PtrArr(*[x.ctypes.data for x in docid_arrays])
             lptr = PtrArr(*[x.ctypes.data for x in label_arrays])
-            check(lib.ub200_pack_feed_host(feats.ctypes.data, n_docs, self.F, dptr, lptr, L, B, self._pin.data_ptr(),
-                                           self._pin.numel(), self._pack_threads), "ub200_pack_feed_host")
+            pin_ptr = self._pin.data_ptr()
+            check(lib.ub200_pack_ids_host(dptr, lptr, L, B, pin_ptr, self._pin.numel()), "ub200_pack_ids_host")
+            self._dev[:2 * off_l].copy_(self._pin[:2 * off_l], non_blocking=True)
+            self._pin_np[off_f + 4 * n_docs * self.F:total] = 0            # the PAD row
+            src = feats.ctypes.data
+            n_chunks = self._pack_chunks if n_docs * self.F >= (1 << 18) else 1
+            rows_per = (n_docs + n_chunks - 1) // n_chunks
+            for r0 in range(0, n_docs, rows_per):
+                r1 = min(n_docs, r0 + rows_per)
+                e0, e1 = r0 * self.F, r1 * self.F
+                check(lib.ub200_convert_f64_f32_host(src + 8 * e0, pin_ptr + off_f + 4 * e0, e1 - e0,
+                                                     self._pack_threads), "ub200_convert_f64_f32_host")
+                b0 = off_f + 4 * e0
+                b1 = total if r1 == n_docs else off_f + 4 * e1
+                self._dev[b0:b1].copy_(self._pin[b0:b1], non_blocking=True)
+            return self.staged_views(self._dev, L, B, n_docs)
         else:
             buf = self._pin_np
             hd = buf[:off_l].view(np.int32).reshape(L, B)

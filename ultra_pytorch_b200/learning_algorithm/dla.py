@@ -104,7 +104,8 @@ class DLA(B200Algorithm):
     def train(self, input_feed):
         """dla.py:179-266 + separate_gradient_update dla.py:141-177."""
         self.rank_list_size = self.exp_settings['selection_bias_cutoff']
-        self.model.train()
+        if not self.model.training:
+            self.model.train()
         st = self._stage(input_feed, self.rank_list_size)
         s = self._read_scalars(self.run_step(st))
         mg = self.hparams.max_gradient_norm

@@ -38,7 +38,8 @@ class LambdaRank(PairDebias):
         """lambda_rank.py:96-216."""
         self.rank_list_size = self.exp_settings['selection_bias_cutoff']
         self.global_step += 1
-        self.model.train()
+        if not self.model.training:
+            self.model.train()
         st = self._stage(input_feed, self.rank_list_size)
         s = self._read_scalars(self.run_step(st))
         self.loss = float(s[0] / s[1])

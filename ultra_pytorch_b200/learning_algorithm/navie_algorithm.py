@@ -54,7 +54,8 @@ class NavieAlgorithm(B200Algorithm):
     def train(self, input_feed):
         """navie_algorithm.py:76-120 / ipw_rank.py:102-182."""
         self.global_step += 1
-        self.model.train()
+        if not self.model.training:
+            self.model.train()
         st = self._stage(input_feed, self.rank_list_size)
         s = self._read_scalars(self.run_step(st))
         self.loss = float(s[0] / s[1])

@@ -67,7 +67,8 @@ class PairDebias(B200Algorithm):
 
     def train(self, input_feed):
         """pairwise_debias.py:106-174."""
-        self.model.train()
+        if not self.model.training:
+            self.model.train()
         st = self._stage(input_feed, self.rank_list_size)
         s = self._read_scalars(self.run_step(st))
         self.loss = float(s[0]) * self._b_global
