@@ -47,7 +47,8 @@ UB200_API int ub200_abi_version(void);
 UB200_API unsigned long long ub200_launch_count(void);
 /* K1 GEMM engine, a bit mask: 1 = forward, 2 = data-gradient, 4 = weight-gradient GEMMs of the hidden layers whose
  * shapes qualify (K % 4 == 0, N % 64 == 0) run on the tcgen05 tensor cores with 3xTF32 error compensation; cleared
- * bits use the CUDA-core fp32 kernels.  Default 7 (env UB200_TC overrides).  Both engines meet the same parity bound;
+* bits use the CUDA-core fp32 kernels; 8 = run the whole forward pass as ONE fused kernel when the net fits the
+ * tensor-memory plan (N_0 <= 256, N_j <= 128).  Default 15 (env UB200_TC overrides).  Both engines meet the same parity bound;
  * the switch exists for A/B tests and profiling.  Returns the previous mask. */
 UB200_API int ub200_set_tc_mode(int mode);
 /* number of parameters of the DNN ranker for (F, hidden[]) in the flat layout above */

@@ -19,12 +19,12 @@ namespace ub200 {
 
 // Bit mask: which GEMMs of the tensor-core friendly hidden layers run on tcgen05 (3xTF32): 1 = forward,
 // 2 = data gradient, 4 = weight gradient; 0 = CUDA-core fp32 kernels everywhere.  Default 7 (env UB200_TC overrides).
-enum { TC_FWD = 1, TC_DGRAD = 2, TC_WGRAD = 4 };
+enum { TC_FWD = 1, TC_DGRAD = 2, TC_WGRAD = 4, TC_FUSED_FWD = 8 };
 static int g_tc_mode = -1;
 static int tc_mode() {
     if (g_tc_mode < 0) {
         const char* e = getenv("UB200_TC");
-        g_tc_mode = e ? atoi(e) & 7 : 7;
+        g_tc_mode = e ? atoi(e) & 15 : 15;
     }
     return g_tc_mode;
 }
@@ -604,7 +604,7 @@ using namespace ub200;
 
 extern "C" UB200_API int ub200_set_tc_mode(int mode) {
     const int old = tc_mode();
-    g_tc_mode = mode & 7;
+    g_tc_mode = mode & 15;
     return old;
 }
 
@@ -639,6 +639,29 @@ extern "C" UB200_API int ub200_mlp_forward(const float* feats, const int32_t* do
     const float* X = feats;
     const int32_t* idx = docid;
     if (int rc = prep_tc_weights(d, w, params, training, st)) return rc;
+    if ((tc_mode() & TC_FUSED_FWD) && (tc_mode() & TC_FWD) && fused_forward_ok(F, d.N, d.n_layers - 1)) {
+        // whole forward pass in one kernel (activations stay in tensor memory between layers)
+        tc::FusedArgs fa{};
+        fa.M = M; fa.L = L; fa.B = B; fa.n_hidden = d.n_layers - 1; fa.K0 = F;
+        fa.feats = feats; fa.docid = docid;
+        for (int j = 0; j < d.n_layers; ++j) {
+            fa.gamma[j] = params + d.off_g[j];
+            fa.beta[j] = params + d.off_b[j];
+            fa.stats[j] = w.stats[j];
+            if (j + 1 < d.n_layers) {
+                fa.N[j] = d.N[j];
+                fa.bias[j] = params + d.off_c[j];
+                fa.wimg_hi[j] = w.wf_hi[j];
+                fa.wimg_lo[j] = w.wf_lo[j];
+                fa.Y[j] = w.Y[j];
+            }
+        }
+        fa.w_final = params + d.off_w[d.n_layers - 1];
+        fa.c_final = params + d.off_c[d.n_layers - 1];
+        fa.scores = scores;
+        fa.write_acts = training ? 1 : 0;
+        return fused_forward(fa, st);
+    }
     for (int j = 0; j < d.n_layers; ++j) {
         const int K = d.K[j], N = d.N[j];
         const float* g = params + d.off_g[j];

@@ -30,8 +30,30 @@ struct PrepTable {
     float* wd_lo[UB200_MAX_LAYERS];
     int K[UB200_MAX_LAYERS], N[UB200_MAX_LAYERS], Kpad[UB200_MAX_LAYERS], Npad[UB200_MAX_LAYERS];
 };
+// arguments of the fully fused forward kernel (mlp_fused.cu)
+struct FusedArgs {
+    int M, L, B;                                  // rows = L * B, scores are [B, L]
+    int n_hidden;                                 // hidden layers (>= 1)
+    int K0;                                       // feature size
+    int N[UB200_MAX_LAYERS];                      // hidden sizes
+    const float* feats;
+    const int32_t* docid;
+    const float* gamma[UB200_MAX_LAYERS];         // LayerNorm j (input of linear j), j = 0 .. n_hidden (final)
+    const float* beta[UB200_MAX_LAYERS];
+    const float* bias[UB200_MAX_LAYERS];          // hidden-layer biases
+    const float* wimg_hi[UB200_MAX_LAYERS];       // pre-split weight images (prep_weights_kernel)
+    const float* wimg_lo[UB200_MAX_LAYERS];
+    const float* w_final;                         // [N_last]
+    const float* c_final;                         // [1]
+    float* Y[UB200_MAX_LAYERS];                   // activations for the backward pass (write_acts)
+    float2* stats[UB200_MAX_LAYERS];              // LayerNorm statistics of every layer input (write_acts)
+    float* scores;
+    int write_acts;
+};
 }  // namespace tc
 
+bool fused_forward_ok(int F, const int* N, int n_hidden);
+int fused_forward(const tc::FusedArgs& a, cudaStream_t st);
 bool tc_layer_ok(int j, int K, int N);
 int tc_prep(const tc::PrepTable& t, int max_elems, cudaStream_t st);
 int tc_forward_layer(const tc::TcArgs& a, cudaStream_t st);
