@@ -639,30 +639,17 @@ extern "C" UB200_API int ub200_mlp_forward(const float* feats, const int32_t* do
     const float* X = feats;
     const int32_t* idx = docid;
     if (int rc = prep_tc_weights(d, w, params, training, st)) return rc;
-    if ((tc_mode() & TC_FUSED_FWD) && (tc_mode() & TC_FWD) && fused_forward_ok(F, d.N, d.n_layers - 1)) {
-        // whole forward pass in one kernel (activations stay in tensor memory between layers)
-        tc::FusedArgs fa{};
-        fa.M = M; fa.L = L; fa.B = B; fa.n_hidden = d.n_layers - 1; fa.K0 = F;
-        fa.feats = feats; fa.docid = docid;
-        for (int j = 0; j < d.n_layers; ++j) {
-            fa.gamma[j] = params + d.off_g[j];
-            fa.beta[j] = params + d.off_b[j];
-            fa.stats[j] = w.stats[j];
-            if (j + 1 < d.n_layers) {
-                fa.N[j] = d.N[j];
-                fa.bias[j] = params + d.off_c[j];
-                fa.wimg_hi[j] = w.wf_hi[j];
-                fa.wimg_lo[j] = w.wf_lo[j];
-                fa.Y[j] = w.Y[j];
-            }
-        }
-        fa.w_final = params + d.off_w[d.n_layers - 1];
-        fa.c_final = params + d.off_c[d.n_layers - 1];
-        fa.scores = scores;
-        fa.write_acts = training ? 1 : 0;
-        return fused_forward(fa, st);
+    // Fused tail: from the first layer j0 whose successors fit the tensor-memory plan (N_j0 <= 256, later N <= 128),
+    // ONE kernel runs the rest of the forward pass with the activations staying in tensor memory.  j0 = 0 for
+    // DNN[256,128,64]; j0 = 1 for the reference default DNN[512,256,128] (layer 0 runs as a per-layer GEMM).
+    const int nh = d.n_layers - 1;
+    int j0 = -1;
+    if ((tc_mode() & TC_FUSED_FWD) && (tc_mode() & TC_FWD)) {
+        if (fused_forward_ok(F, d.N, nh)) j0 = 0;
+        else if (nh >= 2 && fused_forward_ok(d.N[0], d.N + 1, nh - 1)) j0 = 1;
     }
-    for (int j = 0; j < d.n_layers; ++j) {
+    const int n_per_layer = (j0 >= 0) ? j0 : d.n_layers;
+    for (int j = 0; j < n_per_layer; ++j) {
         const int K = d.K[j], N = d.N[j];
         const float* g = params + d.off_g[j];
         const float* bt = params + d.off_b[j];
@@ -691,6 +678,29 @@ extern "C" UB200_API int ub200_mlp_forward(const float* feats, const int32_t* do
             X = w.Y[j];
             idx = nullptr;
         }
+    }
+    if (j0 >= 0) {
+        tc::FusedArgs fa{};
+        fa.M = M; fa.L = L; fa.B = B; fa.n_hidden = nh - j0; fa.K0 = d.K[j0];
+        fa.feats = X; fa.docid = idx;            // layer j0's input: the features (j0 = 0) or Y_{j0-1}
+        for (int j = j0; j < d.n_layers; ++j) {
+            const int q = j - j0;
+            fa.gamma[q] = params + d.off_g[j];
+            fa.beta[q] = params + d.off_b[j];
+            fa.stats[q] = w.stats[j];
+            if (j + 1 < d.n_layers) {
+                fa.N[q] = d.N[j];
+                fa.bias[q] = params + d.off_c[j];
+                fa.wimg_hi[q] = w.wf_hi[j];
+                fa.wimg_lo[q] = w.wf_lo[j];
+                fa.Y[q] = w.Y[j];
+            }
+        }
+        fa.w_final = params + d.off_w[d.n_layers - 1];
+        fa.c_final = params + d.off_c[d.n_layers - 1];
+        fa.scores = scores;
+        fa.write_acts = training ? 1 : 0;
+        return fused_forward(fa, st);
     }
     return 0;
 }
