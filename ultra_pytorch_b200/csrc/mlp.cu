@@ -75,7 +75,7 @@ static bool use_side_streams() {
 struct MlpWorkspace {
     float2* stats[UB200_MAX_LAYERS];   // (mean, rstd) of the input of layer j, [M]
     float* Y[UB200_MAX_LAYERS];        // output of hidden layer j (post-ELU) [M, N_j]
-    float* dz[2];                      // dZ_j ping-pong, [M, maxH] each (layer j reads dz[j & 1], writes dz[(j-1) & 1])
+    float* dz[3];                      // dZ_j rotation, [M, maxH] each (layer j reads dz[j % 3], writes dz[(j-1) % 3])
     float* dxh;                        // [M, maxH]
     float* partials[UB200_MAX_LAYERS];     // per layer: split-M partial weight gradients (layers run concurrently)
     float* fin_scratch[UB200_MAX_LAYERS];  // wgrad_finalize: per-block partial dgamma / dbeta
@@ -113,7 +113,7 @@ static void carve(const LayerDims& d, int M, int training, char* base, MlpWorksp
             w->Y[j] = reinterpret_cast<float*>(base + off);
             off = align_up(off + sizeof(float) * (size_t)M * d.N[j], 256);
         }
-        for (int q = 0; q < 2; ++q) {
+        for (int q = 0; q < 3; ++q) {
             w->dz[q] = reinterpret_cast<float*>(base + off);
             off = align_up(off + sizeof(float) * (size_t)M * maxH, 256);
         }
@@ -142,7 +142,7 @@ static void carve(const LayerDims& d, int M, int training, char* base, MlpWorksp
         float* b = reinterpret_cast<float*>(base + off);
         off = align_up(off + sizeof(float) * (size_t)M * maxH, 256);
         for (int j = 0; j + 1 < d.n_layers; ++j) w->Y[j] = (j & 1) ? b : a;
-        w->dz[0] = w->dz[1] = w->dxh = nullptr;
+        w->dz[0] = w->dz[1] = w->dz[2] = w->dxh = nullptr;
         for (int j = 0; j < UB200_MAX_LAYERS; ++j) {
             w->partials[j] = w->fin_scratch[j] = nullptr;
             w->fin_counters[j] = nullptr;
@@ -493,15 +493,17 @@ __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __rest
             for (int s = kx; s < S; s += 32) dpart += pn[(size_t)s * plane + K];
         dbn = warp_sum(dpart);
         if (n < N && k < K) {
-            float acc[8];
+            float acc[16];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+            for (int q = 0; q < 16; ++q) acc[q] = 0.f;
             int s = 0;
-            for (; s + 7 < S; s += 8) {
+            for (; s + 15 < S; s += 16) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) acc[q] += pn[(size_t)(s + q) * plane + k];
+                for (int q = 0; q < 16; ++q) acc[q] += pn[(size_t)(s + q) * plane + k];
             }
-            for (; s < S; ++s) acc[0] += pn[(size_t)s * plane + k];
+            for (; s < S; ++s) acc[s & 15] += pn[(size_t)s * plane + k];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] += acc[q + 8];
             g = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
         }
     }
@@ -736,7 +738,7 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
         if (ss) cudaStreamWaitEvent(st, ss->done_ev[j], 0);
     };
 
-    // final layer (N = 1): dZ_{nl-2} goes to dz[(nl-2) & 1]
+    // final layer (N = 1): dZ_{nl-2} goes to dz[(nl-2) % 3]
     {
         const int j = nl - 1, K = d.K[j];
         const float* X = (j == 0) ? feats : w.Y[j - 1];
@@ -749,7 +751,7 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
             cudaFuncSetAttribute(final_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         final_bwd_kernel<<<blocks, 256, smem, st>>>(X, idx, w.stats[j], M, K, params + d.off_g[j],
                                                     params + d.off_w[j], dscores, L, B,
-                                                    (j == 0) ? nullptr : w.dz[(j - 1) & 1], w.partials[j]);
+                                                    (j == 0) ? nullptr : w.dz[(j - 1) % 3], w.partials[j]);
         UB_LAUNCH_CHECK("final_bwd_kernel");
         cudaStream_t sb = fork(j);
         final_finalize_kernel<<<(K + 31) / 32, 256, 0, sb>>>(w.partials[j], blocks, K, params + d.off_w[j],
@@ -759,7 +761,7 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
         UB_LAUNCH_CHECK("final_finalize_kernel");
         branch_done(j);
     }
-    // hidden layers, last to first; dz[j & 1] holds dZ_j [M, N_j]
+    // hidden layers, last to first; dz[j % 3] holds dZ_j [M, N_j]
     for (int j = nl - 2; j >= 0; --j) {
         const int K = d.K[j], N = d.N[j];
         const float* X = (j == 0) ? feats : w.Y[j - 1];
@@ -767,7 +769,7 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
         const float* g = params + d.off_g[j];
         const float* bt = params + d.off_b[j];
         const float* W = params + d.off_w[j];
-        const float* dz = w.dz[j & 1];
+        const float* dz = w.dz[j % 3];
         // ---- weight-gradient branch (side stream): G[n, k] (k == K -> db) split over row chunks, then finalize ----
         cudaStream_t sb = fork(j);
         int S_eff, ldp;
@@ -801,10 +803,21 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
         branch_done(j);
         // ---- data-gradient chain (caller's stream) ----
         if (j > 0) {
-            if (use_tc(j, K, N, TC_DGRAD)) {
+            // dZ_{j-1} goes to dz[(j-1) % 3], the buffer dZ_{j+2} lived in: that layer's weight-gradient branch (forked
+            // two layers ago) must have finished reading it
+            const bool tc_d = use_tc(j, K, N, TC_DGRAD);
+            const bool fuse = tc_d && (K == 64 || K == 128 || K == 256);   // one column tile -> LN-backward in the epilogue
+            if (fuse && j + 2 <= nl - 2) wait_branch(j + 2);
+            if (tc_d) {
                 tc::TcArgs t{};
                 t.M = M; t.K = K; t.N = N; t.dZ = dz; t.Bhi = w.wd_hi[j]; t.Blo = w.wd_lo[j];
-                t.ldb = K; t.out = w.dxh; t.ldo = K;
+                t.ldb = K;
+                if (fuse) {
+                    t.fuse_lnbwd = 1; t.X = X; t.stats = w.stats[j];
+                    t.out = w.dz[(j - 1) % 3]; t.ldo = K;
+                } else {
+                    t.out = w.dxh; t.ldo = K;
+                }
                 if (int rc = tc_dgrad_layer(t, st)) return rc;
             } else {
                 GemmArgs b{};
@@ -813,10 +826,11 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
                 launch_gemm<MODE_DGRAD>(b, 1, st);
                 UB_LAUNCH_CHECK("gemm_kernel<DGRAD>");
             }
-            // dZ_{j-1} overwrites the buffer dZ_{j+1} lived in: its weight-gradient branch must have finished
-            if (j + 1 <= nl - 2) wait_branch(j + 1);
-            ln_bwd_elu_kernel<<<row_blocks, 256, 0, st>>>(w.dxh, X, w.stats[j], M, K, w.dz[(j - 1) & 1]);
-            UB_LAUNCH_CHECK("ln_bwd_elu_kernel");
+            if (!fuse) {
+                if (j + 2 <= nl - 2) wait_branch(j + 2);
+                ln_bwd_elu_kernel<<<row_blocks, 256, 0, st>>>(w.dxh, X, w.stats[j], M, K, w.dz[(j - 1) % 3]);
+                UB_LAUNCH_CHECK("ln_bwd_elu_kernel");
+            }
         }
     }
     for (int j = 0; j < nl; ++j) wait_branch(j);    // join every branch

@@ -370,16 +370,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
         } else {
             row_limit = a.N; col_limit = a.ldo;
         }
-        float* out_base = a.out;
-        if (KIND == KIND_WGRAD) out_base += (size_t)blockIdx.z * a.N * a.ldo;
-        constexpr int CPR = BLOCK_N / 4;                    // 16-byte chunks per tile row
+        if (KIND == KIND_DGRAD && a.fuse_lnbwd) {
+            // fused LayerNorm backward + ELU': the tile holds dXhat for FULL rows (BLOCK_N == K).  One warp per row:
+            //   dX = rstd * (dXhat - mean_k(dXhat) - xhat * mean_k(dXhat * xhat)),  dZ_prev = dX * ELU'(x)
+            for (int r = warp; r < BLOCK_M; r += NPROD / 32) {
+                const int grow = i0 + r;
+                if (grow >= a.M) break;
+                const float* x = a.X + (size_t)grow * a.K;
+                const float* g = stile + (size_t)r * TS;
+                const float2 st = a.stats[grow];
+                float s1 = 0.f, s2 = 0.f;
+                for (int k = lane; k < a.K; k += 32) {
+                    const float xh = (x[k] - st.x) * st.y;
+                    const float d = g[k];
+                    s1 += d;
+                    s2 = fmaf(d, xh, s2);
+                }
+                s1 = warp_sum(s1) / (float)a.K;
+                s2 = warp_sum(s2) / (float)a.K;
+                for (int k = lane; k < a.K; k += 32) {
+                    const float xv = x[k];
+                    const float xh = (xv - st.x) * st.y;
+                    const float dx = st.y * (g[k] - s1 - xh * s2);
+                    a.out[(size_t)grow * a.ldo + k] = dx * elu_grad_from_out(xv);
+                }
+            }
+        } else {
+            float* out_base = a.out;
+            if (KIND == KIND_WGRAD) out_base += (size_t)blockIdx.z * a.N * a.ldo;
+            constexpr int CPR = BLOCK_N / 4;                    // 16-byte chunks per tile row
 #pragma unroll 4
-        for (int idx = tid; idx < BLOCK_M * CPR; idx += NPROD) {
-            const int r = idx / CPR, ch = idx % CPR;
-            const int grow = i0 + r, gcol = j0 + ch * 4;
-            if (grow < row_limit && gcol < col_limit)         // limits are multiples of 4
-                *reinterpret_cast<float4*>(out_base + (size_t)grow * a.ldo + gcol) =
-                    *reinterpret_cast<const float4*>(stile + (size_t)r * TS + ch * 4);
+            for (int idx = tid; idx < BLOCK_M * CPR; idx += NPROD) {
+                const int r = idx / CPR, ch = idx % CPR;
+                const int grow = i0 + r, gcol = j0 + ch * 4;
+                if (grow < row_limit && gcol < col_limit)         // limits are multiples of 4
+                    *reinterpret_cast<float4*>(out_base + (size_t)grow * a.ldo + gcol) =
+                        *reinterpret_cast<const float4*>(stile + (size_t)r * TS + ch * 4);
+            }
         }
     }
     if (tid == 0) TC_STAMP(5);
@@ -499,7 +526,7 @@ int tc_forward_layer(const tc::TcArgs& a, cudaStream_t st) {
 
 int tc_dgrad_layer(const tc::TcArgs& a, cudaStream_t st) {
     const int row_tiles = (a.M + tc::BLOCK_M - 1) / tc::BLOCK_M;
-    const int bn = tc::pick_block_n(a.K, row_tiles);
+    const int bn = a.fuse_lnbwd ? a.K : tc::pick_block_n(a.K, row_tiles);   // fused LN-backward needs full rows
     cudaError_t e = tc::launch_kind<tc::KIND_DGRAD>(a, bn, dim3(row_tiles, a.K / bn, 1), st);
     count_launch();
     UB_CHECK(e == cudaSuccess, 100, "tc_gemm_kernel<DGRAD> launch failed: %s", cudaGetErrorString(e));

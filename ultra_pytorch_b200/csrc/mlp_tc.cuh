@@ -19,6 +19,9 @@ struct TcArgs {
     float* out;
     int ldo;
     int rows_per_split;
+    // DGRAD with one column tile (BLOCK_N == K): fuse LayerNorm-backward . ELU' into the epilogue and write dZ_{j-1}
+    // directly (X = Y_{j-1} is both the LayerNorm input and the ELU output; stats = its row statistics)
+    int fuse_lnbwd;
 };
 struct PrepTable {
     int n;
