@@ -60,7 +60,7 @@ UB200_API size_t ub200_mlp_param_count(int F, const int* hidden, int n_hidden);
  * H2D copy of ub200_feed_bytes bytes):
  *     docid int32 [L, B] (position-major) | labels f32 [B, L] | pad to 256 B | feats f32 [n_docs + 1, F] (PAD row = 0)
  * feats_host: f64 [n_docs, F] row-major; docid_cols_host / label_cols_host: L pointers to f32 [B] (the feed's
- * "docid_input{l}" / "label{l}" arrays).  Multi-threaded with OpenMP (n_threads). */
+ * "docid_input{l}" / "label{l}" arrays).  Multi-threaded (n_threads, persistent worker pool). */
 UB200_API size_t ub200_feed_bytes(int n_docs, int F, int L, int B);
 UB200_API int ub200_pack_feed_host(const double* feats_host, int n_docs, int F, const float* const* docid_cols_host,
                          const float* const* label_cols_host, int L, int B, void* dst_host, size_t dst_bytes,
@@ -71,6 +71,14 @@ UB200_API int ub200_pack_feed_host(const double* feats_host, int n_docs, int F, 
 UB200_API int ub200_pack_ids_host(const float* const* docid_cols_host, const float* const* label_cols_host, int L, int B,
                         void* dst_host, size_t dst_bytes);
 UB200_API int ub200_convert_f64_f32_host(const double* src_host, float* dst_host, size_t n, int n_threads);
+
+/* ub200_pack_feed_host into the PINNED buffer `pinned_host` + the H2D copy to `device_dst` on `stream`, pipelined: the
+ * feature rows are converted on a persistent pool of n_threads host threads (the caller included) and the copy of each of
+ * the n_groups groups of rows is enqueued as soon as the group is converted.  Returns when the last copy has been
+ * enqueued; kernels launched on `stream` afterwards see the complete feed (the one H2D transfer of a train() call). */
+UB200_API int ub200_stage_feed(const double* feats_host, int n_docs, int F, const float* const* docid_cols_host,
+                     const float* const* label_cols_host, int L, int B, void* pinned_host, size_t pinned_bytes,
+                     void* device_dst, int n_threads, int n_groups, void* stream);
 
 /* ---- K1: DNN ranker forward / backward ----------------------------------------------------------------
  * Replaces: host gather base_algorithm.py:148-152, cat + f64->f32 cast DNN.py:72-73, the nn.Sequential of

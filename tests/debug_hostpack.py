@@ -30,6 +30,23 @@ ts = []
 for _ in range(30):
     torch.cuda.synchronize(); t0 = time.perf_counter(); dev.copy_(pin, non_blocking=True); torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
 print("H2D %d bytes median %.3f ms (%.1f GB/s)" % (nb, 1e3 * sorted(ts)[15], nb / sorted(ts)[15] / 1e9))
+# pipelined pack + H2D in one call, on 8 rotating (cache-cold) feeds
+cold = [synth.make_feed(100 + i, F, L, B) for i in range(8)]
+st = torch.cuda.current_stream().cuda_stream
+for nt in (4, 8, 16):
+    for ng in (1, 4, 6, 12):
+        ts, te = [], []
+        for it in range(40):
+            fd = cold[it % 8]
+            fe = fd["letor_features"]
+            dd = [fd["docid_input%d" % l] for l in range(L)]; yy = [fd["label%d" % l] for l in range(L)]
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            dptr = PtrArr(*[x.ctypes.data for x in dd]); lptr = PtrArr(*[x.ctypes.data for x in yy])
+            lib.ub200_stage_feed(fe.ctypes.data, n, F, dptr, lptr, L, B, pin.data_ptr(), nb, dev.data_ptr(), nt, ng, st)
+            t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+            ts.append(t1 - t0); te.append(t2 - t0)
+        print("stage_feed nt=%2d groups=%2d: enqueue %.3f ms, data on device after %.3f ms" %
+              (nt, ng, 1e3 * sorted(ts)[20], 1e3 * sorted(te)[20]))
 
 # ---- per-phase cost of train() ----
 import types, cProfile, pstats

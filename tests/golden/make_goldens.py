@@ -45,6 +45,9 @@ CASES = [
     ("lambdarank_click", "lambdarank", 10, 7, 9, 6, [16, 8], "click", 2),
     ("ipw_c2like", "ipw", 136, 40, 40, 16, [256, 128, 64], "click", 1),
     ("dla_wide", "dla", 72, 20, 20, 12, [128, 64, 32], "click", 1),
+    # hidden == [] selects the reference's Linear ranker (ultra/ranking_model/Linear.py: LayerNorm -> Linear(F, 1))
+    ("ipw_linear", "ipw", 10, 6, 8, 8, [], "click", 3),
+    ("lambdarank_linear", "lambdarank", 14, 7, 7, 6, [], "graded", 2),
 ]
 
 
@@ -99,8 +102,8 @@ def run_case(ultra, name, algo, F, L_train, L_max, B, hidden, kind, n_steps):
     exp_settings = {
         "learning_algorithm": ALGOS[algo],
         "learning_algorithm_hparams": "",
-        "ranking_model": "ultra.ranking_model.DNN",
-        "ranking_model_hparams": "hidden_layer_sizes=%s" % str(hidden),
+        "ranking_model": "ultra.ranking_model.DNN" if hidden else "ultra.ranking_model.Linear",
+        "ranking_model_hparams": ("hidden_layer_sizes=%s" % str(hidden)) if hidden else "",
         "selection_bias_cutoff": L_train,
         "max_candidate_num": L_max,
         "metrics": ["ndcg", "err", "mrr"],

@@ -109,3 +109,38 @@ def test_metrics_match_reference_module_when_available():
         ours = m.make_ranking_metric_fn(metric, [1, 3, 5, 10])(labels, scores, None)
         ref = ultra.utils.make_ranking_metric_fn(metric, [1, 3, 5, 10])(labels, scores, None)
         assert torch.equal(torch.as_tensor(ours), torch.as_tensor(ref)), metric
+
+
+def test_host_packer_pool_is_exact_for_any_size_and_thread_count():
+    """csrc/hostpack.cpp: the f64 -> f32 conversion on the persistent worker pool (AVX2 + streaming stores, scalar
+    head/tail) equals numpy's cast bit for bit for ragged sizes, unaligned destinations, any thread count, and after
+    the workers went to sleep; the packed feed has the documented layout."""
+    import ctypes
+    import time
+    from ultra_pytorch_b200 import _capi
+    lib = _capi.lib
+    rs = np.random.RandomState(0)
+    for trial in range(120):
+        n = int(rs.randint(1, 300000)) if trial % 3 else int(rs.randint(1, 70))
+        src = rs.randn(n) * 10.0 ** rs.randint(-3, 3)
+        off = int(rs.randint(0, 8))
+        buf = np.empty(n + 8, np.float32)
+        dst = buf[off:off + n]
+        assert lib.ub200_convert_f64_f32_host(src.ctypes.data, dst.ctypes.data, n, int(rs.randint(1, 9))) == 0
+        assert np.array_equal(dst, src.astype(np.float32)), (trial, n)
+    F, L, B = 24, 7, 33
+    n = 200
+    feats = rs.uniform(-1, 1, (n, F))
+    d = [rs.randint(0, n + 1, B).astype(np.float32) for _ in range(L)]
+    y = [rs.rand(B).astype(np.float32) for _ in range(L)]
+    nb = lib.ub200_feed_bytes(n, F, L, B)
+    out = np.full(nb, 255, np.uint8)
+    PtrArr = ctypes.c_void_p * L
+    time.sleep(0.05)                       # the pool's workers fall asleep after ~2 ms without work
+    assert lib.ub200_pack_feed_host(feats.ctypes.data, n, F, PtrArr(*[x.ctypes.data for x in d]),
+                                    PtrArr(*[x.ctypes.data for x in y]), L, B, out.ctypes.data, nb, 4) == 0
+    off_f = (8 * L * B + 255) // 256 * 256
+    hf = out[off_f:].view(np.float32).reshape(n + 1, F)
+    assert np.array_equal(hf[:n], feats.astype(np.float32)) and not hf[n].any()
+    assert np.array_equal(out[:4 * L * B].view(np.int32).reshape(L, B), np.stack(d).astype(np.int32))
+    assert np.array_equal(out[4 * L * B:8 * L * B].view(np.float32).reshape(B, L), np.stack(y).T)

@@ -47,8 +47,9 @@ def build_from_golden(g, tmp_path):
         hp = "propensity_estimator_json=%s" % p
     exp_settings = {
         "learning_algorithm_hparams": hp,
-        "ranking_model": "ultra_pytorch_b200.ranking_model.DNN",
-        "ranking_model_hparams": "hidden_layer_sizes=%s" % str([int(h) for h in g["meta_hidden"]]),
+        "ranking_model": "ultra_pytorch_b200.ranking_model.%s" % ("DNN" if len(g["meta_hidden"]) else "Linear"),
+        "ranking_model_hparams": ("hidden_layer_sizes=%s" % str([int(h) for h in g["meta_hidden"]]))
+        if len(g["meta_hidden"]) else "",
         "selection_bias_cutoff": int(g["meta_L_train"]),
         "max_candidate_num": int(g["meta_L_max"]),
         "metrics": ["ndcg", "err", "mrr"],

@@ -17,21 +17,29 @@ LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libultra_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-fopenmp", "--cudart", "static"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--cudart", "static"]
 FLAGS = [f for f in FLAGS if f != "--use_fast_math=false"]
+
+
+CXX = os.environ.get("CXX", "g++")
+CXXFLAGS = ["-O3", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-pthread", "-I/usr/local/cuda/include"]
 
 
 def _sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+def _host_sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cpp")))
+
+
 def _fingerprint():
     h = hashlib.sha256()
-    for p in _sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + \
+    for p in _sources() + _host_sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + \
             [os.path.join(os.path.dirname(HERE), "include", "ultra_b200.h")]:
         with open(p, "rb") as f:
             h.update(f.read())
-    h.update(" ".join(FLAGS).encode())
+    h.update(" ".join(FLAGS + CXXFLAGS).encode())
     return h.hexdigest()
 
 
@@ -47,7 +55,12 @@ def build(force=False, verbose=False):
         cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         subprocess.check_call(cmd)
         objs.append(obj)
-    cmd = [NVCC, "-shared", "-o", LIBPATH] + objs + ["--cudart", "static", "-lcuda", "-Xcompiler", "-fopenmp"]
+    for src in _host_sources():      # host-only code (the feed packer): plain g++
+        obj = os.path.join(LIBDIR, os.path.basename(src)[:-4] + ".host.o")
+        subprocess.check_call([CXX] + CXXFLAGS + ["-c", src, "-o", obj])
+        objs.append(obj)
+    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIBPATH] + objs + \
+        ["--cudart", "static", "-lcuda", "-Xcompiler", "-pthread"]
     subprocess.check_call(cmd)
     with open(stamp, "w") as f:
         f.write(fp)

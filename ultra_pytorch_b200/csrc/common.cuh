@@ -34,6 +34,54 @@ void count_launch();
         }                                                                                  \
     } while (0)
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------------
+// Every kernel of the step calls griddep_launch() first (the next kernel of the stream / graph may start being
+// scheduled once ALL blocks of this grid have started, i.e. it only takes SMs this grid leaves idle) and
+// griddep_wait() after its own on-chip set-up (barrier init, tensor-memory allocation) and BEFORE its first access
+// to global memory: the wait returns when every prerequisite grid has completed and flushed, so the data flow is
+// exactly that of ordinary stream order while launch latency and prologues overlap the previous kernel's tail.
+// Both are no-ops when the kernel was launched without the programmatic attribute.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();     // UB200_PDL (default off: graph kernel-to-kernel gaps measured ~0.1 us, nothing to hide), optim.cu
+// Launch priority of the kernels launched by this host thread from now on (0 = default).  The backward pass gives
+// the data-gradient chain (the critical path) the greatest priority and the weight-gradient side branches the
+// least, so that when both are pending the block scheduler places the critical kernel's CTAs first.
+int& launch_priority();
+struct PriorityScope {
+    int saved;
+    explicit PriorityScope(int p) : saved(launch_priority()) { launch_priority() = p; }
+    ~PriorityScope() { launch_priority() = saved; }
+};
+
+// <<<grid, block, smem, st>>> with the programmatic-stream-serialization attribute when PDL is enabled
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    unsigned n_at = 0;
+    if (pdl_enabled()) {
+        at[n_at].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n_at].val.programmaticStreamSerializationAllowed = 1;
+        ++n_at;
+    }
+    if (launch_priority() != 0) {
+        at[n_at].id = cudaLaunchAttributePriority;
+        at[n_at].val.priority = launch_priority();
+        ++n_at;
+    }
+    cfg.attrs = n_at ? at : nullptr;
+    cfg.numAttrs = n_at;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(static_cast<Args&&>(args))...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

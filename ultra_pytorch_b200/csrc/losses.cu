@@ -54,6 +54,8 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict
                                                           float* __restrict__ sums, unsigned int* counter,
                                                           float* __restrict__ partials) {
     extern __shared__ float sm[];
+    griddep_launch();
+    griddep_wait();
     // DLA shared: prop[L], sm_p[L] (softmax of prop), then per-warp accumulators acc[nw][L]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     float* prop = sm;
@@ -245,6 +247,8 @@ __global__ void __launch_bounds__(256) pairwise_kernel(const float* __restrict__
     float* raw_y = raw_s + L;
     int* pos = reinterpret_cast<int*>(raw_y + L);   // LAMBDA: rank of original index
     __shared__ float red[8];
+    griddep_launch();
+    griddep_wait();
 
     for (int i = threadIdx.x; i < L; i += blockDim.x) {
         tp[i] = t_plus[i];
@@ -363,6 +367,8 @@ __global__ void __launch_bounds__(256) pairwise_kernel(const float* __restrict__
 
 __global__ void em_update_kernel(float* __restrict__ t_plus, float* __restrict__ t_minus,
                                  const float* __restrict__ out, int L, float em_step, float expo, int safe) {
+    griddep_launch();
+    griddep_wait();
     const float Tp0 = out[0], Tm0 = out[L];
     for (int i = threadIdx.x; i < L; i += blockDim.x) {
         float rp = safe ? safe_div_f(out[i], Tp0) : out[i] / Tp0;
@@ -404,10 +410,10 @@ extern "C" UB200_API int ub200_softmax_ce(const float* scores, const float* labe
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int grid = loss_grid(B, 8);
     if (weight_mode == 0)
-        softmax_ce_kernel<0><<<grid, 256, 0, st>>>(scores, labels, B, L, nullptr, 0, nullptr, nullptr, dscores, nullptr,
+        launch_k(softmax_ce_kernel<0>, grid, 256, 0, st, scores, labels, B, L, nullptr, 0, nullptr, nullptr, dscores, nullptr,
                                                    sums, w.counter, w.partials);
     else
-        softmax_ce_kernel<1><<<grid, 256, 0, st>>>(scores, labels, B, L, table, table_len, nullptr, nullptr, dscores,
+        launch_k(softmax_ce_kernel<1>, grid, 256, 0, st, scores, labels, B, L, table, table_len, nullptr, nullptr, dscores,
                                                    nullptr, sums, w.counter, w.partials);
     UB_LAUNCH_CHECK("softmax_ce_kernel");
     return 0;
@@ -427,7 +433,7 @@ extern "C" UB200_API int ub200_dla_loss(const float* scores, const float* clicks
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(softmax_ce_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int grid = loss_grid(B, 8);
-    softmax_ce_kernel<2><<<grid, 256, smem, st>>>(scores, clicks, B, L, nullptr, 0, prop_w, prop_b, dscores, dprop,
+    launch_k(softmax_ce_kernel<2>, grid, 256, smem, st, scores, clicks, B, L, nullptr, 0, prop_w, prop_b, dscores, dprop,
                                                   sums, w.counter, w.partials);
     UB_LAUNCH_CHECK("softmax_ce_kernel<dla>");
     return 0;
@@ -449,7 +455,7 @@ static int launch_pairwise(const float* scores, const float* labels, int B, int 
     int threads = (L + 31) / 32 * 32;
     if (threads > 256) threads = 256;
     const int grid = loss_grid(B, 1);
-    pairwise_kernel<LAMBDA><<<grid, threads, smem, st>>>(scores, labels, B, L, sigma, t_plus, t_minus, dscores, out,
+    launch_k(pairwise_kernel<LAMBDA>, grid, threads, smem, st, scores, labels, B, L, sigma, t_plus, t_minus, dscores, out,
                                                          w.counter, w.partials);
     UB_LAUNCH_CHECK("pairwise_kernel");
     return 0;
@@ -472,7 +478,7 @@ extern "C" UB200_API int ub200_pairdebias(const float* scores, const float* clic
 extern "C" UB200_API int ub200_em_update(float* t_plus, float* t_minus, const float* out, int L, float em_step, float reg_p,
                                int safe_div, void* stream) {
     UB_CHECK(L > 0 && t_plus && t_minus && out, 1, "em_update: bad arguments");
-    em_update_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(t_plus, t_minus, out, L, em_step,
+    launch_k(em_update_kernel, 1, 256, 0, static_cast<cudaStream_t>(stream), t_plus, t_minus, out, L, em_step,
                                                                       1.f / (reg_p + 1.f), safe_div);
     UB_LAUNCH_CHECK("em_update_kernel");
     return 0;

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(F_NTHREADS, 1) fwd_fused_kernel(FusedArgs a) {
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+    griddep_launch();
     FZ_STAMP(0);
     const int i0 = blockIdx.x * 128;
     const int q4 = warp & 3, cg = (warp >> 2) & 3;
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(F_NTHREADS, 1) fwd_fused_kernel(FusedArgs a) {
         fence_mbar_init();
     }
     if (warp == F_MMA_WARP) tmem_alloc(tmem_slot, 512);
+    griddep_wait();      // barrier init + tensor-memory allocation overlap the previous kernel's tail
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -406,7 +408,7 @@ int fused_forward(const tc::FusedArgs& a, cudaStream_t st) {
         UB_CHECK(e == cudaSuccess, 100, "fwd_fused_kernel attribute: %s", cudaGetErrorString(e));
         configured = true;
     }
-    tc::fwd_fused_kernel<<<(a.M + 127) / 128, tc::F_NTHREADS, smem, st>>>(a);
+    launch_k(tc::fwd_fused_kernel, (a.M + 127) / 128, tc::F_NTHREADS, smem, st, a);
     UB_LAUNCH_CHECK("fwd_fused_kernel");
     return 0;
 }

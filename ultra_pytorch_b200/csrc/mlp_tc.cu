@@ -75,14 +75,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+    griddep_launch();
     if (tid == 0) TC_STAMP(0);
     const int i0 = blockIdx.x * BLOCK_M;        // first row of the MMA "M" dimension (m, or n for WGRAD)
-    const int j0 = blockIdx.y * BLOCK_N;        // first row of the MMA "N" dimension (n / k / k)
+    // WGRAD: blockIdx.y = row split, blockIdx.z = column tile
+    const int j0 = (KIND == KIND_WGRAD ? blockIdx.z : blockIdx.y) * BLOCK_N;   // first row of the MMA "N" dimension
     int c_begin = 0, c_end;
     if (KIND == KIND_FWD) c_end = a.K;
     else if (KIND == KIND_DGRAD) c_end = a.N;
     else {
-        c_begin = blockIdx.z * a.rows_per_split;
+        c_begin = blockIdx.y * a.rows_per_split;
         c_end = min(a.M, c_begin + a.rows_per_split);
     }
     const int n_chunks = (c_end - c_begin + BLOCK_K - 1) / BLOCK_K;
@@ -100,6 +102,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
     // the number of accumulation steps; keeping the 2^-12-times-smaller correction terms out of the main accumulator
     // cuts its accumulation count by 3 (measured at K = 700: scores 1.1e-5 -> inside the 1e-5 bound).
     if (warp == MMA_WARP) tmem_alloc(tmem_slot, 2 * BLOCK_N);
+    griddep_wait();      // everything above is on-chip set-up; global memory is touched only from here on
     if (KIND == KIND_FWD && tid < BLOCK_N) sbias[tid] = (j0 + tid < a.N) ? a.bias[j0 + tid] : 0.f;
     tc_fence_before();
     __syncthreads();
@@ -108,6 +111,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) TC_STAMP(1);
 
+    float4 csum_keep = zero4;
     if (warp < MMA_WARP) {
         // =========================== producers ===========================
         // Global loads of chunk it+1 are issued before chunk it is transformed and stored (register double
@@ -199,9 +203,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
             const int n_col = i0 + blk_a * 32 + c * 4;
             const int k_col = j0 + blk_b * 32 + c * 4;
             const bool a_ok = n_col < a.N;
-            const int b_kind = (k_col + 3 < a.K) ? 0 : (k_col <= a.K ? 1 : 2);   // 0 full, 1 row tail (+ ones), 2 zero
+            // 0 full, 1 row tail (+ ones column), 2 zero.  colsum mode (K % 64 == 0): no ones column, db comes from csum
+            const int b_kind = (k_col + 3 < a.K) ? 0 : ((k_col <= a.K && !a.colsum) ? 1 : 2);
             float4 av_c[NA], av_n[NA], bv_c[NBV], bv_n[NBV];
             float2 bs_c[NBV], bs_n[NBV];
+            float4 csum = zero4;                         // column sums of dZ over this CTA's rows (colsum mode)
             int d1[NBV], d2[NBV];                        // gathered row ids of chunk it+1 / it+2 (layer 0)
             auto load_ids = [&](int it, int* d) {
 #pragma unroll
@@ -261,7 +267,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
                 uint8_t* b_hi = a_lo + A_TILE_BYTES;
                 uint8_t* b_lo = b_hi + B_TILE_BYTES;
 #pragma unroll
-                for (int e = 0; e < NA; ++e) st_split(a_hi, a_lo, swz_mn32(ml_a + e * 16, blk_a, c, 4), av_c[e]);
+                for (int e = 0; e < NA; ++e) {
+                    st_split(a_hi, a_lo, swz_mn32(ml_a + e * 16, blk_a, c, 4), av_c[e]);
+                    csum.x += av_c[e].x; csum.y += av_c[e].y; csum.z += av_c[e].z; csum.w += av_c[e].w;
+                }
 #pragma unroll
                 for (int e = 0; e < NBV; ++e) {
                     float4 v = bv_c[e];
@@ -282,6 +291,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
                     bs_c[e] = bs_n[e];
                 }
             }
+            csum_keep = csum;
         }
     } else if (lane == 0) {
         // =========================== MMA issuer (one thread) ===========================
@@ -339,6 +349,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
         //    touches 32 cache lines per instruction and made the epilogue half of the kernel time).
         constexpr int TS = BLOCK_N + 4;                     // tile row stride in floats
         float* stile = reinterpret_cast<float*>(smem);
+        // colsum mode: per-warp column sums of dZ [16 warps][32 lanes] float4, behind the tile (the ring is free now)
+        constexpr int CS_OFF = (BLOCK_M * TS * 4 + 1023) / 1024 * 1024;
+        static_assert(CS_OFF + 16 * 32 * 16 <= STAGES * STAGE_BYTES, "column-sum scratch does not fit the ring");
+        const bool do_colsum = KIND == KIND_WGRAD && a.colsum && j0 == 0;
+        if (do_colsum) reinterpret_cast<float4*>(smem + CS_OFF)[warp * 32 + lane] = csum_keep;
         const int q4 = warp & 3;
         const int trow = q4 * 32 + lane;
         const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16);
@@ -368,7 +383,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
         } else if (KIND == KIND_DGRAD) {
             row_limit = a.M; col_limit = a.K;
         } else {
-            row_limit = a.N; col_limit = a.ldo;
+            row_limit = a.N; col_limit = a.colsum ? a.K : a.ldo;   // colsum: columns K.. are written below
         }
         if (KIND == KIND_DGRAD && a.fuse_lnbwd) {
             // fused LayerNorm backward + ELU': the tile holds dXhat for FULL rows (BLOCK_N == K).  One warp per row:
@@ -397,7 +412,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
             }
         } else {
             float* out_base = a.out;
-            if (KIND == KIND_WGRAD) out_base += (size_t)blockIdx.z * a.N * a.ldo;
+            if (KIND == KIND_WGRAD) out_base += (size_t)blockIdx.y * a.N * a.ldo;
+            if (do_colsum && tid < BLOCK_M && i0 + tid < a.N) {
+                // db partial of row n = i0 + tid: the 16 producer warps covered disjoint contraction rows; lane
+                // (n / 32) * 8 + (n % 32) / 4 of every warp holds columns 4 * (n / 4) .. + 3.  Fixed order.
+                const float* cs = reinterpret_cast<const float*>(smem + CS_OFF);
+                const int src_lane = (tid >> 5) * 8 + ((tid & 31) >> 2);
+                float sum = 0.f;
+#pragma unroll
+                for (int w = 0; w < NPROD / 32; ++w) sum += cs[(w * 32 + src_lane) * 4 + (tid & 3)];
+                float* orow = out_base + (size_t)(i0 + tid) * a.ldo;
+                orow[a.K] = sum;
+                for (int k = a.K + 1; k < a.ldo; ++k) orow[k] = 0.f;
+            }
             constexpr int CPR = BLOCK_N / 4;                    // 16-byte chunks per tile row
 #pragma unroll 4
             for (int idx = tid; idx < BLOCK_M * CPR; idx += NPROD) {
@@ -423,6 +450,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(TcArgs a) {
 // Pre-split the weights once per step: forward operand Wf[n][Kpad] = W[n][k] and data-gradient operand
 // Wd[k][Npad] = W[n][k] * gamma[k] (transposed), each as (hi, lo) with zero padding to a multiple of 32.
 __global__ void __launch_bounds__(256) prep_weights_kernel(PrepTable t) {
+    griddep_launch();
+    griddep_wait();
     // Output "images": for every 32-wide contraction chunk, [rows x 128 B] in the exact 128B-swizzled shared-memory
     // order, so that a tile (any multiple-of-8 row range of one chunk) is ONE contiguous cp.async.bulk copy.
     //   forward operand   rows = n (N),  contraction = k: value W[n][k]
@@ -464,8 +493,7 @@ static cudaError_t launch_one(const TcArgs& a, dim3 grid, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    tc_gemm_kernel<KIND, BLOCK_N><<<grid, NTHREADS, smem, st>>>(a);
-    return cudaGetLastError();
+    return launch_k(tc_gemm_kernel<KIND, BLOCK_N>, grid, NTHREADS, smem, st, a);
 }
 
 template <int KIND>
@@ -510,7 +538,7 @@ int tc_prep(const tc::PrepTable& t, int max_elems, cudaStream_t st) {
     int bx = (max_elems + 256 * 4 - 1) / (256 * 4);
     if (bx > 4 * kNumSMs) bx = 4 * kNumSMs;
     if (bx < 1) bx = 1;
-    tc::prep_weights_kernel<<<dim3(bx, t.n), 256, 0, st>>>(t);
+    launch_k(tc::prep_weights_kernel, dim3(bx, t.n), 256, 0, st, t);
     UB_LAUNCH_CHECK("prep_weights_kernel");
     return 0;
 }
@@ -535,11 +563,12 @@ int tc_dgrad_layer(const tc::TcArgs& a, cudaStream_t st) {
 
 static int wgrad_block_n(int cols) { return cols > 128 ? 256 : (cols > 64 ? 128 : 64); }
 
-// split count of the weight-gradient contraction over the M rows: one wave of CTAs, each split >= 128 rows
-int tc_wgrad_splits(int M, int N, int K) {
-    const int cols = K + 1, bn = wgrad_block_n(cols);
+// split count of the weight-gradient contraction over the M rows: one wave of CTAs on `sm_budget` SMs (the side
+// branches of the backward pass leave the rest to the concurrent data-gradient kernel), each split >= 128 rows
+int tc_wgrad_splits(int M, int N, int K, int sm_budget) {
+    const int cols = tc_wgrad_colsum(K) ? K : K + 1, bn = wgrad_block_n(cols);
     const int tiles = ((N + tc::BLOCK_M - 1) / tc::BLOCK_M) * ((cols + bn - 1) / bn);
-    int s = kNumSMs / tiles;
+    int s = sm_budget / tiles;
     const int max_s = (M + 127) / 128;
     if (s > max_s) s = max_s;
     return s < 1 ? 1 : s;
@@ -547,9 +576,9 @@ int tc_wgrad_splits(int M, int N, int K) {
 
 int tc_wgrad_layer(const tc::TcArgs& a, int splits, cudaStream_t st) {
     const int row_tiles = (a.N + tc::BLOCK_M - 1) / tc::BLOCK_M;
-    const int cols = a.K + 1;
+    const int cols = a.colsum ? a.K : a.K + 1;
     const int bn = wgrad_block_n(cols);
-    cudaError_t e = tc::launch_kind<tc::KIND_WGRAD>(a, bn, dim3(row_tiles, (cols + bn - 1) / bn, splits), st);
+    cudaError_t e = tc::launch_kind<tc::KIND_WGRAD>(a, bn, dim3(row_tiles, splits, (cols + bn - 1) / bn), st);
     count_launch();
     UB_CHECK(e == cudaSuccess, 100, "tc_gemm_kernel<WGRAD> launch failed: %s", cudaGetErrorString(e));
     return 0;

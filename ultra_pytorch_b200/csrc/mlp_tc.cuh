@@ -22,6 +22,10 @@ struct TcArgs {
     // DGRAD with one column tile (BLOCK_N == K): fuse LayerNorm-backward . ELU' into the epilogue and write dZ_{j-1}
     // directly (X = Y_{j-1} is both the LayerNorm input and the ELU output; stats = its row statistics)
     int fuse_lnbwd;
+    // WGRAD when K is a multiple of 64: the bias gradient db[n] = sum_m dZ[m, n] is accumulated by the A-operand
+    // producers (which stream dZ anyway) instead of a "ones" column of the B operand, which would otherwise open an
+    // extra, almost empty column tile (K = 256 -> 257 columns -> two 256-wide tiles) or double the tile width
+    int colsum;
 };
 struct PrepTable {
     int n;
@@ -61,6 +65,7 @@ bool tc_layer_ok(int j, int K, int N);
 int tc_prep(const tc::PrepTable& t, int max_elems, cudaStream_t st);
 int tc_forward_layer(const tc::TcArgs& a, cudaStream_t st);
 int tc_dgrad_layer(const tc::TcArgs& a, cudaStream_t st);
-int tc_wgrad_splits(int M, int N, int K);
+int tc_wgrad_splits(int M, int N, int K, int sm_budget = kNumSMs);
 int tc_wgrad_layer(const tc::TcArgs& a, int splits, cudaStream_t st);
+inline bool tc_wgrad_colsum(int K) { return K % 64 == 0; }
 }  // namespace ub200

@@ -1,7 +1,10 @@
 // clip_grad_norm_ + Adagrad / SGD on a flat fp32 parameter buffer (sm_100a).
 // Replaces BaseAlgorithm.opt_step (base_algorithm.py:208-226) and DLA.separate_gradient_update (dla.py:141-166).
-// Two launches: (1) deterministic global L2 norm of the (loss-normalised) gradient, (2) clip + update.
+// ONE launch (grid <= number of SMs, so every block is resident): per-block partial sums of squares, an in-kernel grid
+// barrier, then every block adds the partials in the same fixed order (deterministic, identical in every block) and
+// applies clip + update.  UB200_OPT_FUSED=0 selects the older two-launch form (norm kernel, then update kernel).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -32,6 +35,8 @@ __global__ void __launch_bounds__(256) grad_norm_kernel(const float* __restrict_
                                                          const float* __restrict__ den, float scale_const,
                                                          unsigned int* counter, float* __restrict__ norm_slot,
                                                          float* __restrict__ partials, float* __restrict__ norm_out) {
+    griddep_launch();
+    griddep_wait();
     __shared__ float red[8];
     const float sc = grad_scale(den, scale_const);
     float s = 0.f;
@@ -63,6 +68,8 @@ __global__ void __launch_bounds__(256) clip_update_kernel(float* __restrict__ p,
                                                            const float* __restrict__ den, float scale_const,
                                                            float max_norm, float lr, int mode,
                                                            const float* __restrict__ norm_slot) {
+    griddep_launch();
+    griddep_wait();
     float sc = grad_scale(den, scale_const);
     if (max_norm > 0.f) {
         float coef = max_norm / (norm_slot[0] + 1e-6f);     // torch.nn.utils.clip_grad_norm_
@@ -84,6 +91,102 @@ __global__ void __launch_bounds__(256) clip_update_kernel(float* __restrict__ p,
         }
         p[i] = pi;
     }
+}
+
+// norm + clip + update in one launch.  `bar` = {arrive, depart, timeout flag}: all zero on entry and on exit.
+__global__ void __launch_bounds__(256) clip_update_fused_kernel(float* __restrict__ p, float* __restrict__ g,
+                                                                 float* __restrict__ state, size_t n,
+                                                                 const float* __restrict__ den, float scale_const,
+                                                                 float max_norm, float lr, int mode,
+                                                                 unsigned int* bar, float* __restrict__ partials,
+                                                                 float* __restrict__ norm_slot,
+                                                                 float* __restrict__ norm_out) {
+    griddep_launch();
+    griddep_wait();
+    __shared__ float red[8];
+    __shared__ float s_norm;
+    float sc = grad_scale(den, scale_const);
+    float s = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float v = g[i] * sc;
+        s = fmaf(v, v, s);
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) t += red[q];
+        partials[blockIdx.x] = t;
+        // ---- grid barrier: every block is resident (grid <= SM count), so spinning cannot starve a block ----
+        __threadfence();
+        atomicAdd(&bar[0], 1u);
+        const long long t0 = clock64();
+        unsigned int seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+            if (seen < gridDim.x && clock64() - t0 > (1ll << 31)) {      // ~1 s: never hang the device
+                bar[2] = 1u;
+                break;
+            }
+        } while (seen < gridDim.x);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        // fixed summation order (lane-strided, then the xor butterfly): bitwise the same value in every block
+        float tot = 0.f;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) tot += __ldcg(&partials[b]);
+        tot = warp_sum(tot);
+        if (threadIdx.x == 0) {
+            s_norm = sqrtf(tot);
+            // last block to leave re-arms the barrier for the next launch
+            if (atomicAdd(&bar[1], 1u) == gridDim.x - 1) {
+                bar[0] = 0u;
+                __threadfence();
+                bar[1] = 0u;
+                norm_slot[0] = s_norm;
+                if (norm_out) norm_out[0] = s_norm;
+            }
+        }
+    }
+    __syncthreads();
+    if (max_norm > 0.f) {
+        float coef = max_norm / (s_norm + 1e-6f);     // torch.nn.utils.clip_grad_norm_
+        sc *= fminf(coef, 1.f);
+    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float gi = g[i] * sc;
+        g[i] = gi;
+        float pi = p[i];
+        if (mode == 2) {
+            pi -= lr * gi;
+        } else {
+            float ss = gi * gi;
+            if (mode == 0) {
+                ss += state[i];
+                state[i] = ss;
+            }
+            pi -= lr * gi / (sqrtf(ss) + 1e-10f);              // torch.optim.Adagrad, eps = 1e-10
+        }
+        p[i] = pi;
+    }
+}
+
+static int env_flag(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? (v[0] != '0') : dflt;
+}
+bool pdl_enabled() {
+    static const int on = env_flag("UB200_PDL", 0);
+    return on != 0;
+}
+int& launch_priority() {
+    static thread_local int p = 0;
+    return p;
+}
+static bool opt_fused() {
+    static const int on = env_flag("UB200_OPT_FUSED", 1);
+    return on != 0;
 }
 
 }  // namespace ub200
@@ -110,14 +213,22 @@ extern "C" UB200_API int ub200_clip_update(float* params, float* grads, float* s
     float* norm_slot = reinterpret_cast<float*>(static_cast<char*>(workspace) + 64);
     float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
     int grid = (int)((n + 256 * 4 - 1) / (256 * 4));
-    if (grid > kOptBlocks) grid = kOptBlocks;
     if (grid < 1) grid = 1;
+    if ((max_norm > 0.f || norm_out) && opt_fused()) {
+        if (grid > kNumSMs) grid = kNumSMs;       // all blocks resident: the in-kernel grid barrier is safe
+        launch_k(clip_update_fused_kernel, grid, 256, 0, st, params, grads, state_sum, n, den, scale_const, max_norm,
+                 lr, mode, counter + 4, partials, norm_slot, norm_out);
+        UB_LAUNCH_CHECK("clip_update_fused_kernel");
+        return 0;
+    }
+    if (grid > kOptBlocks) grid = kOptBlocks;
     if (max_norm > 0.f || norm_out) {
-        grad_norm_kernel<<<grid, 256, 0, st>>>(grads, n, den, scale_const, counter, norm_slot, partials, norm_out);
+        launch_k(grad_norm_kernel, grid, 256, 0, st, grads, n, den, scale_const, counter, norm_slot, partials,
+                 norm_out);
         UB_LAUNCH_CHECK("grad_norm_kernel");
     }
-    clip_update_kernel<<<grid, 256, 0, st>>>(params, grads, state_sum, n, den, scale_const, max_norm, lr, mode,
-                                             norm_slot);
+    launch_k(clip_update_kernel, grid, 256, 0, st, params, grads, state_sum, n, den, scale_const, max_norm, lr, mode,
+             norm_slot);
     UB_LAUNCH_CHECK("clip_update_kernel");
     return 0;
 }

@@ -56,8 +56,8 @@ class RankerEngine(object):
         self._loss_ws = None
         self._pin = None
         self._dev = None
-        self._pack_threads = int(os.environ.get("UB200_PACK_THREADS", str(min(8, os.cpu_count() or 1))))
-        self._pack_chunks = int(os.environ.get("UB200_PACK_CHUNKS", "4"))
+        self._pack_threads = int(os.environ.get("UB200_PACK_THREADS", str(min(16, os.cpu_count() or 1))))
+        self._pack_chunks = int(os.environ.get("UB200_PACK_CHUNKS", "6"))
         self._scores = {}
         self._dscores = {}
 
@@ -138,27 +138,15 @@ class RankerEngine(object):
                 _f32_vec(docid_arrays[0]) and _f32_vec(docid_arrays[-1]) and _f32_vec(label_arrays[0]) and
                 _f32_vec(label_arrays[-1]))
         if fast:
-            # C packer straight into pinned memory, pipelined with the H2D copy: ids/labels first, then the feature rows
-            # in a few chunks (f64 -> f32 on `_pack_threads` host threads); the copy of chunk i overlaps the conversion
-            # of chunk i+1.  All copies are on the current stream, so the kernels that follow see complete data.
+            # ONE C call: ids/labels + the f64 -> f32 conversion of the feature rows on the persistent host thread pool,
+            # straight into pinned memory, with the H2D copy of every finished group of rows enqueued on the current
+            # stream while the rest is still being converted (csrc/hostpack.cpp).
             PtrArr = ctypes.c_void_p * L
             dptr = PtrArr(*[x.ctypes.data for x in docid_arrays])
             lptr = PtrArr(*[x.ctypes.data for x in label_arrays])
-            pin_ptr = self._pin.data_ptr()
-            check(lib.ub200_pack_ids_host(dptr, lptr, L, B, pin_ptr, self._pin.numel()), "ub200_pack_ids_host")
-            self._dev[:2 * off_l].copy_(self._pin[:2 * off_l], non_blocking=True)
-            self._pin_np[off_f + 4 * n_docs * self.F:total] = 0            # the PAD row
-            src = feats.ctypes.data
-            n_chunks = self._pack_chunks if n_docs * self.F >= (1 << 18) else 1
-            rows_per = (n_docs + n_chunks - 1) // n_chunks
-            for r0 in range(0, n_docs, rows_per):
-                r1 = min(n_docs, r0 + rows_per)
-                e0, e1 = r0 * self.F, r1 * self.F
-                check(lib.ub200_convert_f64_f32_host(src + 8 * e0, pin_ptr + off_f + 4 * e0, e1 - e0,
-                                                     self._pack_threads), "ub200_convert_f64_f32_host")
-                b0 = off_f + 4 * e0
-                b1 = total if r1 == n_docs else off_f + 4 * e1
-                self._dev[b0:b1].copy_(self._pin[b0:b1], non_blocking=True)
+            check(lib.ub200_stage_feed(feats.ctypes.data, n_docs, self.F, dptr, lptr, L, B, self._pin.data_ptr(),
+                                       self._pin.numel(), self._dev.data_ptr(), self._pack_threads, self._pack_chunks,
+                                       _stream()), "ub200_stage_feed")
             return self.staged_views(self._dev, L, B, n_docs)
         else:
             buf = self._pin_np

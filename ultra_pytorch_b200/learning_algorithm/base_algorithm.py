@@ -42,6 +42,7 @@ _RANKER_ALIASES = {
     # the reference class path is accepted and mapped to the B200 implementation, so a settings JSON only has to
     # switch the learning algorithm to move the whole hot path onto the GPU kernels
     "ultra.ranking_model.DNN": "ultra_pytorch_b200.ranking_model.DNN",
+    "ultra.ranking_model.Linear": "ultra_pytorch_b200.ranking_model.Linear",
 }
 
 

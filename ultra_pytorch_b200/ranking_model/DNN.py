@@ -26,8 +26,11 @@ class DNN(nn.Module):
             raise NotImplementedError(
                 "ultra_pytorch_b200.DNN implements the reference defaults activation_func='elu', norm='layer' "
                 "(got %r, %r); there is no fallback path" % (self.hparams.activation_func, self.hparams.norm))
+        self._setup(feature_size, self.hparams.hidden_layer_sizes, extra_floats)
+
+    def _setup(self, feature_size, hidden, extra_floats):
         self.feature_size = int(feature_size)
-        self.output_sizes = list(self.hparams.hidden_layer_sizes) + [1]
+        self.output_sizes = list(hidden) + [1]
         # Build the same module sequence as the reference ON THE CPU first: with the same torch seed the
         # initial weights are bit-identical to the reference's (DNN.py:43-55).
         self.sequential = nn.Sequential()
@@ -38,7 +41,7 @@ class DNN(nn.Module):
             if j != len(self.output_sizes) - 1:
                 self.sequential.add_module('act{}'.format(j), nn.ELU())
             k = n
-        self.engine = RankerEngine(self.feature_size, self.hparams.hidden_layer_sizes, extra_floats=extra_floats)
+        self.engine = RankerEngine(self.feature_size, list(hidden), extra_floats=extra_floats)
         self._bind()
 
     def _bind(self):
