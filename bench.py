@@ -117,7 +117,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -226,7 +226,6 @@ def main_b200(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     eager_launches = _capi.lib.ub200_launch_count() - launches0
     t = torch.tensor([ms], device="cuda")
     if world > 1:
@@ -271,9 +270,18 @@ def main_b200(args):
     except Exception:  # noqa: BLE001
         pass
     peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+    traffic, traffic_src = None, None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of the K1 kernels of ONE step, from the committed ncu --set full
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        ent = tr.get("%s_B%d" % (args.workload, B))
+        if ent:
+            traffic, traffic_src = ent["k1_dram_bytes_per_step"], tr.get("source")
+    except Exception:  # noqa: BLE001
+        pass
     achieved_tf = flops / (k1_ms / 1e3) / 1e12
     roofline = {"bound": "tensor", "achieved": round(achieved_tf, 3), "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": round(achieved_tf / peak_tf, 5), "traffic": None,
+                "frac": round(achieved_tf / peak_tf, 5), "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_hbm_bytes": int(4 * L * B * F),
                 "kernel": "K1 DNN forward+backward (all launches of ub200_mlp_forward + ub200_mlp_backward)",
                 "ms_per_launch_group": round(k1_ms, 4), "fwd_ms": round(fwd_ms, 4),
                 "algorithmic_flops": flops, "peak_source": "MEASURED_PEAKS.json bf16 burst" if peaks else "fallback",
@@ -288,6 +296,7 @@ def main_b200(args):
         model.train(feeds[k % n_host])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions (value leg .. e2e leg)
     t = torch.tensor([e2e_s], device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

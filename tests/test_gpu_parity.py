@@ -237,7 +237,7 @@ def test_dla_loss_vs_oracle(B, L):
     assert abs(dp[L] - r["dprop_b"]) <= 2e-5 * max(abs(r["dprop_b"]), np.abs(r["dprop_w"]).max())
 
 
-@pytest.mark.parametrize("B,L", [(3, 2), (8, 6), (64, 40), (32, 200), (5, 300)])
+@pytest.mark.parametrize("B,L", [(3, 2), (2, 3), (8, 6), (4, 45), (64, 40), (32, 200), (5, 300), (2, 600)])
 @pytest.mark.parametrize("kind", ["lambdarank", "pairdebias"])
 def test_pairwise_vs_oracle(B, L, kind):
     from ultra_pytorch_b200.engine import RankerEngine

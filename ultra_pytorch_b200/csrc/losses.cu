@@ -226,13 +226,28 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 
 // LAMBDA = true : LambdaRank (lambda_rank.py:116-135, 247-291) - positions are predicted ranks
 // LAMBDA = false: PairDebias (pairwise_debias.py:142-157)       - positions are display positions
+//
+// Every UNORDERED pair {i, j} is evaluated exactly once (the reference's [L, L] matrices hold each pair twice, as
+// (i, j) and (j, i), and both directions share every transcendental): thread i visits the partners j = (i + k) mod L
+// for k = 1 .. L/2 ("round-robin tournament"), so within one step k the partners of a warp's lanes are all different
+// and the partner-side contributions go to per-warp shared-memory arrays without atomics; a __syncwarp() per step
+// is the only synchronisation.  Owner-side sums stay in registers.  Everything is added in a fixed order, so the
+// result is bitwise reproducible.  Issue-bound: ~8 MUFU + ~60 FP32 instructions per pair.
+// Warp w owns rows 32 * (w % nrb) .. + 31 and the k-group w / nrb: a list of 200 positions runs on 14 warps
+// (7 row blocks x 2 groups of 50 steps), two lists per SM, so the long dependency chain of one pair is hidden by
+// other warps.
+struct PairAcc {
+    float Tp, Tm, g, ls;
+};
+
 template <bool LAMBDA>
-__global__ void __launch_bounds__(256) pairwise_kernel(const float* __restrict__ scores,
+__global__ void __launch_bounds__(512) pairwise_kernel(const float* __restrict__ scores,
                                                         const float* __restrict__ labels, int B, int L, float sigma,
                                                         const float* __restrict__ t_plus,
                                                         const float* __restrict__ t_minus,
                                                         float* __restrict__ dscores, float* __restrict__ out,
-                                                        unsigned int* counter, float* __restrict__ partials) {
+                                                        unsigned int* counter, float* __restrict__ partials,
+                                                        int n_groups) {
     extern __shared__ float sm[];
     float* ps = sm;              // scores in position order (sorted for LAMBDA)
     float* ys = ps + L;          // labels in position order
@@ -240,50 +255,89 @@ __global__ void __launch_bounds__(256) pairwise_kernel(const float* __restrict__
     float* dc = gn + L;          // LAMBDA: 1/log2(pos+2)
     float* tp = dc + L;
     float* tm = tp + L;
-    float* accp = tm + L;        // block accumulators of T+ / T-
+    float* rtp = tm + L;         // 1 / t+ , 1 / t-
+    float* rtm = rtp + L;
+    float* accp = rtm + L;       // block accumulators of T+ / T- over this block's lists
     float* accm = accp + L;
-    float* gr = accm + L;        // gradient in position order
-    float* raw_s = gr + L;       // LAMBDA: unsorted copy
+    float* gr = accm + L;        // owner-side results of the current list: gradient, T+, T-
+    float* oTp = gr + L;
+    float* oTm = oTp + L;
+    float* raw_s = oTm + L;      // LAMBDA: unsorted copy
     float* raw_y = raw_s + L;
     int* pos = reinterpret_cast<int*>(raw_y + L);   // LAMBDA: rank of original index
-    __shared__ float red[8];
+    int* ipos = pos + L;                            // LAMBDA: ideal rank (by label) of original index
+    float* part = reinterpret_cast<float*>(ipos + L);  // [nwarps][3][L] partner-side g, T+, T-
+    __shared__ float red[32];
     griddep_launch();
     griddep_wait();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    float* pg = part + (size_t)wid * 3 * L;
+    float* pTp = pg + L;
+    float* pTm = pTp + L;
 
     for (int i = threadIdx.x; i < L; i += blockDim.x) {
-        tp[i] = t_plus[i];
-        tm[i] = t_minus[i];
+        const float a = t_plus[i], b = t_minus[i];
+        tp[i] = a;
+        tm[i] = b;
+        rtp[i] = 1.f / a;
+        rtm[i] = 1.f / b;
         accp[i] = 0.f;
         accm[i] = 0.f;
         if (LAMBDA) dc[i] = 1.f / log2f((float)i + 2.f);
     }
+    const int half = L / 2;
+    const int nrb = (L + 31) / 32;                         // row blocks of 32 positions
+    const int kgroup = n_groups > 1 ? wid / nrb : 0;       // this warp's k-group (n_groups > 1: nw == nrb * n_groups)
+    const int ksteps = (half + n_groups - 1) / n_groups;
+    const int k_lo = kgroup * ksteps + 1;
+    const int k_hi = min(half, (kgroup + 1) * ksteps);
     float loss_acc = 0.f, idcg_acc = 0.f;
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         __syncthreads();
         const float* s = scores + (size_t)b * L;
         const float* y = labels + (size_t)b * L;
+        for (int q = threadIdx.x; q < 3 * L * nw; q += blockDim.x) part[q] = 0.f;
         if (LAMBDA) {
             for (int i = threadIdx.x; i < L; i += blockDim.x) {
                 raw_s[i] = s[i];
                 raw_y[i] = y[i];
+                pos[i] = 0;
+                ipos[i] = 0;
             }
             __syncthreads();
             // stable descending rank by counting (torch.sort(descending=True), lambda_rank.py:116) and the ideal
-            // rank of each label for the IDCG (lambda_rank.py:126, 263-266: natural log, summed over the batch)
+            // rank of each label for the IDCG (lambda_rank.py:126, 263-266: natural log, summed over the batch).
+            // The k-groups split the j range; integer atomics are order independent.
+            {
+                const int jn = (L + n_groups - 1) / n_groups;
+                const int j_lo = kgroup * jn, j_hi = min(L, j_lo + jn);
+                for (int i = (n_groups > 1 ? (wid % nrb) * 32 + lane : (int)threadIdx.x); i < L;
+                     i += (n_groups > 1 ? L : (int)blockDim.x)) {
+                    const float si = raw_s[i], yi = raw_y[i];
+                    int r = 0, ir = 0;
+                    for (int j = j_lo; j < j_hi; ++j) {
+                        const float sj = raw_s[j], yj = raw_y[j];
+                        r += (sj > si) || (sj == si && j < i);
+                        ir += (yj > yi) || (yj == yi && j < i);
+                    }
+                    if (n_groups > 1) {
+                        atomicAdd(&pos[i], r);
+                        atomicAdd(&ipos[i], ir);
+                    } else {
+                        pos[i] = r;
+                        ipos[i] = ir;
+                    }
+                }
+            }
+            __syncthreads();
             for (int i = threadIdx.x; i < L; i += blockDim.x) {
                 const float si = raw_s[i], yi = raw_y[i];
-                int r = 0, ir = 0;
-                for (int j = 0; j < L; ++j) {
-                    const float sj = raw_s[j], yj = raw_y[j];
-                    r += (sj > si) || (sj == si && j < i);
-                    ir += (yj > yi) || (yj == yi && j < i);
-                }
-                pos[i] = r;
+                const int r = pos[i];
                 ps[r] = si;
                 ys[r] = yi;
                 const float gain = exp2f(yi) - 1.f;
                 gn[r] = gain;
-                idcg_acc += gain / logf((float)ir + 2.f);
+                idcg_acc += gain / logf((float)ipos[i] + 2.f);
             }
         } else {
             for (int i = threadIdx.x; i < L; i += blockDim.x) {
@@ -292,58 +346,107 @@ __global__ void __launch_bounds__(256) pairwise_kernel(const float* __restrict__
             }
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < L; i += blockDim.x) {
-            const float si = ps[i], yi = ys[i], tpi = tp[i], tmi = tm[i];
+        // all lanes of a warp run the same number of steps (the __syncwarp below), also those without a row
+        for (int ib = (n_groups > 1 ? wid % nrb : wid) * 32; ib < L; ib += (n_groups > 1 ? L + 32 : (int)blockDim.x)) {
+            const int i = ib + lane;
+            const bool have = i < L;
+            const int ii = have ? i : 0;
+            const float si = ps[ii], yi = ys[ii], tpi = tp[ii], tmi = tm[ii], rtpi = rtp[ii], rtmi = rtm[ii];
+            const float gi = LAMBDA ? gn[ii] : 0.f, di = LAMBDA ? dc[ii] : 0.f;
             float Tp = 0.f, Tm = 0.f, g = 0.f, ls = 0.f;
-            if (LAMBDA) {
-                const float gi = gn[i], di = dc[i];
-                for (int j = 0; j < L; ++j) {
+            for (int k = k_lo; k <= k_hi; ++k) {
+                int j = ii + k;
+                if (j >= L) j -= L;
+                // for even L the antipodal pair (k == L/2) would be met from both ends
+                const bool act = have && !(2 * k == L && i >= half);
+                if (LAMBDA) {
                     const float delta = fabsf(gi - gn[j]) * fabsf(di - dc[j]);
-                    if (delta == 0.f) continue;   // also skips j == i
-                    const float dlt = sigma * (si - ps[j]);
-                    const float pij = 1.f / (expf(-dlt) + 1.f);
-                    const float pji = 1.f / (expf(dlt) + 1.f);
-                    const float Sij = fminf(fmaxf(yi - ys[j], -1.f), 1.f);
-                    const float Pij = 0.5f * (1.f + Sij), Pji = 0.5f * (1.f - Sij);
-                    // BCEWithLogits applied to the probability p (lambda_rank.py:128)
-                    const float tij = delta * (pij - pij * Pij + log1pf(expf(-pij)));
-                    const float tji = delta * (pji - pji * Pji + log1pf(expf(-pji)));
-                    const float inv_ij = safe_div_f(1.f, tpi * tm[j]);
-                    const float inv_ji = safe_div_f(1.f, tp[j] * tmi);
-                    Tp += tij / tm[j];
-                    Tm += tji / tp[j];
-                    ls = fmaf(tij, inv_ij, ls);
-                    const float aij = delta * (sigmoid_f(pij) - Pij) * sigma * pij * (1.f - pij) * inv_ij;
-                    const float aji = delta * (sigmoid_f(pji) - Pji) * sigma * pji * (1.f - pji) * inv_ji;
-                    g += aij - aji;
-                }
-            } else {
-                for (int j = 0; j < L; ++j) {
-                    if (j == i) continue;
+                    if (act && delta != 0.f) {
+                        const float d = sigma * (si - ps[j]);
+                        // p_ij = 1 / (exp(-d) + 1), p_ji = 1 / (exp(d) + 1) from ONE exponential of -|d| (no overflow)
+                        const float e = expf(-fabsf(d));
+                        const float p_big = 1.f / (1.f + e), p_small = e * p_big;
+                        const float pij = d >= 0.f ? p_big : p_small, pji = d >= 0.f ? p_small : p_big;
+                        const float Sij = fminf(fmaxf(yi - ys[j], -1.f), 1.f);
+                        const float Pij = 0.5f * (1.f + Sij), Pji = 0.5f * (1.f - Sij);
+                        // BCEWithLogits applied to the probability p (lambda_rank.py:128): p - p*P + log1p(exp(-p));
+                        // its derivative needs sigmoid(p) = 1 / (1 + exp(-p)) of the same exponential
+                        const float uij = __expf(-pij), uji = __expf(-pji);
+                        const float tij = delta * (pij - pij * Pij + __logf(1.f + uij));
+                        const float tji = delta * (pji - pji * Pji + __logf(1.f + uji));
+                        const float sgij = 1.f / (1.f + uij), sgji = 1.f / (1.f + uji);
+                        const float tpj = tp[j], tmj = tm[j], rtpj = rtp[j], rtmj = rtm[j];
+                        const float inv_ij = (tpi * tmj == 0.f) ? 0.f : rtpi * rtmj;      // metrics._safe_div
+                        const float inv_ji = (tpj * tmi == 0.f) ? 0.f : rtpj * rtmi;
+                        Tp = fmaf(tij, rtmj, Tp);                 // T+_i += t_ij / t-_j
+                        Tm = fmaf(tji, rtpj, Tm);                 // T-_i += t_ji / t+_j
+                        ls += tij * inv_ij + tji * inv_ji;
+                        const float aij = delta * (sgij - Pij) * sigma * pij * (1.f - pij) * inv_ij;
+                        const float aji = delta * (sgji - Pji) * sigma * pji * (1.f - pji) * inv_ji;
+                        g += aij - aji;
+                        pg[j] += aji - aij;
+                        pTp[j] = fmaf(tji, rtmi, pTp[j]);         // T+_j += t_ji / t-_i
+                        pTm[j] = fmaf(tij, rtpi, pTm[j]);         // T-_j += t_ij / t+_i
+                    }
+                } else {
                     const float cj = ys[j];
                     const float mij = fminf(1.f, fmaxf(yi - cj, 0.f));
                     const float mji = fminf(1.f, fmaxf(cj - yi, 0.f));
-                    if (mij == 0.f && mji == 0.f) continue;
-                    const float dlt = ps[j] - si;                 // s_j - s_i
-                    const float inv_ij = 1.f / (tpi * tm[j]);
-                    const float inv_ji = 1.f / (tp[j] * tmi);
-                    if (mij != 0.f) {
-                        const float t = mij * softplus_f(dlt);
-                        Tp += t / tm[j];
-                        ls = fmaf(t, inv_ij, ls);
-                        g -= mij * sigmoid_f(dlt) * inv_ij;
-                    }
-                    if (mji != 0.f) {
-                        const float t = mji * softplus_f(-dlt);
-                        Tm += t / tp[j];
-                        g += mji * sigmoid_f(-dlt) * inv_ji;
+                    if (act && (mij != 0.f || mji != 0.f)) {
+                        // at most one direction is active: a = the clicked side, b = the other one
+                        const bool fwd = mij != 0.f;
+                        const float m = fwd ? mij : mji;
+                        const float dlt = fwd ? ps[j] - si : si - ps[j];          // s_b - s_a
+                        const float t = m * softplus_f(dlt);
+                        const float sg = m * sigmoid_f(dlt);
+                        const float rtpa = fwd ? rtpi : rtp[j], rtma = fwd ? rtmi : rtm[j];
+                        const float rtpb = fwd ? rtp[j] : rtpi, rtmb = fwd ? rtm[j] : rtmi;
+                        (void)rtma; (void)rtpb;
+                        const float inv = rtpa * rtmb;                            // 1 / (t+_a t-_b), no safe-div
+                        ls = fmaf(t, inv, ls);
+                        const float ga = -sg * inv;
+                        if (fwd) {
+                            Tp = fmaf(t, rtmb, Tp);               // T+_a += t / t-_b
+                            pTm[j] = fmaf(t, rtpa, pTm[j]);       // T-_b += t / t+_a
+                            g += ga;
+                            pg[j] -= ga;
+                        } else {
+                            pTp[j] = fmaf(t, rtmb, pTp[j]);
+                            Tm = fmaf(t, rtpa, Tm);
+                            pg[j] += ga;
+                            g -= ga;
+                        }
                     }
                 }
+                __syncwarp();
             }
+            if (have) {
+                // owner-side sums: k-group 0 writes the per-position slots, the other groups add theirs into their
+                // warp's partner-side arrays (the k loop is over, every lane touches only its own index)
+                if (kgroup == 0) {
+                    gr[i] = g;
+                    oTp[i] = Tp;
+                    oTm[i] = Tm;
+                } else {
+                    pg[i] += g;
+                    pTp[i] += Tp;
+                    pTm[i] += Tm;
+                }
+            }
+            loss_acc += ls;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < L; i += blockDim.x) {
+            float g = gr[i], Tp = oTp[i], Tm = oTm[i];
+            for (int w = 0; w < nw; ++w) {
+                const float* q = part + (size_t)w * 3 * L;
+                g += q[i];
+                Tp += q[L + i];
+                Tm += q[2 * L + i];
+            }
+            gr[i] = g;
             accp[i] += Tp;
             accm[i] += Tm;
-            gr[i] = g;
-            loss_acc += ls;
         }
         __syncthreads();
         for (int i = threadIdx.x; i < L; i += blockDim.x)
@@ -448,15 +551,26 @@ static int launch_pairwise(const float* scores, const float* labels, int B, int 
     UB_CHECK(workspace_bytes >= loss_ws_bytes(2 * L + 2), 3, "pairwise: workspace too small");
     LossWs w = loss_ws(workspace);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t smem = sizeof(float) * 12 * (size_t)L;
+    // warps = row blocks x k-groups, at most 16 (two lists per SM); lists longer than 512 loop over their row blocks
+    const int nrb = (L + 31) / 32;
+    int groups = 1;
+    if (nrb <= 8) {
+        groups = 16 / nrb;
+        const int max_by_steps = (L / 2) / 4;           // at least 4 pair steps per group
+        if (groups > max_by_steps) groups = max_by_steps;
+        if (groups > 4) groups = 4;
+        if (groups < 1) groups = 1;
+    }
+    int threads = 32 * nrb * groups;
+    if (threads > 512) threads = 512;                   // only when groups == 1
+    // 17 per-position arrays + per-warp partner-side arrays [warps][3][L]
+    const size_t smem = sizeof(float) * (17 + 3 * (size_t)(threads / 32)) * (size_t)L;
     UB_CHECK(smem <= 200 * 1024, 4, "pairwise: list length %d too large", L);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(pairwise_kernel<LAMBDA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int threads = (L + 31) / 32 * 32;
-    if (threads > 256) threads = 256;
     const int grid = loss_grid(B, 1);
     launch_k(pairwise_kernel<LAMBDA>, grid, threads, smem, st, scores, labels, B, L, sigma, t_plus, t_minus, dscores, out,
-                                                         w.counter, w.partials);
+             w.counter, w.partials, groups);
     UB_LAUNCH_CHECK("pairwise_kernel");
     return 0;
 }
