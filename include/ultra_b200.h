@@ -162,6 +162,35 @@ UB200_API int ub200_clip_update(float* params, float* grads, float* state_sum, s
                       float max_norm, float lr, int mode, float* norm_out,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- C1: data-parallel exchange of the flat gradient buffer over NVLink peer memory ----------------------------------
+ * Nothing in the reference corresponds to this (it is single-process); it is the ONE collective of a data-parallel
+ * step: the in-place SUM over ranks of [DNN grads | loss normalisers | EM / DenoisingNet partials].
+ * peer_bufs[r] / peer_flags[r]: rank r's buffer of n floats / flag array (size: ub200_peer_flag_bytes), both in
+ * symmetric memory (mapped into this process; HOST arrays of device pointers, world entries); flags zero before the
+ * first call.  scratch: n floats, ctl: zeroed bytes (size: ub200_peer_ctl_bytes) (both local).  Every rank must issue the
+ * same sequence of calls.  Ranks add in the order 0..world-1, so all replicas receive bitwise identical sums.
+ * Graph-capturable, no host synchronisation. */
+UB200_API size_t ub200_peer_ctl_bytes(void);
+UB200_API size_t ub200_peer_flag_bytes(int world);
+UB200_API int ub200_peer_allreduce(const void* const* peer_bufs, const void* const* peer_flags, int rank, int world,
+                         float* scratch, size_t n, void* ctl, void* stream);
+
+/* The same exchange FUSED with the optimizer step: one kernel = SUM over ranks of the flat buffer `own` (n floats: the
+ * gradients of the n_params parameters followed by the trailing normalisers / partials) + ub200_clip_update on the
+ * summed gradient (same arithmetic, same modes; the normaliser is own[den_index] AFTER the sum, den_index < 0 = none).
+ * Push model over NVLink: every rank stores its buffer into every peer's inbox (peer_inbox[r]: ub200_dp_inbox_bytes
+ * bytes of symmetric memory on rank r, double buffered by step parity) and signals per-block flags (peer_flags[r]:
+ * ub200_dp_flag_bytes zeroed bytes of symmetric memory); one handshake per step, sums in rank order (bitwise equal
+ * replicas).  ctl: ub200_dp_ctl_bytes zeroed local bytes.  On return (stream order) own[0, n_params) holds the clipped
+ * summed gradient and own[n_params, n) the summed trailing floats.  world == 1 degenerates to ub200_clip_update. */
+UB200_API size_t ub200_dp_inbox_bytes(int world, size_t n);
+UB200_API size_t ub200_dp_flag_bytes(int world);
+UB200_API size_t ub200_dp_ctl_bytes(void);
+UB200_API int ub200_dp_reduce_update(float* own, size_t n, const void* const* peer_inbox, const void* const* peer_flags,
+                           int rank, int world, float* params, float* state_sum, size_t n_params, long long den_index,
+                           float scale_const, float max_norm, float lr, int mode, float* norm_out, void* ctl,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,8 +56,9 @@ def main():
         # single-GPU reference on the merged batches (rank 0 only; same seeds)
         err = 0.0
         if rank == 0:
-            prev = dist.group.WORLD
             torch.manual_seed(0)
+            # world_size() == 1 makes the reference model a plain single-GPU one (no symmetric-memory rendezvous, which
+            # is collective, and no exchange in its steps)
             la.B200Algorithm.world_size = staticmethod(lambda: 1)
             ref = getattr(la, algo)(ds, settings)
             ref.model.load_state_dict(init)

@@ -183,7 +183,7 @@ def test_mlp_forward_backward_vs_oracle(F, hidden, L, B):
     assert np.array_equal(grads, grads2)
 
 
-@pytest.mark.parametrize("B,L", [(1, 1), (7, 5), (300, 40), (64, 200), (33, 45)])
+@pytest.mark.parametrize("B,L", [(1, 1), (7, 5), (300, 40), (64, 200), (33, 45), (20, 100), (3, 300), (20000, 40)])
 @pytest.mark.parametrize("mode", ["na", "ipw"])
 def test_softmax_ce_vs_oracle(B, L, mode):
     from ultra_pytorch_b200.engine import RankerEngine
@@ -300,6 +300,51 @@ def test_clip_update_vs_oracle(mode):
         if mode == 0:
             assert_close(sd.cpu().numpy(), ss, 1e-5, "state_sum")
     assert_close(pd.cpu().numpy(), ref, 1e-5, "params")
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_dp_reduce_update_single_rank_vs_oracle(mode):
+    """The fused exchange + optimizer kernel (csrc/peer.cu) with world == 1: no peers, so it must reproduce
+    clip_grad_norm_ + Adagrad / SGD on its own buffer, with the normaliser taken from the trailing floats."""
+    import ctypes
+    from ultra_pytorch_b200 import _capi
+    from ultra_pytorch_b200.engine import RankerEngine
+    lib = _capi.lib
+    rs = np.random.RandomState(10 + mode)
+    RankerEngine(4, [])
+    n_params, n = 100003, 100003 + 7
+    p = rs.randn(n_params).astype(np.float32)
+    g = (3.0 * rs.randn(n)).astype(np.float32)
+    g[n_params + 1] = 7.5                                  # the normaliser lives behind the gradients
+    st = rs.rand(n_params).astype(np.float32)
+    pd, gd, sd = _dev(p), _dev(g), _dev(st)
+    norm = torch.zeros(1, device="cuda")
+    inbox = torch.zeros(int(lib.ub200_dp_inbox_bytes(1, n)) // 4, device="cuda")
+    flags = torch.zeros(int(lib.ub200_dp_flag_bytes(1)) // 4, dtype=torch.int32, device="cuda")
+    ctl = torch.zeros(int(lib.ub200_dp_ctl_bytes()), dtype=torch.uint8, device="cuda")
+    Ptr = ctypes.c_void_p * 1
+    for rep in range(2):                                   # twice: the kernel re-arms its own barrier / sequence number
+        pd.copy_(_dev(p)); gd.copy_(_dev(g)); sd.copy_(_dev(st))
+        _capi.check(lib.ub200_dp_reduce_update(gd.data_ptr(), n, Ptr(inbox.data_ptr()), Ptr(flags.data_ptr()), 0, 1,
+                                               pd.data_ptr(), sd.data_ptr(), n_params, n_params + 1, 2.0, 5.0, 0.05,
+                                               mode, norm.data_ptr(), ctl.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream), "ub200_dp_reduce_update")
+        torch.cuda.synchronize()
+        gs = g[:n_params].astype(np.float64) * 2.0 / 7.5
+        nrm = np.sqrt((gs ** 2).sum())
+        gc = gs * min(1.0, 5.0 / (nrm + 1e-6))
+        assert abs(norm.item() - nrm) <= 1e-5 * nrm
+        got = gd.cpu().numpy()
+        assert_close(got[:n_params], gc, 1e-5, "clipped grad")
+        assert np.array_equal(got[n_params:], g[n_params:])          # trailing floats: the (single-rank) sum
+        if mode == 2:
+            ref = p - 0.05 * gc
+        else:
+            ss = gc ** 2 + (st if mode == 0 else 0.0)
+            ref = p - 0.05 * gc / (np.sqrt(ss) + 1e-10)
+            if mode == 0:
+                assert_close(sd.cpu().numpy(), ss, 1e-5, "state_sum")
+        assert_close(pd.cpu().numpy(), ref, 1e-5, "params")
 
 
 def test_lambdarank_roundtrip_properties_full_size():

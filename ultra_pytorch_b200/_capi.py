@@ -39,6 +39,14 @@ SIGNATURES = {
     "ub200_em_update": (_i, [_vp, _vp, _vp, _i, _f, _f, _i, _vp]),
     "ub200_opt_workspace_bytes": (_sz, [_sz]),
     "ub200_clip_update": (_i, [_vp, _vp, _vp, _sz, _vp, _f, _f, _f, _i, _vp, _vp, _sz, _vp]),
+    "ub200_peer_ctl_bytes": (_sz, []),
+    "ub200_peer_flag_bytes": (_sz, [_i]),
+    "ub200_peer_allreduce": (_i, [_vp, _vp, _i, _i, _vp, _sz, _vp, _vp]),
+    "ub200_dp_inbox_bytes": (_sz, [_i, _sz]),
+    "ub200_dp_flag_bytes": (_sz, [_i]),
+    "ub200_dp_ctl_bytes": (_sz, []),
+    "ub200_dp_reduce_update": (_i, [_vp, _sz, _vp, _vp, _i, _i, _vp, _vp, _sz, ctypes.c_longlong, _f, _f, _f, _i, _vp,
+                                    _vp, _vp]),
 }
 
 

@@ -11,6 +11,7 @@
 // Plain C++ (g++): no device code in this file.
 #include <cuda_runtime_api.h>
 #include <immintrin.h>
+#include <sched.h>
 #include <stdint.h>
 #include <string.h>
 #include <unistd.h>
@@ -95,12 +96,21 @@ struct Slot {
 
 class Pool {
 public:
-    explicit Pool(int n) : n_(n) {
+    explicit Pool(int max_workers) : max_(max_workers) {
         for (int s = 0; s < 2; ++s)
             for (int g = 0; g < kMaxGroups; ++g) slots_[s].group_done[g].store(0);
-        for (int i = 0; i < n_; ++i) std::thread(&Pool::worker, this, i).detach();
     }
-    int workers() const { return n_; }
+    int max_workers() const { return max_; }
+    // workers are created on demand: a process that packs with 2 threads (8 ranks sharing 16 cores) must not keep 15
+    // spinning threads around
+    void ensure(int n) {
+        if (n > max_) n = max_;
+        std::lock_guard<std::mutex> lk(call_mu_);
+        while (n_ < n) {
+            std::thread(&Pool::worker, this, n_).detach();
+            ++n_;
+        }
+    }
 
     // runs `job` on the caller + up to job.n_workers pool threads; `on_poll` is called by the caller after each
     // block it converts and while it waits (used to issue the H2D copies of finished groups)
@@ -125,6 +135,7 @@ public:
             on_poll(s);
             if (all) break;
             _mm_pause();
+            sched_yield();
         }
     }
     static bool group_complete(const Slot& s, const Job& j, int k) {
@@ -155,7 +166,8 @@ private:
             auto t0 = std::chrono::steady_clock::now();
             while ((g = gen_.load()) == seen) {
                 _mm_pause();
-                if ((++spins & 1023) == 0 &&
+                if ((++spins & 63) == 0) sched_yield();      // oversubscribed cores go to whoever has work
+                if ((spins & 1023) == 0 &&
                     std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(2000)) {
                     std::unique_lock<std::mutex> lk(mu_);
                     sleepers_.fetch_add(1);
@@ -177,7 +189,8 @@ private:
         }
     }
 
-    const int n_;
+    const int max_;
+    int n_ = 0;
     Slot slots_[2];
     std::atomic<uint64_t> gen_{0};
     std::atomic<int> sleepers_{0};
@@ -195,7 +208,7 @@ Pool* pool() {
         unsigned hc = std::thread::hardware_concurrency();
         int n = hc > 1 ? (int)hc - 1 : 0;
         if (n > 31) n = 31;
-        p = new Pool(n);
+        p = new Pool(n);                      // upper bound; threads are spawned by ensure()
         owner = getpid();
     }
     return p;
@@ -208,8 +221,9 @@ Job make_job(const double* src, float* dst, long long n, int n_threads, int n_gr
     j.n = n;
     j.nblocks = (n + kBlock - 1) / kBlock;
     int w = (n_threads < 1 ? 1 : n_threads) - 1;
-    if (w > pool()->workers()) w = pool()->workers();
+    if (w > pool()->max_workers()) w = pool()->max_workers();
     if (j.nblocks < 4) w = 0;                                  // tiny inputs: not worth waking anybody
+    if (w > 0) pool()->ensure(w);
     j.n_workers = w;
     if (n_groups > kMaxGroups) n_groups = kMaxGroups;
     if (n_groups > j.nblocks) n_groups = (int)j.nblocks;

@@ -8,14 +8,18 @@
 
 namespace ub200 {
 
-constexpr int kLossBlocks = 2 * kNumSMs;
+constexpr int kLossBlocks = 2 * kNumSMs;       // K3 and the DLA variant of K2
+constexpr int kLossBlocksWide = 8 * kNumSMs;   // K2 (NA / IPW): enough resident warps to cover the HBM latency
 
 // workspace: [counter (uint, padded to 64 floats)] [partials: kLossBlocks x width floats]
 struct LossWs {
     unsigned int* counter;
     float* partials;
 };
-static size_t loss_ws_bytes(int width) { return 256 + sizeof(float) * (size_t)kLossBlocks * width; }
+static size_t loss_ws_bytes(int width) {
+    const size_t a = sizeof(float) * (size_t)kLossBlocks * width, b = sizeof(float) * (size_t)kLossBlocksWide * 2;
+    return 256 + (a > b ? a : b);
+}
 static LossWs loss_ws(void* ws) {
     LossWs w;
     w.counter = static_cast<unsigned int*>(ws);
@@ -43,6 +47,121 @@ struct ListStats {
     float W;      // sum of weighted labels
     float dsum;   // sum of d (1, or 0 for an empty list)
 };
+
+// NA / IPW, lists of up to 32 * NPL positions: the list lives in registers (one global read of scores and labels,
+// one exponential per element), the next list of the warp is prefetched while the current one is reduced, and the
+// grid is large enough (up to 8 blocks per SM) to keep the HBM pipe busy.  Algorithmic traffic 12 L + 8 bytes per list.
+template <int MODE, int NPL>   // MODE 0 = no weights, 1 = IPW table
+__global__ void __launch_bounds__(256) softmax_ce_reg_kernel(const float* __restrict__ scores,
+                                                              const float* __restrict__ labels, int B, int L,
+                                                              const float* __restrict__ table, int table_len,
+                                                              float* __restrict__ dscores, float* __restrict__ sums,
+                                                              unsigned int* counter, float* __restrict__ partials) {
+    griddep_launch();
+    griddep_wait();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int stride = gridDim.x * nw;
+    float tw[NPL];                                   // IPW weight of this lane's positions (loop invariant)
+#pragma unroll
+    for (int e = 0; e < NPL; ++e) {
+        const int l = lane + 32 * e;
+        tw[e] = (MODE == 1 && l < L) ? table[min(l, table_len - 1)] : 1.f;
+    }
+    // D lists of this warp are in flight ahead of the one being reduced (register ring of D + 1 slots)
+    constexpr int D = NPL <= 2 ? 3 : (NPL <= 4 ? 2 : 1);
+    float sbuf[D + 1][NPL], ybuf[D + 1][NPL];
+    auto load = [&](int bb, float* s_, float* y_) {
+#pragma unroll
+        for (int e = 0; e < NPL; ++e) {
+            const int l = lane + 32 * e;
+            const bool ok = bb < B && l < L;
+            s_[e] = ok ? __ldg(scores + (size_t)bb * L + l) : -INFINITY;
+            y_[e] = ok ? __ldg(labels + (size_t)bb * L + l) : 0.f;
+        }
+    };
+    float num = 0.f, den = 0.f;
+    auto reduce_list = [&](const float* sv, const float* yv, int b) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < NPL; ++e) m = fmaxf(m, sv[e]);
+        m = warp_max(m);
+        float pe[NPL], w[NPL];
+        float esum = 0.f, W = 0.f;
+#pragma unroll
+        for (int e = 0; e < NPL; ++e) {
+            const bool ok = lane + 32 * e < L;
+            pe[e] = ok ? expf(sv[e] - m) : 0.f;
+            esum += pe[e];
+            float pw = 1.f;
+            if (MODE == 1) pw = (yv[e] > 0.f) ? tw[e] : 0.f;           // ipw_rank.py:116-128
+            w[e] = ok ? (yv[e] + 1e-7f) * pw : 0.f;
+            W += w[e];
+        }
+        esum = warp_sum(esum);
+        W = warp_sum(W);
+        const float lse = m + logf(esum);
+        const float inv_e = 1.f / esum;
+        float ll = 0.f, dsum = 0.f;
+#pragma unroll
+        for (int e = 0; e < NPL; ++e) {
+            const bool ok = lane + 32 * e < L;
+            const float d = (W != 0.f) ? w[e] / W : 0.f;              // nan_to_num(w / W)
+            w[e] = d;
+            if (ok) ll = fmaf(-d, sv[e] - lse, ll);
+            dsum += d;
+        }
+        ll = warp_sum(ll);
+        dsum = warp_sum(dsum);
+#pragma unroll
+        for (int e = 0; e < NPL; ++e) {
+            const int l = lane + 32 * e;
+            if (l < L) dscores[(size_t)b * L + l] = (pe[e] * inv_e * dsum - w[e]) * W;
+        }
+        num += ll * W;
+        den += W;
+    };
+    int b = blockIdx.x * nw + wid;
+#pragma unroll
+    for (int u = 0; u < D; ++u) load(b + u * stride, sbuf[u], ybuf[u]);
+    while (b < B) {
+#pragma unroll
+        for (int u = 0; u < D + 1; ++u) {
+            if (b < B) {
+                load(b + D * stride, sbuf[(u + D) % (D + 1)], ybuf[(u + D) % (D + 1)]);
+                reduce_list(sbuf[u], ybuf[u], b);
+                b += stride;
+            }
+        }
+    }
+    // block partials [num, den], then the last block adds all of them in a fixed order
+    __shared__ float red[8][2];
+    __shared__ float wide[256][2];
+    if (lane == 0) {
+        red[wid][0] = num;
+        red[wid][1] = den;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        float t = 0.f;
+        for (int q = 0; q < nw; ++q) t += red[q][threadIdx.x];
+        partials[(size_t)blockIdx.x * 2 + threadIdx.x] = t;
+    }
+    if (last_block_ticket(counter, gridDim.x)) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) {
+            a0 += partials[(size_t)q * 2];
+            a1 += partials[(size_t)q * 2 + 1];
+        }
+        wide[threadIdx.x][0] = a0;
+        wide[threadIdx.x][1] = a1;
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            float t = 0.f;
+            for (int q = 0; q < (int)blockDim.x; ++q) t += wide[q][threadIdx.x];
+            sums[threadIdx.x] = t;
+        }
+    }
+}
 
 template <int MODE>   // 0 = no weights, 1 = IPW table, 2 = DLA
 __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict__ scores,
@@ -511,6 +630,23 @@ extern "C" UB200_API int ub200_softmax_ce(const float* scores, const float* labe
     UB_CHECK(workspace_bytes >= loss_ws_bytes(2), 3, "softmax_ce: workspace too small");
     LossWs w = loss_ws(workspace);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (L <= 256) {
+        // register-resident lists (the normal case: list lengths 10-200)
+        int grid = (B + 7) / 8;
+        if (grid > kLossBlocksWide) grid = kLossBlocksWide;
+#define UB_K2(MODE_, NPL_)                                                                                          \
+        launch_k(softmax_ce_reg_kernel<MODE_, NPL_>, grid, 256, 0, st, scores, labels, B, L, table, table_len, dscores, \
+                 sums, w.counter, w.partials)
+        const int npl = (L + 31) / 32;
+        if (weight_mode == 0) {
+            if (npl <= 1) UB_K2(0, 1); else if (npl <= 2) UB_K2(0, 2); else if (npl <= 4) UB_K2(0, 4); else UB_K2(0, 8);
+        } else {
+            if (npl <= 1) UB_K2(1, 1); else if (npl <= 2) UB_K2(1, 2); else if (npl <= 4) UB_K2(1, 4); else UB_K2(1, 8);
+        }
+#undef UB_K2
+        UB_LAUNCH_CHECK("softmax_ce_reg_kernel");
+        return 0;
+    }
     const int grid = loss_grid(B, 8);
     if (weight_mode == 0)
         launch_k(softmax_ce_kernel<0>, grid, 256, 0, st, scores, labels, B, L, nullptr, 0, nullptr, nullptr, dscores, nullptr,

@@ -46,7 +46,8 @@ class RankerEngine(object):
         self.params = torch.zeros(self.P, **f32)
         # gradient buffer with E trailing floats for the loss normalisers / EM partials, so that data-parallel
         # ranks need ONE all-reduce per step
-        self.gradbuf = torch.zeros(self.P + self.E, **f32)
+        self.peer = None
+        self.gradbuf = self._alloc_gradbuf(f32)
         self.grads = self.gradbuf[:self.P]
         self.extra = self.gradbuf[self.P:]
         self.state_sum = torch.zeros(self.P, **f32)
@@ -56,10 +57,86 @@ class RankerEngine(object):
         self._loss_ws = None
         self._pin = None
         self._dev = None
-        self._pack_threads = int(os.environ.get("UB200_PACK_THREADS", str(min(16, os.cpu_count() or 1))))
+        # host packer threads: the ranks of a node share its cores (torchrun exports LOCAL_WORLD_SIZE); spinning workers
+        # of 8 ranks x 16 threads on 16 cores would starve each other
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        self._pack_threads = int(os.environ.get("UB200_PACK_THREADS",
+                                                str(max(1, min(16, (os.cpu_count() or 1) // local_world)))))
         self._pack_chunks = int(os.environ.get("UB200_PACK_CHUNKS", "6"))
         self._scores = {}
         self._dscores = {}
+
+    # ---- data-parallel exchange buffer ----------------------------------------------------------------
+    def _alloc_gradbuf(self, f32):
+        """Single GPU: a plain device buffer.  Data parallel (NCCL process group, one rank per GPU of one node): the
+        buffer and a flag array are allocated in SYMMETRIC memory so that every rank can read every peer's gradients
+        over NVLink (csrc/peer.cu); if symmetric memory is unavailable the step falls back to ONE NCCL all-reduce."""
+        import torch.distributed as dist
+        from .learning_algorithm.base_algorithm import B200Algorithm
+        n = self.P + self.E
+        # NOTE: in data-parallel mode constructing an engine is a COLLECTIVE operation (symmetric-memory rendezvous):
+        # every rank must build the same rankers in the same order, like wrapping a module in DDP
+        if B200Algorithm.world_size() <= 1 or os.environ.get("UB200_DP_PEER", "1") == "0" or \
+                dist.get_backend() != "nccl":
+            return torch.zeros(n, **f32)
+        try:
+            import torch.distributed._symmetric_memory as symm
+            world, rank = dist.get_world_size(), dist.get_rank()
+            group = dist.group.WORLD
+            buf = symm.empty(n, dtype=torch.float32, device=self.device)
+            flags = symm.empty(max(64, 2 * world), dtype=torch.int32, device=self.device)
+            buf.zero_()
+            flags.zero_()
+            # fused exchange + optimizer (push model): per-rank inboxes [2][world][n] and per-block flags
+            inbox = symm.empty(int(lib.ub200_dp_inbox_bytes(world, n)) // 4, dtype=torch.float32, device=self.device)
+            pflags = symm.empty(int(lib.ub200_dp_flag_bytes(world)) // 4, dtype=torch.int32, device=self.device)
+            inbox.zero_()
+            pflags.zero_()
+            hb = symm.rendezvous(buf, group)
+            hf = symm.rendezvous(flags, group)
+            hi = symm.rendezvous(inbox, group)
+            hp = symm.rendezvous(pflags, group)
+            torch.cuda.synchronize()
+            dist.barrier()                        # every rank's flags are zero before anybody signals
+            PtrArr = ctypes.c_void_p * world
+            self.peer = {
+                "bufs": PtrArr(*[int(p) for p in hb.buffer_ptrs]), "flags": PtrArr(*[int(p) for p in hf.buffer_ptrs]),
+                "inbox": PtrArr(*[int(p) for p in hi.buffer_ptrs]), "pflags": PtrArr(*[int(p) for p in hp.buffer_ptrs]),
+                "rank": rank, "world": world, "handles": (hb, hf, hi, hp), "tensors": (flags, inbox, pflags),
+                "scratch": torch.zeros(n, **f32),
+                "ctl": torch.zeros(int(lib.ub200_peer_ctl_bytes()), dtype=torch.uint8, device=self.device),
+                "dp_ctl": torch.zeros(int(lib.ub200_dp_ctl_bytes()), dtype=torch.uint8, device=self.device),
+            }
+            assert int(hb.buffer_ptrs[rank]) == buf.data_ptr()
+            return buf
+        except Exception as e:  # noqa: BLE001  (no symmetric memory on this system: NCCL all-reduce instead)
+            if os.environ.get("UB200_DP_PEER", "1") == "2":
+                raise
+            print("ultra_pytorch_b200: symmetric memory unavailable (%s); data-parallel steps use ncclAllReduce" % (e,))
+            self.peer = None
+            return torch.zeros(n, **f32)
+
+    def allreduce_gradbuf(self):
+        """ONE exchange per step over [DNN grads | loss normalisers | EM / DenoisingNet partials]."""
+        import torch.distributed as dist
+        if self.peer is not None:
+            p = self.peer
+            check(lib.ub200_peer_allreduce(p["bufs"], p["flags"], p["rank"], p["world"], _ptr(p["scratch"]),
+                                           self.gradbuf.numel(), _ptr(p["ctl"]), _stream()), "ub200_peer_allreduce")
+        else:
+            dist.all_reduce(self.gradbuf, op=dist.ReduceOp.SUM)
+
+    def dp_reduce_update(self, state_sum, den, scale_const, max_norm, lr, mode, norm_out=None):
+        """Fused exchange + optimizer of the ranker's parameters (csrc/peer.cu: dp_reduce_update_kernel): SUM of the
+        whole flat buffer over the ranks through NVLink peer memory, then clip_grad_norm_ + Adagrad / SGD on the summed
+        gradient, in ONE kernel.  `den` is a view INTO self.gradbuf (the normaliser is read after the sum)."""
+        p = self.peer
+        den_index = -1 if den is None else (den.data_ptr() - self.gradbuf.data_ptr()) // 4
+        assert den is None or 0 <= den_index < self.gradbuf.numel()
+        check(lib.ub200_dp_reduce_update(_ptr(self.gradbuf), self.gradbuf.numel(), p["inbox"], p["pflags"], p["rank"],
+                                         p["world"], _ptr(self.params), _ptr(state_sum), self.P, den_index,
+                                         float(scale_const), float(max_norm), float(lr), int(mode), _ptr(norm_out),
+                                         _ptr(p["dp_ctl"]), _stream()), "ub200_dp_reduce_update")
 
     # ---- parameter views -------------------------------------------------------------------------
     def layer_slices(self):

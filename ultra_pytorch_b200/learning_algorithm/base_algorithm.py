@@ -85,7 +85,8 @@ class B200Algorithm(_reference_base()):
 
     def run_step(self, st):
         """device_step(st), replayed from CUDA graphs once the (B, L, buffer) combination has been seen twice."""
-        dp = self.world_size() > 1
+        # data parallel over peer memory: the exchange is one of OUR kernels, so the whole step is one graph again
+        dp = self.world_size() > 1 and self.engine.peer is None
         if not self.USE_GRAPH or (dp and not self.USE_GRAPH_DP):
             return self.device_step(st)
         key = (st.B, st.L, st.feats.data_ptr(), st.docid.data_ptr())
@@ -149,8 +150,21 @@ class B200Algorithm(_reference_base()):
     def _allreduce_gradbuf(self):
         """ONE all-reduce per step over [DNN grads | loss normalisers | EM / DenoisingNet partials]."""
         if self.world_size() > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.engine.gradbuf, op=dist.ReduceOp.SUM)
+            self.engine.allreduce_gradbuf()
+
+    def _exchange_and_update(self, state_sum, den, scale_const, lr, mode, norm_out):
+        """The end of every training step: exchange of the flat gradient buffer between the data-parallel ranks (if
+        any) + clip_grad_norm_ + optimizer step of the ranker (base_algorithm.py:208-226).  With peer memory both
+        happen in one kernel; otherwise ONE all-reduce (NCCL) and the single-GPU optimizer kernel."""
+        eng = self.engine
+        mg = self.hparams.max_gradient_norm
+        fused = os.environ.get("UB200_DP_FUSED", "1") != "0"
+        if self.world_size() > 1 and eng.peer is not None and fused:
+            eng.dp_reduce_update(state_sum, den, scale_const, mg, lr, mode, norm_out)
+            return
+        if self._phase is None:
+            self._allreduce_gradbuf()
+        eng.clip_update(eng.params, eng.grads, state_sum, den, scale_const, mg, lr, mode, norm_out)
 
     # ---- input staging --------------------------------------------------------------------------------
     def _stage(self, input_feed, list_size):

@@ -87,16 +87,15 @@ class DLA(B200Algorithm):
             eng.backward(st.feats, docid, L, B, dscores)
         if self._phase == "pre":
             return None
-        if self._phase is None:
-            self._allreduce_gradbuf()
         # fresh optimizers every step (dla.py:153-154): accumulator starts from zero -> mode 1; the two parameter
-        # groups are clipped separately (dla.py:161-163)
+        # groups are clipped separately (dla.py:161-163).  The ranker's update goes first: in data-parallel mode it
+        # carries the exchange of the whole flat buffer, DenoisingNet gradients and normalisers included.
         mode = self._opt_mode(fresh=True)
         mg = self.hparams.max_gradient_norm
+        self._exchange_and_update(None, self._sums[1:2], float(self.hparams.ranker_loss_weight), self.learning_rate,
+                                  mode, self._norms[1:2])
         eng.clip_update(flat, self._dprop, None, self._sums[3:4], 1.0, mg, self.propensity_learning_rate, mode,
                         self._norms[0:1])
-        eng.clip_update(eng.params, eng.grads, None, self._sums[1:2], float(self.hparams.ranker_loss_weight), mg,
-                        self.learning_rate, mode, self._norms[1:2])
         self._scal[:4].copy_(self._sums)
         self._scal[4:6].copy_(self._norms)
         return self._scal

@@ -31,8 +31,8 @@ class LambdaRank(PairDebias):
     def _update(self, out, L, B):
         # gains are normalised by ONE batch-global IDCG (lambda_rank.py:263-266, 277): applied here as 1/idcg
         eng = self.engine
-        eng.clip_update(eng.params, eng.grads, eng.state_sum, out[2 * L + 1:2 * L + 2], 1.0,
-                        self.hparams.max_gradient_norm, self.learning_rate, self._opt_mode(), eng.norm)
+        self._exchange_and_update(eng.state_sum, out[2 * L + 1:2 * L + 2], 1.0, self.learning_rate, self._opt_mode(),
+                                  eng.norm)
 
     def train(self, input_feed):
         """lambda_rank.py:96-216."""

@@ -45,10 +45,7 @@ class NavieAlgorithm(B200Algorithm):
             eng.backward(st.feats, docid, L, B, dscores)
         if self._phase == "pre":
             return None
-        if self._phase is None:
-            self._allreduce_gradbuf()
-        eng.clip_update(eng.params, eng.grads, eng.state_sum, sums[1:2], 1.0, self.hparams.max_gradient_norm,
-                        self.learning_rate, self._opt_mode(), eng.norm)
+        self._exchange_and_update(eng.state_sum, sums[1:2], 1.0, self.learning_rate, self._opt_mode(), eng.norm)
         return sums
 
     def train(self, input_feed):

@@ -50,9 +50,7 @@ class PairDebias(B200Algorithm):
             eng.backward(st.feats, docid, L, B, dscores)
         if self._phase == "pre":
             return None
-        if self._phase is None:
-            self._allreduce_gradbuf()
-        self._update(out, L, B)
+        self._update(out, L, B)                          # exchange (data parallel) + clip + optimizer
         self._scal.copy_(out[2 * L:2 * L + 2])          # loss (+ idcg) before anything reuses the buffer
         eng.em_update(self.t_plus, self.t_minus, out, self.hparams.EM_step_size, self.hparams.regulation_p,
                       self.SAFE_DIV)
@@ -62,8 +60,7 @@ class PairDebias(B200Algorithm):
         # the reference's loss carries a x batch_size factor ([B]*[B,1] broadcast, base_algorithm.py:246-247)
         eng = self.engine
         self._b_global = float(B * self.world_size())
-        eng.clip_update(eng.params, eng.grads, eng.state_sum, None, self._b_global, self.hparams.max_gradient_norm,
-                        self.learning_rate, self._opt_mode(), eng.norm)
+        self._exchange_and_update(eng.state_sum, None, self._b_global, self.learning_rate, self._opt_mode(), eng.norm)
 
     def train(self, input_feed):
         """pairwise_debias.py:106-174."""
