@@ -48,10 +48,26 @@ struct ListStats {
     float dsum;   // sum of d (1, or 0 for an empty list)
 };
 
-// NA / IPW, lists of up to 32 * NPL positions: the list lives in registers (one global read of scores and labels,
-// one exponential per element), the next list of the warp is prefetched while the current one is reduced, and the
-// grid is large enough (up to 8 blocks per SM) to keep the HBM pipe busy.  Algorithmic traffic 12 L + 8 bytes per list.
-template <int MODE, int NPL>   // MODE 0 = no weights, 1 = IPW table
+// NA / IPW, lists of up to G * EPL positions: a list is owned by a GROUP of G lanes (8, 16 or 32), EPL elements per
+// lane, so a warp reduces 32 / G lists at once (4 lists of 40 positions: 3 shuffle steps per reduction instead of 5 and
+// no idle half-warp) and the whole list lives in registers: one global read of scores and labels, one exponential
+// per element, the next lists prefetched while the current ones are reduced.  Algorithmic traffic 12 L + 8 bytes per
+// list; ncu showed the warp-per-list form issue-bound (325 warp instructions per list, 81 % issue-active at 15 % DRAM
+// throughput) - this form needs ~60.
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int G>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <int MODE, int G, int EPL>   // MODE 0 = no weights, 1 = IPW table
 __global__ void __launch_bounds__(256) softmax_ce_reg_kernel(const float* __restrict__ scores,
                                                               const float* __restrict__ labels, int B, int L,
                                                               const float* __restrict__ table, int table_len,
@@ -59,37 +75,43 @@ __global__ void __launch_bounds__(256) softmax_ce_reg_kernel(const float* __rest
                                                               unsigned int* counter, float* __restrict__ partials) {
     griddep_launch();
     griddep_wait();
+    constexpr int LPW = 32 / G;                      // lists per warp
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int stride = gridDim.x * nw;
-    float tw[NPL];                                   // IPW weight of this lane's positions (loop invariant)
+    const int gl = lane % G, gi = lane / G;          // lane inside the group, group inside the warp
+    const int stride = gridDim.x * nw * LPW;
+    float tw[EPL];                                   // IPW weight of this lane's positions (loop invariant)
 #pragma unroll
-    for (int e = 0; e < NPL; ++e) {
-        const int l = lane + 32 * e;
+    for (int e = 0; e < EPL; ++e) {
+        const int l = gl + G * e;
         tw[e] = (MODE == 1 && l < L) ? table[min(l, table_len - 1)] : 1.f;
     }
-    // D lists of this warp are in flight ahead of the one being reduced (register ring of D + 1 slots)
-    constexpr int D = NPL <= 2 ? 3 : (NPL <= 4 ? 2 : 1);
-    float sbuf[D + 1][NPL], ybuf[D + 1][NPL];
+    float sv[EPL], yv[EPL], sn[EPL], yn[EPL];
     auto load = [&](int bb, float* s_, float* y_) {
 #pragma unroll
-        for (int e = 0; e < NPL; ++e) {
-            const int l = lane + 32 * e;
+        for (int e = 0; e < EPL; ++e) {
+            const int l = gl + G * e;
             const bool ok = bb < B && l < L;
             s_[e] = ok ? __ldg(scores + (size_t)bb * L + l) : -INFINITY;
             y_[e] = ok ? __ldg(labels + (size_t)bb * L + l) : 0.f;
         }
     };
+    int b = (blockIdx.x * nw + wid) * LPW + gi;
+    load(b, sv, yv);
     float num = 0.f, den = 0.f;
-    auto reduce_list = [&](const float* sv, const float* yv, int b) {
+    // every lane of the warp runs the same number of iterations (shuffles); groups past the end work on empty lists
+    const int b_warp0 = (blockIdx.x * nw + wid) * LPW;
+    for (int bw = b_warp0; bw < B; bw += stride, b += stride) {
+        load(b + stride, sn, yn);                    // in flight while these lists are reduced
+        const bool live = b < B;
         float m = -INFINITY;
 #pragma unroll
-        for (int e = 0; e < NPL; ++e) m = fmaxf(m, sv[e]);
-        m = warp_max(m);
-        float pe[NPL], w[NPL];
+        for (int e = 0; e < EPL; ++e) m = fmaxf(m, sv[e]);
+        m = group_max<G>(m);
+        float pe[EPL], w[EPL];
         float esum = 0.f, W = 0.f;
 #pragma unroll
-        for (int e = 0; e < NPL; ++e) {
-            const bool ok = lane + 32 * e < L;
+        for (int e = 0; e < EPL; ++e) {
+            const bool ok = live && gl + G * e < L;
             pe[e] = ok ? expf(sv[e] - m) : 0.f;
             esum += pe[e];
             float pw = 1.f;
@@ -97,42 +119,40 @@ __global__ void __launch_bounds__(256) softmax_ce_reg_kernel(const float* __rest
             w[e] = ok ? (yv[e] + 1e-7f) * pw : 0.f;
             W += w[e];
         }
-        esum = warp_sum(esum);
-        W = warp_sum(W);
+        esum = group_sum<G>(esum);
+        W = group_sum<G>(W);
         const float lse = m + logf(esum);
         const float inv_e = 1.f / esum;
         float ll = 0.f, dsum = 0.f;
 #pragma unroll
-        for (int e = 0; e < NPL; ++e) {
-            const bool ok = lane + 32 * e < L;
+        for (int e = 0; e < EPL; ++e) {
+            const bool ok = live && gl + G * e < L;
             const float d = (W != 0.f) ? w[e] / W : 0.f;              // nan_to_num(w / W)
             w[e] = d;
             if (ok) ll = fmaf(-d, sv[e] - lse, ll);
             dsum += d;
         }
-        ll = warp_sum(ll);
-        dsum = warp_sum(dsum);
+        ll = group_sum<G>(ll);
+        dsum = group_sum<G>(dsum);
+        if (live) {
 #pragma unroll
-        for (int e = 0; e < NPL; ++e) {
-            const int l = lane + 32 * e;
-            if (l < L) dscores[(size_t)b * L + l] = (pe[e] * inv_e * dsum - w[e]) * W;
-        }
-        num += ll * W;
-        den += W;
-    };
-    int b = blockIdx.x * nw + wid;
-#pragma unroll
-    for (int u = 0; u < D; ++u) load(b + u * stride, sbuf[u], ybuf[u]);
-    while (b < B) {
-#pragma unroll
-        for (int u = 0; u < D + 1; ++u) {
-            if (b < B) {
-                load(b + D * stride, sbuf[(u + D) % (D + 1)], ybuf[(u + D) % (D + 1)]);
-                reduce_list(sbuf[u], ybuf[u], b);
-                b += stride;
+            for (int e = 0; e < EPL; ++e) {
+                const int l = gl + G * e;
+                if (l < L) dscores[(size_t)b * L + l] = (pe[e] * inv_e * dsum - w[e]) * W;
+            }
+            if (gl == 0) {
+                num += ll * W;
+                den += W;
             }
         }
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+            sv[e] = sn[e];
+            yv[e] = yn[e];
+        }
     }
+    num = warp_sum(num);                             // lanes with gl != 0 hold zeros
+    den = warp_sum(den);
     // block partials [num, den], then the last block adds all of them in a fixed order
     __shared__ float red[8][2];
     __shared__ float wide[256][2];
@@ -631,18 +651,33 @@ extern "C" UB200_API int ub200_softmax_ce(const float* scores, const float* labe
     LossWs w = loss_ws(workspace);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (L <= 256) {
-        // register-resident lists (the normal case: list lengths 10-200)
-        int grid = (B + 7) / 8;
+        // register-resident lists (the normal case: list lengths 10-200): G lanes per list, EPL elements per lane
+        const int G = L <= 64 ? 8 : (L <= 128 ? 16 : 32);
+        const int epl = (L + G - 1) / G;
+        const int lists_per_block = 8 * (32 / G);
+        int grid = (B + lists_per_block - 1) / lists_per_block;
         if (grid > kLossBlocksWide) grid = kLossBlocksWide;
-#define UB_K2(MODE_, NPL_)                                                                                          \
-        launch_k(softmax_ce_reg_kernel<MODE_, NPL_>, grid, 256, 0, st, scores, labels, B, L, table, table_len, dscores, \
-                 sums, w.counter, w.partials)
-        const int npl = (L + 31) / 32;
-        if (weight_mode == 0) {
-            if (npl <= 1) UB_K2(0, 1); else if (npl <= 2) UB_K2(0, 2); else if (npl <= 4) UB_K2(0, 4); else UB_K2(0, 8);
-        } else {
-            if (npl <= 1) UB_K2(1, 1); else if (npl <= 2) UB_K2(1, 2); else if (npl <= 4) UB_K2(1, 4); else UB_K2(1, 8);
+#define UB_K2(MODE_, G_, EPL_)                                                                                       \
+        launch_k(softmax_ce_reg_kernel<MODE_, G_, EPL_>, grid, 256, 0, st, scores, labels, B, L, table, table_len,  \
+                 dscores, sums, w.counter, w.partials)
+#define UB_K2_G8(MODE_)                                                                                                \
+        switch (epl) {                                                                                                 \
+            case 1: UB_K2(MODE_, 8, 1); break;                                                                         \
+            case 2: UB_K2(MODE_, 8, 2); break;                                                                         \
+            case 3: UB_K2(MODE_, 8, 3); break;                                                                         \
+            case 4: UB_K2(MODE_, 8, 4); break;                                                                         \
+            case 5: UB_K2(MODE_, 8, 5); break;                                                                         \
+            case 6: UB_K2(MODE_, 8, 6); break;                                                                         \
+            default: UB_K2(MODE_, 8, 8); break;                                                                        \
         }
+        if (weight_mode == 0) {
+            if (G == 8) { UB_K2_G8(0) } else if (G == 16) { if (epl <= 6) UB_K2(0, 16, 6); else UB_K2(0, 16, 8); }
+            else { if (epl <= 6) UB_K2(0, 32, 6); else UB_K2(0, 32, 8); }
+        } else {
+            if (G == 8) { UB_K2_G8(1) } else if (G == 16) { if (epl <= 6) UB_K2(1, 16, 6); else UB_K2(1, 16, 8); }
+            else { if (epl <= 6) UB_K2(1, 32, 6); else UB_K2(1, 32, 8); }
+        }
+#undef UB_K2_G8
 #undef UB_K2
         UB_LAUNCH_CHECK("softmax_ce_reg_kernel");
         return 0;
