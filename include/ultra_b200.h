@@ -162,6 +162,16 @@ UB200_API int ub200_clip_update(float* params, float* grads, float* state_sum, s
                       float max_norm, float lr, int mode, float* norm_out,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- N3: Plackett-Luce re-ranking for the stochastic online simulation ------------------------------------------
+ * Replaces the per-query host loop of StochasticOnlineSimulationFeed.simulate_clicks_online
+ * (stochastic_online_simulation_feed.py:100-177: np.random.choice(list_len, replace=False, p=softmax(tau * scores))).
+ * scores [B, L] f32; docid [L, B] i32 position-major with PAD id == n_docs, or NULL (every position valid);
+ * perm [B, L] i32: perm[b][r] = original position of the document ranked r-th; positions at or behind the list's
+ * length (1 + last real document) stay in place.  Gumbel-top-k with Philox4x32-10 noise keyed by (seed, offset, b, l):
+ * the same arguments give the same permutations.  Distribution-level parity with the reference (tested). */
+UB200_API int ub200_pl_sample(const float* scores, const int32_t* docid, int n_docs, int B, int L, float tau,
+                    unsigned long long seed, unsigned long long offset, int32_t* perm, void* stream);
+
 /* ---- C1: data-parallel exchange of the flat gradient buffer over NVLink peer memory ----------------------------------
  * Nothing in the reference corresponds to this (it is single-process); it is the ONE collective of a data-parallel
  * step: the in-place SUM over ranks of [DNN grads | loss normalisers | EM / DenoisingNet partials].

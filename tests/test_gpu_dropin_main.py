@@ -21,6 +21,14 @@ SETTINGS = {
     # the vectorised feed drop-in together with the B200 algorithm
     "pairdebias_b200feed": ("ultra_pytorch_b200.learning_algorithm.PairDebias",
                             "ultra_pytorch_b200.input_layer.ClickSimulationFeed"),
+    # BASELINE config 5: online simulation + DLA, with the reference's own feed (it calls validation(feed, True) and
+    # re-ranks on the host) and with the drop-in whose Plackett-Luce sampling runs on the GPU
+    "dla_online_reffeed": ("ultra_pytorch_b200.learning_algorithm.DLA",
+                           "ultra.input_layer.StochasticOnlineSimulationFeed"),
+    "dla_online_b200feed": ("ultra_pytorch_b200.learning_algorithm.DLA",
+                            "ultra_pytorch_b200.input_layer.StochasticOnlineSimulationFeed"),
+    # the Linear ranker
+    "ipw_linear": ("ultra_pytorch_b200.learning_algorithm.IPWrank", "ultra.input_layer.ClickSimulationFeed"),
 }
 
 
@@ -41,8 +49,8 @@ def test_unmodified_main_py_drives_the_plugin(algo, tmp_path):
         "train_input_feed": feed, "train_input_hparams": "",
         "valid_input_feed": "ultra.input_layer.DirectLabelFeed", "valid_input_hparams": "",
         "test_input_feed": "ultra.input_layer.DirectLabelFeed", "test_input_hparams": "",
-        "ranking_model": "ultra_pytorch_b200.ranking_model.DNN",
-        "ranking_model_hparams": "hidden_layer_sizes=[64, 32]",
+        "ranking_model": "ultra_pytorch_b200.ranking_model.%s" % ("Linear" if algo.endswith("_linear") else "DNN"),
+        "ranking_model_hparams": "" if algo.endswith("_linear") else "hidden_layer_sizes=[64, 32]",
         "learning_algorithm": cls, "learning_algorithm_hparams": "",
         "metrics": ["err", "ndcg"], "metrics_topn": [1, 3, 5, 10], "objective_metric": "ndcg_10",
     }

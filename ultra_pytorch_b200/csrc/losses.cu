@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) softmax_ce_reg_kernel(const float* __rest
 #pragma unroll
         for (int e = 0; e < EPL; ++e) {
             const bool ok = live && gl + G * e < L;
-            pe[e] = ok ? expf(sv[e] - m) : 0.f;
+            pe[e] = ok ? __expf(sv[e] - m) : 0.f;                      // ex2.approx: |rel err| < 2^-21, argument <= 0
             esum += pe[e];
             float pw = 1.f;
             if (MODE == 1) pw = (yv[e] > 0.f) ? tw[e] : 0.f;           // ipw_rank.py:116-128
@@ -123,11 +123,12 @@ __global__ void __launch_bounds__(256) softmax_ce_reg_kernel(const float* __rest
         W = group_sum<G>(W);
         const float lse = m + logf(esum);
         const float inv_e = 1.f / esum;
+        const float inv_W = (W != 0.f) ? 1.f / W : 0.f;               // nan_to_num(w / W): one reciprocal per list
         float ll = 0.f, dsum = 0.f;
 #pragma unroll
         for (int e = 0; e < EPL; ++e) {
             const bool ok = live && gl + G * e < L;
-            const float d = (W != 0.f) ? w[e] / W : 0.f;              // nan_to_num(w / W)
+            const float d = w[e] * inv_W;
             w[e] = d;
             if (ok) ll = fmaf(-d, sv[e] - lse, ll);
             dsum += d;

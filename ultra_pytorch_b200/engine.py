@@ -299,6 +299,15 @@ class RankerEngine(object):
         check(lib.ub200_em_update(_ptr(t_plus), _ptr(t_minus), _ptr(out), t_plus.numel(), float(em_step),
                                   float(reg_p), int(bool(safe_div)), _stream()), "ub200_em_update")
 
+    # ---- N3: Plackett-Luce re-ranking (online simulation feeds) -------------------------------------------
+    def pl_sample(self, scores, docid, n_docs, tau, seed, offset=0):
+        """scores [B, L] cuda f32, docid [L, B] cuda i32 (PAD id == n_docs) or None -> perm [B, L] cuda i32."""
+        B, L = scores.shape
+        perm = torch.empty(B, L, dtype=torch.int32, device=self.device)
+        check(lib.ub200_pl_sample(_ptr(scores), _ptr(docid), int(n_docs), B, L, float(tau), int(seed), int(offset),
+                                  _ptr(perm), _stream()), "ub200_pl_sample")
+        return perm
+
     # ---- optimizer ------------------------------------------------------------------------------------
     def clip_update(self, params, grads, state_sum, den, scale_const, max_norm, lr, mode, norm_out=None):
         n = params.numel()

@@ -186,6 +186,7 @@ class B200Algorithm(_reference_base()):
         self.model.eval()
         L = self.max_candidate_num
         st = self._stage(input_feed, L)
+        self._last_validation_stage = st          # the online feeds re-rank on the device from these buffers
         eng = self.engine
         with torch.no_grad():
             scores = eng.forward(st.feats, st.docid.view(-1), L, st.B, training=False)
