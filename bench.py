@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py - queries/sec of the ULTRA training hot path on B200 (contract: see the task statement / DESIGN.md).
 
-    python bench.py --gpus 1 --steps 200 --warmup 20                     # the B200 arm (this repo's kernels)
+    python bench.py --gpus 1 --steps 1000 --warmup 20                    # the B200 arm (this repo's kernels)
     python bench.py --impl reference --gpus 1 --steps 10 --warmup 3      # the reference's own CPU path
     torchrun --nproc-per-node N ... bench.py --gpus N ...                # data-parallel, one rank per GPU
 
@@ -35,7 +35,7 @@ L2_BYTES = 126 * 1024 * 1024
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2_ipw_mslr10k")
