@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=0, help="override the batch size B (default: workload's, 256)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the informational feed + train leg")
     ap.add_argument("--cpu-steps", type=int, default=0, help="timed steps of the cpu_baseline sample (0 = auto)")
     return ap.parse_args()
 
@@ -98,6 +99,11 @@ def main_reference(args):
         "e2e": {"value": r["queries_per_s"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if r.get("feed_ms_per_step") is not None:
+        tot = r["feed_ms_per_step"] + r["ms_per_step"]
+        line["pipeline"] = {"what": "reference feed get_batch + train() per step (what main.py's loop runs)",
+                            "unit": "queries/s", "value": round(w["B"] / (tot / 1e3), 1), "ms_per_step": round(tot, 3),
+                            "feed_ms_per_step": r["feed_ms_per_step"]}
     print(json.dumps(line))
 
 
@@ -305,6 +311,31 @@ def main_b200(args):
            "h2d_bytes_per_step": int(model.last_h2d_bytes), "d2h_bytes_per_step": int(model.last_d2h_bytes),
            "ms_per_step": round(1e3 * e2e_s / args.steps, 4)}
 
+    # ---- pipeline leg (informational): what main.py's loop does per step - feed.get_batch() + model.train() - with
+    # the drop-in ClickSimulationFeed on a synthetic data set, (a) in the reference's feed format (feature rows copied
+    # per batch) and (b) with the data set resident in HBM (input_layer/resident.py: only ids + labels move) ----
+    pipeline = None
+    if w["labels"] == "click" and not args.no_pipeline:
+        import random as _random
+        from ultra_pytorch_b200.input_layer import ClickSimulationFeed
+        _random.seed(1234 + rank)
+        ds = synth.synthetic_dataset(2048, L, F, seed=7 + rank)
+        pipeline = {"what": "ClickSimulationFeed.get_batch + train() per step, synthetic data set of 2048 queries",
+                    "unit": "queries/s"}
+        n_pipe = max(20, min(args.steps, 200))
+        for name, hp in (("host_rows", ""), ("resident", "resident_features=True")):
+            feeder = ClickSimulationFeed(model, B, "click_model_json=%s,%s" % (synth.PBM_JSON, hp))
+            for _ in range(6):
+                model.train(feeder.get_batch(ds, check_validation=True)[0])
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_pipe):
+                model.train(feeder.get_batch(ds, check_validation=True)[0])
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            pipeline[name] = {"value": round(world * B * n_pipe / dt, 1), "ms_per_step": round(1e3 * dt / n_pipe, 4),
+                              "h2d_bytes_per_step": int(model.last_h2d_bytes)}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": "queries/s", "n_gpus": world, "steps": args.steps,
@@ -318,6 +349,8 @@ def main_b200(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "kernels_per_step": int(per_step),
             "roofline": roofline,
         }
+        if pipeline is not None:
+            line["pipeline"] = pipeline
         if world == 1 and not args.no_cpu_baseline:
             n = args.cpu_steps or cpu_steps_for(args.workload)
             r = run_cpu_arm(args.workload, args.batch, n, 3)

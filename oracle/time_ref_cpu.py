@@ -65,10 +65,17 @@ def main():
                 for i in range(a.steps):
                     model.train(dict(feeds[i % n_feeds]))
                 dt = time.perf_counter() - t0
+                # what main.py's loop pays per step besides train(): the reference feed's get_batch (main.py:154)
+                n_fb = 3
+                t1 = time.perf_counter()
+                for _ in range(n_fb):
+                    feeder.get_batch(ds, check_validation=True)
+                feed_ms = 1e3 * (time.perf_counter() - t1) / n_fb
         nb = len(feeds[0][model.labels_name[0]])
         assert nb == B or w["labels"] != "click", (nb, B)
         B = nb
     else:
+        feed_ms = None
         kind = "port"
         from oracle import ultra_oracle as uo
         rs = np.random.RandomState(0)
@@ -106,7 +113,7 @@ def main():
         pass
     print(json.dumps({
         "queries_per_s": round(B * a.steps / dt, 2), "ms_per_step": round(1e3 * dt / a.steps, 3), "cores": cores,
-        "kind": kind, "cpu": cpu,
+        "kind": kind, "cpu": cpu, "feed_ms_per_step": None if feed_ms is None else round(feed_ms, 3),
         "sample": "%d timed train() steps (+%d warm-up) of %s B=%d L=%d F=%d DNN%s on %d host threads (%s), "
                   "pre-built feeds, torch %s" % (a.steps, a.warmup, w["algo"], B, L, F, hidden, cores, cpu,
                                                  torch.__version__)}))

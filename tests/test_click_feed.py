@@ -123,3 +123,32 @@ def test_matches_reference_feed(tmp_path, oracle_mode):
             n += B
         sigma = np.sqrt(np.maximum(ta + tb, 1.0))
         assert (np.abs(ta - tb) < 5 * sigma).all(), (ta, tb)
+
+
+def test_resident_feed_is_a_valid_reference_format_feed_with_global_ids(tmp_path):
+    """resident_features=True (input_layer/resident.py): `letor_features` is a zero-copy view of the data set's whole
+    matrix, doc ids are global row ids and PAD = number of rows - the gathered rows equal the per-batch copy of the
+    default mode, list for list."""
+    from ultra_pytorch_b200.input_layer.resident import ResidentFeatures
+    L, F, B = 7, 5, 16
+    ds = FakeData(40, L, F)
+    plain, _ = _ours(tmp_path, L, F, B, "oracle_mode=True")
+    res, _ = _ours(tmp_path, L, F, B, "oracle_mode=True,resident_features=True")
+    fa, _ = plain.get_next_batch(3, ds)
+    fb, _ = res.get_next_batch(3, ds)
+    assert isinstance(fb["letor_features"], ResidentFeatures) and isinstance(fb["letor_features"], np.ndarray)
+    assert fb["letor_features"].shape == (len(ds.features), F)
+    assert np.shares_memory(fb["letor_features"], res._features)
+    da = np.stack([fa["docid_input%d" % l] for l in range(L)], axis=1).astype(int)
+    db = np.stack([fb["docid_input%d" % l] for l in range(L)], axis=1).astype(int)
+    na, nb = fa["letor_features"].shape[0], fb["letor_features"].shape[0]
+    assert np.array_equal(da == na, db == nb)                                   # same PAD pattern
+    # what the reference's get_ranking_scores would gather (zero PAD row appended at index n, base_algorithm.py:148-152)
+    ga = np.concatenate([fa["letor_features"], np.zeros((1, F))])[da]
+    gb = np.concatenate([np.asarray(fb["letor_features"]), np.zeros((1, F))])[db]
+    assert np.array_equal(ga, gb)
+    for l in range(L):
+        assert np.array_equal(fa["label%d" % l], fb["label%d" % l])
+    # a second batch re-uses the same view object (the engine keys its device copy on it)
+    fc, _ = res.get_next_batch(0, ds)
+    assert fc["letor_features"] is fb["letor_features"]

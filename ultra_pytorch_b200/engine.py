@@ -194,6 +194,9 @@ class RankerEngine(object):
         docid_arrays / label_arrays: L arrays of [B] (f32 in the feeds, base_algorithm.py:176-186).
         Device layout: docid i32 [L, B] (position-major) | labels f32 [B, L] |
                        feats f32 [n_docs+1, F] (last row = zero PAD, base_algorithm.py:148-149)."""
+        from .input_layer.resident import ResidentFeatures
+        if isinstance(letor_features, ResidentFeatures):
+            return self._stage_resident(letor_features, docid_arrays, label_arrays)
         feats = np.asarray(letor_features)
         n_docs = feats.shape[0] if feats.ndim == 2 else 0
         L = len(docid_arrays)
@@ -239,6 +242,53 @@ class RankerEngine(object):
         # the pinned buffer is reused next step: callers sync once per step (loss read-back) before re-staging
         self._dev[:total].copy_(self._pin[:total], non_blocking=True)
         return self.staged_views(self._dev, L, B, n_docs)
+
+    def _stage_resident(self, feats, docid_arrays, label_arrays):
+        """The feed's `letor_features` is the data set's whole feature matrix (input_layer/resident.py) and the doc ids
+        are global row ids: keep the matrix in HBM (uploaded once, fp32, zero PAD row appended) and move only ids and
+        labels per step."""
+        n_rows, F = feats.shape
+        if F != self.F:
+            raise _capi.UltraB200Error("resident feature matrix has %d columns, the ranker expects %d" % (F, self.F))
+        if n_rows >= (1 << 24):
+            raise _capi.UltraB200Error("doc ids travel as float32 in the feed format: at most 2^24 rows per data set")
+        key = feats.resident_key()
+        if getattr(self, "_resident_key", None) != key:
+            dev = torch.empty((n_rows + 1) * F, dtype=torch.float32, device=self.device)
+            chunk_rows = max(1, (32 << 20) // (4 * F))
+            pin = torch.empty(chunk_rows * F, dtype=torch.float32, pin_memory=True)
+            src = feats.ctypes.data
+            for r0 in range(0, n_rows, chunk_rows):
+                r1 = min(n_rows, r0 + chunk_rows)
+                n = (r1 - r0) * F
+                check(lib.ub200_convert_f64_f32_host(src + 8 * r0 * F, pin.data_ptr(), n, self._pack_threads),
+                      "ub200_convert_f64_f32_host")
+                dev[r0 * F:r1 * F].copy_(pin[:n], non_blocking=True)
+                torch.cuda.current_stream().synchronize()           # the pinned chunk is reused
+            dev[n_rows * F:].zero_()                                 # PAD row (base_algorithm.py:148-149)
+            self._resident = dev.view(n_rows + 1, F)
+            self._resident_key = key
+            self._resident_host = feats                              # keeps the address alive while it is the key
+        L = len(docid_arrays)
+        B = len(docid_arrays[0])
+        nbytes = 8 * L * B
+        if self._pin is None or self._pin.numel() < nbytes:
+            cap = int(nbytes * 1.5) + 1024
+            self._pin = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+            self._dev = torch.empty(cap, dtype=torch.uint8, device=self.device)
+            self._pin_np = self._pin.numpy()
+        PtrArr = ctypes.c_void_p * L
+        d = [np.ascontiguousarray(x, dtype=np.float32) for x in docid_arrays]
+        y = [np.ascontiguousarray(x, dtype=np.float32) for x in label_arrays]
+        check(lib.ub200_pack_ids_host(PtrArr(*[x.ctypes.data for x in d]), PtrArr(*[x.ctypes.data for x in y]), L, B,
+                                      self._pin.data_ptr(), self._pin.numel()), "ub200_pack_ids_host")
+        self._dev[:nbytes].copy_(self._pin[:nbytes], non_blocking=True)
+        st = Staged()
+        st.docid = self._dev[:4 * L * B].view(torch.int32).view(L, B)
+        st.labels = self._dev[4 * L * B:nbytes].view(torch.float32).view(B, L)
+        st.feats = self._resident
+        st.B, st.L, st.n_docs, st.h2d_bytes = B, L, n_rows, nbytes
+        return st
 
     def staged_views(self, dev, L, B, n_docs):
         off_l = 4 * L * B

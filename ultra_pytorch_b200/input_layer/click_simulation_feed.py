@@ -16,6 +16,7 @@ import random
 import numpy as np
 
 from ..hparams import HParams
+from .resident import ResidentFeatures
 
 ORIGINAL_EXAM_PROB = [0.68, 0.61, 0.48, 0.34, 0.28, 0.20, 0.11, 0.10, 0.08, 0.06]   # click_models.py:76-77
 
@@ -57,6 +58,7 @@ class ClickSimulationFeed(object):
             oracle_mode=False,
             dynamic_bias_eta_change=0.0,
             dynamic_bias_step_interval=1000,
+            resident_features=False,       # B200 extension: emit global doc ids + the whole matrix (resident.py)
         )
         print('Create simluated clicks feed')
         print(hparam_str)
@@ -103,17 +105,38 @@ class ClickSimulationFeed(object):
         p = self.click_model.click_probability(labels)
         return (self.rng.random(labels.shape) < p).astype(np.float64)
 
+    def _simulate_queries(self, idx):
+        """_simulate(self._labels[idx]) with the click probabilities of the whole data set cached per (data set, eta):
+        P(click) depends only on (query, position), so a batch is one row gather + one uniform draw."""
+        if self.hparams.oracle_mode:
+            return self._labels[idx].copy()
+        key = (id(self._labels), float(self.click_model.eta), self.click_model.exam_prob.tobytes())
+        if getattr(self, "_pclick_key", None) != key:
+            self._pclick = self.click_model.click_probability(self._labels)
+            self._pclick_key = key
+        p = self._pclick[idx]
+        return (self.rng.random(p.shape) < p).astype(np.float64)
+
     def _assemble(self, idx, clicks):
         """idx [b] query indices, clicks [b, L] -> (input_feed, info_map) in the reference's format."""
         init, _, features = self._init, self._labels, self._features
         L = self.rank_list_size
         rows = init[idx]                                                   # [b, L]
         real = rows >= 0
-        n_real = real.sum(axis=1)
-        base = np.concatenate([[0], np.cumsum(n_real)[:-1]])
-        n_docs = int(n_real.sum())
-        letor_features = features[rows[real]]                              # real docs, list by list, in order
-        docid = np.where(real, base[:, None] + np.arange(L)[None, :], n_docs)   # base + x ; PAD id = n_docs
+        if getattr(self.hparams, "resident_features", False):
+            # global row ids into the data set's whole (device-resident) feature matrix; PAD id = number of rows
+            if getattr(self, "_resident_src", None) is not features:
+                self._resident_src = features
+                self._resident_view = ResidentFeatures(features)
+            letor_features = self._resident_view
+            n_docs = features.shape[0]
+            docid = np.where(real, rows, n_docs)
+        else:
+            n_real = real.sum(axis=1)
+            base = np.concatenate([[0], np.cumsum(n_real)[:-1]])
+            n_docs = int(n_real.sum())
+            letor_features = features[rows[real]]                          # real docs, list by list, in order
+            docid = np.where(real, base[:, None] + np.arange(L)[None, :], n_docs)   # base + x ; PAD id = n_docs
         input_feed = {self.model.letor_features_name: letor_features}
         docid_f = np.ascontiguousarray(docid.T.astype(np.float32))         # [L, b]
         label_f = np.ascontiguousarray(clicks.T.astype(np.float32))
@@ -140,7 +163,7 @@ class ClickSimulationFeed(object):
         while have < B:
             n_try = max(8, int((B - have) * 1.5) + 4)
             cand = (self.rng.random(n_try) * length).astype(np.int64)
-            clicks = self._simulate(labels[cand])
+            clicks = self._simulate_queries(cand)
             keep = clicks.sum(axis=1) > 0 if check_validation else np.ones(n_try, dtype=bool)
             cand, clicks = cand[keep][:B - have], clicks[keep][:B - have]
             sel_idx.append(cand)
@@ -170,7 +193,7 @@ class ClickSimulationFeed(object):
         self._check_list_size(data_set)
         _, labels, _ = self._arrays(data_set)
         idx = np.asarray(indices, dtype=np.int64)
-        clicks = self._simulate(labels[idx])
+        clicks = self._simulate_queries(idx)
         if check_validation:
             keep = clicks.sum(axis=1) > 0
             idx, clicks = idx[keep], clicks[keep]

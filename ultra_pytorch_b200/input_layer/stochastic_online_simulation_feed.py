@@ -30,6 +30,7 @@ class StochasticOnlineSimulationFeed(ClickSimulationFeed):
             dynamic_bias_eta_change=0.0,
             dynamic_bias_step_interval=1000,
             tau=1.0,
+            resident_features=False,       # B200 extension, see input_layer/resident.py
         )
         print('Create online stochastic simluation feed')
         print(hparam_str)

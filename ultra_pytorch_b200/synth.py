@@ -10,6 +10,8 @@ import numpy as np
 EXAM_PROB = np.array([0.68, 0.61, 0.48, 0.34, 0.28, 0.20, 0.11, 0.10, 0.08, 0.06])
 CLICK_PROB = np.array([0.1, 0.16, 0.28, 0.52, 1.0])
 IPW_JSON = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "ipw_pbm_analytic.json")
+# the PBM click model of the reference's examples (example/ClickModel/pbm_0.1_1.0_4_1.0.json: same numbers)
+PBM_JSON = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "pbm_0.1_1.0_4_1.0.json")
 
 WORKLOADS = {
     # BASELINE.json configs[1..4] (B = the reference's default --batch_size, main.py:42)
@@ -76,3 +78,21 @@ def train_flops_per_query(F, L, hidden):
     ns = list(hidden) + [1]
     macs = sum(k * n for k, n in zip(ks, ns))
     return L * (6 * macs - 2 * F * ns[0])
+
+
+class SyntheticDataset(object):
+    """In-memory stand-in for ultra.utils.data_utils.Raw_data after pad() (data_utils.py:476-498): `features` (one row
+    per document + the trailing zero row pad() appends), `initial_list[q]` (row ids, -1 = PAD), `labels[q]`."""
+
+    def __init__(self, n_queries, L, F, seed=0, max_label=4):
+        rs = np.random.RandomState(seed)
+        self.feature_size, self.rank_list_size = F, L
+        feats = rs.uniform(-1.0, 1.0, size=(n_queries * L + 1, F)).astype(np.float32).astype(np.float64)
+        feats[-1] = 0.0
+        self.features = feats                                   # an ndarray works wherever the list of lists does
+        self.initial_list = np.arange(n_queries * L, dtype=np.int64).reshape(n_queries, L).tolist()
+        self.labels = rs.randint(0, max_label + 1, size=(n_queries, L)).astype(float).tolist()
+
+
+def synthetic_dataset(n_queries, L, F, seed=0):
+    return SyntheticDataset(n_queries, L, F, seed)
