@@ -313,7 +313,8 @@ def main_b200(args):
 
     # ---- pipeline leg (informational): what main.py's loop does per step - feed.get_batch() + model.train() - with
     # the drop-in ClickSimulationFeed on a synthetic data set, (a) in the reference's feed format (feature rows copied
-    # per batch) and (b) with the data set resident in HBM (input_layer/resident.py: only ids + labels move) ----
+    # per batch), (b) with the data set resident in HBM (input_layer/resident.py: only ids + labels move) and (c) with
+    # query sampling + click simulation + batch assembly on the device as well (csrc/sampling.cu) ----
     pipeline = None
     if w["labels"] == "click" and not args.no_pipeline:
         import random as _random
@@ -323,7 +324,7 @@ def main_b200(args):
         pipeline = {"what": "ClickSimulationFeed.get_batch + train() per step, synthetic data set of 2048 queries",
                     "unit": "queries/s"}
         n_pipe = max(20, min(args.steps, 200))
-        for name, hp in (("host_rows", ""), ("resident", "resident_features=True")):
+        for name, hp in (("host_rows", ""), ("resident", "resident_features=True"), ("device", "device_batches=True")):
             feeder = ClickSimulationFeed(model, B, "click_model_json=%s,%s" % (synth.PBM_JSON, hp))
             for _ in range(6):
                 model.train(feeder.get_batch(ds, check_validation=True)[0])

@@ -172,6 +172,18 @@ UB200_API int ub200_clip_update(float* params, float* grads, float* state_sum, s
 UB200_API int ub200_pl_sample(const float* scores, const int32_t* docid, int n_docs, int B, int L, float tau,
                     unsigned long long seed, unsigned long long offset, int32_t* perm, void* stream);
 
+/* ---- N1: click simulation + batch assembly on the device ----------------------------------------------------------
+ * Replaces ClickSimulationFeed.get_batch (click_simulation_feed.py:101-174) + PositionBiasedModel.sampleClicksForOneList
+ * (click_models.py:80-110) for a data set resident in HBM.  init_list [nq, L] i32 (row ids, < 0 = PAD), rel [nq, L] f32
+ * (true labels, 0 at PADs).  Per batch slot b: query ~ U{0..nq-1}; click_l ~ Bernoulli(exam_prob[min(l, n_exam-1)] *
+ * click_prob[min(label, n_cp-1)]) (oracle_mode: click = label); with check_validation the draw repeats (at most
+ * max_rounds times) until the list has a click.  Writes docid [L, B] i32 (PAD -> pad_id), labels [B, L] f32 and
+ * query_idx [B] (may be NULL).  Philox4x32-10 keyed by (seed, offset, slot, round, position). */
+UB200_API int ub200_click_batch(const int32_t* init_list, const float* rel, int nq, int L, const float* exam_prob,
+                      int n_exam, const float* click_prob, int n_cp, int oracle_mode, int check_validation,
+                      int max_rounds, int B, int pad_id, unsigned long long seed, unsigned long long offset,
+                      int32_t* docid, float* labels, int32_t* query_idx, void* stream);
+
 /* ---- C1: data-parallel exchange of the flat gradient buffer over NVLink peer memory ----------------------------------
  * Nothing in the reference corresponds to this (it is single-process); it is the ONE collective of a data-parallel
  * step: the in-place SUM over ranks of [DNN grads | loss normalisers | EM / DenoisingNet partials].

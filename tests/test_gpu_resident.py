@@ -45,3 +45,68 @@ def test_resident_dataset_trains_bit_identically(algo, tmp_path):
     assert la_ == lb
     assert torch.equal(pa, pb) and torch.equal(sa, sb) and ma == mb
     assert hb == 8 * L * B and ha > 20 * hb          # ids + labels only vs ids + labels + feature rows
+
+
+def _feed_arrays(tmp_path, nq, L, F, B, hp=""):
+    import ultra_pytorch_b200.learning_algorithm as la
+    from ultra_pytorch_b200.input_layer import ClickSimulationFeed
+    la.B200Algorithm.VERBOSE = False
+    ds = FakeData(nq, L, F)
+    p = os.path.join(str(tmp_path), "pbm.json")
+    with open(p, "w") as f:
+        json.dump(PBM, f)
+    settings = {"learning_algorithm_hparams": "", "ranking_model": "ultra_pytorch_b200.ranking_model.DNN",
+                "ranking_model_hparams": "hidden_layer_sizes=[32, 16]", "selection_bias_cutoff": L,
+                "max_candidate_num": L, "metrics": ["ndcg"], "metrics_topn": [1, 3]}
+    torch.manual_seed(0)
+    random.seed(0)
+    model = la.NavieAlgorithm(types.SimpleNamespace(feature_size=F), settings)
+    feed = ClickSimulationFeed(model, B, "click_model_json=%s,device_batches=True,%s" % (p, hp))
+    return ds, model, feed, settings
+
+
+@pytest.mark.parametrize("check_validation", [False, True])
+def test_device_click_batches_have_the_reference_distribution(check_validation, tmp_path):
+    """csrc/sampling.cu click_batch_kernel: queries uniform (conditioned on >= 1 click under check_validation), clicks
+    ~ Bernoulli(exam_prob[l] * click_prob[label]) (PAD positions count as label 0, as in the reference), doc ids and
+    PADs copied from the initial list."""
+    nq, L, F, B = 24, 8, 12, 262144
+    ds, model, feed, _ = _feed_arrays(tmp_path, nq, L, F, B)
+    f, info = feed.get_batch(ds, check_validation=check_validation)
+    init, rel, feats = feed._arrays(ds)
+    q = np.asarray(info["rank_list_idxs"])
+    docid = np.stack([f["docid_input%d" % l] for l in range(L)], axis=1).astype(np.int64)     # materialises
+    clicks = np.stack([f["label%d" % l] for l in range(L)], axis=1)
+    n_rows = feats.shape[0]
+    assert f["letor_features"].shape == (n_rows, F) and docid.shape == (B, L)
+    assert np.array_equal(docid, np.where(init[q] >= 0, init[q], n_rows))
+    exam = np.asarray(PBM["exam_prob"])[np.minimum(np.arange(L), 9)]
+    p = exam[None, :] * np.asarray(PBM["click_prob"])[rel.astype(int)]                         # [nq, L]
+    p_any = 1.0 - np.prod(1.0 - p, axis=1)
+    want_q = p_any / p_any.sum() if check_validation else np.full(nq, 1.0 / nq)
+    got_q = np.bincount(q, minlength=nq) / float(B)
+    assert np.all(np.abs(got_q - want_q) <= 5 * np.sqrt(want_q * (1 - want_q) / B) + 1e-6)
+    if check_validation:
+        assert np.all(clicks.sum(axis=1) > 0)
+    else:
+        for qi in range(nq):
+            sel = q == qi
+            got = clicks[sel].mean(axis=0)
+            assert np.all(np.abs(got - p[qi]) <= 5 * np.sqrt(p[qi] * (1 - p[qi]) / sel.sum()) + 1e-6), qi
+
+
+def test_training_from_device_batches_equals_training_from_their_host_copy(tmp_path):
+    import ultra_pytorch_b200.learning_algorithm as la
+    nq, L, F, B = 120, 10, 136, 64
+    ds, model_a, feed, settings = _feed_arrays(tmp_path, nq, L, F, B)
+    torch.manual_seed(0)
+    model_b = la.NavieAlgorithm(types.SimpleNamespace(feature_size=F), settings)
+    assert torch.equal(model_a.engine.params, model_b.engine.params)
+    for step in range(6):
+        f, _ = feed.get_batch(ds, check_validation=True)
+        host = {k: f[k] for k in f.keys()}                      # plain dict, numpy arrays (+ the resident view)
+        la_, _, _ = model_a.train(f)
+        assert model_a.last_h2d_bytes == 0
+        lb, _, _ = model_b.train(host)
+        assert la_ == lb
+    assert torch.equal(model_a.engine.params, model_b.engine.params)

@@ -85,9 +85,95 @@ __global__ void __launch_bounds__(256) pl_sample_kernel(const float* __restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// N1 - click simulation + batch assembly on the device (position-biased click model).
+//
+// Replaces ClickSimulationFeed.get_batch (ultra/input_layer/click_simulation_feed.py:101-174) and
+// PositionBiasedModel.sampleClicksForOneList (ultra/utils/click_models.py:80-110) for a data set whose initial
+// lists, relevance labels and features are resident in HBM: one warp per batch slot draws a query uniformly,
+// simulates a click on every position with P = exam_prob[min(l, last)] * click_prob[label] (PAD positions count as
+// label 0, as in the reference), and - with check_validation - repeats until the list has at least one click: the
+// accepted (query, clicks) pairs have exactly the distribution of the reference's "skip lists without clicks until the
+// batch is full" loop.  Output goes straight into the step's staging buffers (doc ids position-major, labels
+// list-major); nothing touches the host.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) click_batch_kernel(const int32_t* __restrict__ init_list,
+                                                           const float* __restrict__ rel, int nq, int L,
+                                                           const float* __restrict__ exam_prob, int n_exam,
+                                                           const float* __restrict__ click_prob, int n_cp,
+                                                           int oracle_mode, int check_validation, int max_rounds, int B,
+                                                           int pad_id, unsigned long long seed,
+                                                           unsigned long long offset, int32_t* __restrict__ docid,
+                                                           float* __restrict__ labels, int32_t* __restrict__ query_idx) {
+    griddep_launch();
+    griddep_wait();
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint32_t off_lo = (uint32_t)offset, off_hi = (uint32_t)(offset >> 32);
+    int q = 0;
+    for (int round = 0; round < max_rounds; ++round) {
+        // one query per (slot, round): counter word 0 = 0xFFFFFFFF is never a position
+        const uint4 rq = philox4x32_10(make_uint4(0xFFFFFFFFu, (uint32_t)b, off_lo, (off_hi << 12) ^ (uint32_t)round), key);
+        q = (int)(((unsigned long long)rq.x * (unsigned long long)nq) >> 32);
+        int any = 0;
+        if (!oracle_mode) {
+            for (int l = lane; l < L; l += 32) {
+                const float y = rel[(size_t)q * L + l];
+                int yi = y > 0.f ? (int)y : 0;
+                if (yi >= n_cp) yi = n_cp - 1;
+                const float p = exam_prob[l < n_exam ? l : n_exam - 1] * click_prob[yi];
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)l, (uint32_t)b, off_lo, (off_hi << 12) ^ (uint32_t)round), key);
+                any |= (u01_open(r.x) < p) ? 1 : 0;
+            }
+        } else {
+            for (int l = lane; l < L; l += 32) any |= rel[(size_t)q * L + l] > 0.f ? 1 : 0;
+        }
+        any = __any_sync(0xffffffffu, any);
+        if (!check_validation || any || round == max_rounds - 1) {
+            // accepted: regenerate the same draws (same counters) and write the list
+            for (int l = lane; l < L; l += 32) {
+                const int id = init_list[(size_t)q * L + l];
+                const float y = rel[(size_t)q * L + l];
+                float c;
+                if (oracle_mode) {
+                    c = y;
+                } else {
+                    int yi = y > 0.f ? (int)y : 0;
+                    if (yi >= n_cp) yi = n_cp - 1;
+                    const float p = exam_prob[l < n_exam ? l : n_exam - 1] * click_prob[yi];
+                    const uint4 r = philox4x32_10(make_uint4((uint32_t)l, (uint32_t)b, off_lo, (off_hi << 12) ^ (uint32_t)round), key);
+                    c = (u01_open(r.x) < p) ? 1.f : 0.f;
+                }
+                docid[(size_t)l * B + b] = id >= 0 ? id : pad_id;
+                labels[(size_t)b * L + l] = c;
+            }
+            break;
+        }
+    }
+    if (lane == 0 && query_idx) query_idx[b] = q;
+}
+
 }  // namespace ub200
 
 using namespace ub200;
+
+extern "C" UB200_API int ub200_click_batch(const int32_t* init_list, const float* rel, int nq, int L,
+                                           const float* exam_prob, int n_exam, const float* click_prob, int n_cp,
+                                           int oracle_mode, int check_validation, int max_rounds, int B, int pad_id,
+                                           unsigned long long seed, unsigned long long offset, int32_t* docid,
+                                           float* labels, int32_t* query_idx, void* stream) {
+    UB_CHECK(init_list && rel && docid && labels && nq > 0 && L > 0 && B > 0, 2, "click_batch: bad arguments");
+    UB_CHECK(oracle_mode || (exam_prob && click_prob && n_exam > 0 && n_cp > 0), 2, "click_batch: click model missing");
+    UB_CHECK(max_rounds >= 1 && max_rounds < (1 << 12), 1, "click_batch: max_rounds must be in [1, 4096)");
+    const int grid = (B + 7) / 8;
+    launch_k(click_batch_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), init_list, rel, nq, L, exam_prob,
+             n_exam, click_prob, n_cp, oracle_mode, check_validation, max_rounds, B, pad_id, seed, offset, docid, labels,
+             query_idx);
+    UB_LAUNCH_CHECK("click_batch_kernel");
+    return 0;
+}
 
 extern "C" UB200_API int ub200_pl_sample(const float* scores, const int32_t* docid, int n_docs, int B, int L, float tau,
                                          unsigned long long seed, unsigned long long offset, int32_t* perm,

@@ -247,6 +247,49 @@ class RankerEngine(object):
         """The feed's `letor_features` is the data set's whole feature matrix (input_layer/resident.py) and the doc ids
         are global row ids: keep the matrix in HBM (uploaded once, fp32, zero PAD row appended) and move only ids and
         labels per step."""
+        n_rows = feats.shape[0]
+        self.ensure_resident(feats)
+        L = len(docid_arrays)
+        B = len(docid_arrays[0])
+        nbytes = 8 * L * B
+        if self._pin is None or self._pin.numel() < nbytes:
+            cap = int(nbytes * 1.5) + 1024
+            self._pin = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+            self._dev = torch.empty(cap, dtype=torch.uint8, device=self.device)
+            self._pin_np = self._pin.numpy()
+        PtrArr = ctypes.c_void_p * L
+        d = [np.ascontiguousarray(x, dtype=np.float32) for x in docid_arrays]
+        y = [np.ascontiguousarray(x, dtype=np.float32) for x in label_arrays]
+        check(lib.ub200_pack_ids_host(PtrArr(*[x.ctypes.data for x in d]), PtrArr(*[x.ctypes.data for x in y]), L, B,
+                                      self._pin.data_ptr(), self._pin.numel()), "ub200_pack_ids_host")
+        self._dev[:nbytes].copy_(self._pin[:nbytes], non_blocking=True)
+        st = Staged()
+        st.docid = self._dev[:4 * L * B].view(torch.int32).view(L, B)
+        st.labels = self._dev[4 * L * B:nbytes].view(torch.float32).view(B, L)
+        st.feats = self._resident
+        st.B, st.L, st.n_docs, st.h2d_bytes = B, L, n_rows, nbytes
+        return st
+
+    def stage_device_feed(self, feed):
+        """A batch assembled on the device (input_layer/resident.py: DeviceFeed): nothing to pack, nothing to copy."""
+        self.ensure_resident(dict.__getitem__(feed, feed.model.letor_features_name))
+        st = Staged()
+        st.docid, st.labels, st.feats = feed.docid, feed.labels, self._resident
+        st.B, st.L, st.n_docs, st.h2d_bytes = feed.B, feed.L, feed.n_rows, 0
+        return st
+
+    def click_batch(self, init_list, rel, exam_prob, click_prob, oracle_mode, check_validation, max_rounds, pad_id, seed,
+                    offset, docid, labels, query_idx):
+        nq, L = init_list.shape
+        B = docid.shape[1]
+        check(lib.ub200_click_batch(_ptr(init_list), _ptr(rel), nq, L, _ptr(exam_prob),
+                                    0 if exam_prob is None else exam_prob.numel(), _ptr(click_prob),
+                                    0 if click_prob is None else click_prob.numel(), int(oracle_mode),
+                                    int(check_validation), int(max_rounds), B, int(pad_id), int(seed), int(offset),
+                                    _ptr(docid), _ptr(labels), _ptr(query_idx), _stream()), "ub200_click_batch")
+
+    def ensure_resident(self, feats):
+        """Uploads the data set's whole feature matrix (fp32 + zero PAD row) unless it is the one already resident."""
         n_rows, F = feats.shape
         if F != self.F:
             raise _capi.UltraB200Error("resident feature matrix has %d columns, the ranker expects %d" % (F, self.F))
@@ -269,26 +312,6 @@ class RankerEngine(object):
             self._resident = dev.view(n_rows + 1, F)
             self._resident_key = key
             self._resident_host = feats                              # keeps the address alive while it is the key
-        L = len(docid_arrays)
-        B = len(docid_arrays[0])
-        nbytes = 8 * L * B
-        if self._pin is None or self._pin.numel() < nbytes:
-            cap = int(nbytes * 1.5) + 1024
-            self._pin = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
-            self._dev = torch.empty(cap, dtype=torch.uint8, device=self.device)
-            self._pin_np = self._pin.numpy()
-        PtrArr = ctypes.c_void_p * L
-        d = [np.ascontiguousarray(x, dtype=np.float32) for x in docid_arrays]
-        y = [np.ascontiguousarray(x, dtype=np.float32) for x in label_arrays]
-        check(lib.ub200_pack_ids_host(PtrArr(*[x.ctypes.data for x in d]), PtrArr(*[x.ctypes.data for x in y]), L, B,
-                                      self._pin.data_ptr(), self._pin.numel()), "ub200_pack_ids_host")
-        self._dev[:nbytes].copy_(self._pin[:nbytes], non_blocking=True)
-        st = Staged()
-        st.docid = self._dev[:4 * L * B].view(torch.int32).view(L, B)
-        st.labels = self._dev[4 * L * B:nbytes].view(torch.float32).view(B, L)
-        st.feats = self._resident
-        st.B, st.L, st.n_docs, st.h2d_bytes = B, L, n_rows, nbytes
-        return st
 
     def staged_views(self, dev, L, B, n_docs):
         off_l = 4 * L * B

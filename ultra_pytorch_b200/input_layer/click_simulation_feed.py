@@ -16,7 +16,7 @@ import random
 import numpy as np
 
 from ..hparams import HParams
-from .resident import ResidentFeatures
+from .resident import DeviceFeed, ResidentFeatures
 
 ORIGINAL_EXAM_PROB = [0.68, 0.61, 0.48, 0.34, 0.28, 0.20, 0.11, 0.10, 0.08, 0.06]   # click_models.py:76-77
 
@@ -45,6 +45,29 @@ class _PositionBiasedModel(object):
         return exam[None, :] * self.click_prob[rel]
 
 
+class _LazyInfo(dict):
+    """info_map of a device batch (click_simulation_feed.py:158-163): values are fetched from the device on first use."""
+
+    def __init__(self, feed):
+        dict.__init__(self)
+        self._feed = feed
+
+    def __missing__(self, key):
+        f = self._feed
+        if key == 'rank_list_idxs':
+            v = f.query_idx.cpu().numpy().tolist()
+        elif key == 'input_list':
+            v = f.docid.cpu().numpy().T.astype(np.int64)
+        elif key == 'click_list':
+            v = f.labels.cpu().numpy().astype(np.float64)
+        elif key == 'letor_features':
+            v = dict.__getitem__(f, f.model.letor_features_name)
+        else:
+            raise KeyError(key)
+        self[key] = v
+        return v
+
+
 class ClickSimulationFeed(object):
     MAX_SAMPLE_ROUND_NUM = 100
 
@@ -59,6 +82,7 @@ class ClickSimulationFeed(object):
             dynamic_bias_eta_change=0.0,
             dynamic_bias_step_interval=1000,
             resident_features=False,       # B200 extension: emit global doc ids + the whole matrix (resident.py)
+            device_batches=False,          # B200 extension: sample queries + clicks on the GPU (implies resident)
         )
         print('Create simluated clicks feed')
         print(hparam_str)
@@ -151,10 +175,60 @@ class ClickSimulationFeed(object):
                              " %d != %d." % (len(data_set.initial_list[0]), self.rank_list_size))
 
     # ---- reference API ----------------------------------------------------------------------------------------
+    # ---- N1 on the device: query sampling + click simulation + batch assembly in one kernel ------------------------
+    def _device_batch(self, data_set, check_validation):
+        import torch
+        eng = getattr(self.model, "engine", None)
+        if eng is None:
+            raise TypeError("device_batches=True needs a B200 learning algorithm (the batch is assembled in its "
+                            "device buffers)")
+        init, labels, features = self._arrays(data_set)
+        if getattr(self, "_resident_src", None) is not features:
+            self._resident_src = features
+            self._resident_view = ResidentFeatures(features)
+        eng.ensure_resident(self._resident_view)
+        dev = eng.device
+        key = (id(init), id(labels))
+        if getattr(self, "_dev_key", None) != key:
+            self._dev_init = torch.from_numpy(init.astype(np.int32)).to(dev)
+            self._dev_rel = torch.from_numpy(labels.astype(np.float32)).to(dev)
+            L, B = self.rank_list_size, self.batch_size
+            # a small ring of output buffers: a feed handed out earlier stays valid for a few more batches, and the
+            # CUDA graphs of the training step (keyed on the buffer addresses) are reused
+            self._dev_ring = [(torch.empty(L, B, dtype=torch.int32, device=dev),
+                               torch.empty(B, L, dtype=torch.float32, device=dev),
+                               torch.empty(B, dtype=torch.int32, device=dev)) for _ in range(4)]
+            self._dev_key = key
+            self._dev_cm_key = None
+            self._dev_seed = random.getrandbits(63)
+            self._dev_calls = 0
+        oracle = bool(self.hparams.oracle_mode)
+        if not oracle:
+            cm_key = (float(self.click_model.eta), self.click_model.exam_prob.tobytes())
+            if self._dev_cm_key != cm_key:
+                self._dev_exam = torch.from_numpy(self.click_model.exam_prob.astype(np.float32)).to(dev)
+                self._dev_cp = torch.from_numpy(self.click_model.click_prob.astype(np.float32)).to(dev)
+                self._dev_cm_key = cm_key
+        self._dev_calls += 1
+        docid, lab, qidx = self._dev_ring[self._dev_calls % len(self._dev_ring)]
+        eng.click_batch(self._dev_init, self._dev_rel, None if oracle else self._dev_exam,
+                        None if oracle else self._dev_cp, oracle, bool(check_validation), 1000, features.shape[0],
+                        self._dev_seed, self._dev_calls, docid, lab, qidx)
+        return DeviceFeed(self.model, self._resident_view, docid, lab, qidx, features.shape[0])
+
     def get_batch(self, data_set, check_validation=False, data_format="ULTRA"):
         """Random batch for training (click_simulation_feed.py:101-174): draws queries uniformly with replacement and,
         with check_validation, keeps only lists with at least one click until batch_size lists are collected."""
         self._check_list_size(data_set)
+        if getattr(self.hparams, "device_batches", False):
+            feed = self._device_batch(data_set, check_validation)
+            self.global_batch_count += 1
+            if self.hparams.dynamic_bias_eta_change != 0 and not self.hparams.oracle_mode:
+                if self.global_batch_count % self.hparams.dynamic_bias_step_interval == 0:
+                    self.click_model.eta += self.hparams.dynamic_bias_eta_change
+                    self.click_model.setExamProb(self.click_model.eta)
+                    print('Dynamically change bias severity eta to %.3f' % self.click_model.eta)
+            return feed, _LazyInfo(feed)
         init, labels, _ = self._arrays(data_set)
         length = init.shape[0]
         B = self.batch_size

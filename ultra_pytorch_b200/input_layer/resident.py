@@ -24,3 +24,52 @@ class ResidentFeatures(np.ndarray):
     def resident_key(self):
         """Identity of the underlying matrix (address + shape): the engine re-uploads when it changes."""
         return (self.ctypes.data, self.shape)
+
+
+class DeviceFeed(dict):
+    """An `input_feed` whose doc ids and labels were produced ON THE DEVICE (csrc/sampling.cu: click_batch_kernel).
+
+    A B200 learning algorithm consumes `.docid` (i32 [L, B]) / `.labels` (f32 [B, L]) in place - no host work, no
+    H2D copy.  For everybody else it still behaves like the reference's dict: the first access to a
+    `docid_input{l}` / `label{l}` key copies the batch to the host once and materialises the numpy arrays
+    (`letor_features` is the ResidentFeatures view, available without any copy)."""
+
+    def __init__(self, model, features, docid, labels, query_idx, n_rows):
+        dict.__init__(self)
+        self.model = model
+        self.docid, self.labels, self.query_idx = docid, labels, query_idx     # device tensors
+        self.L, self.B = docid.shape
+        self.n_rows = n_rows
+        dict.__setitem__(self, model.letor_features_name, features)
+        self._names = set(model.docid_inputs_name[:self.L]) | set(model.labels_name[:self.L])
+        self._materialised = False
+
+    def materialise(self):
+        if not self._materialised:
+            d = self.docid.cpu().numpy().astype(np.float32)           # [L, B]
+            y = np.ascontiguousarray(self.labels.cpu().numpy().T)     # [L, B]
+            for l in range(self.L):
+                dict.__setitem__(self, self.model.docid_inputs_name[l], d[l])
+                dict.__setitem__(self, self.model.labels_name[l], y[l])
+            self._materialised = True
+        return self
+
+    def __getitem__(self, key):
+        if not self._materialised and key in self._names:
+            self.materialise()
+        return dict.__getitem__(self, key)
+
+    def __contains__(self, key):
+        return key in self._names or dict.__contains__(self, key)
+
+    def keys(self):
+        return self.materialise() and dict.keys(self)
+
+    def items(self):
+        return self.materialise() and dict.items(self)
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __len__(self):
+        return 1 + len(self._names)

@@ -168,6 +168,13 @@ class B200Algorithm(_reference_base()):
 
     # ---- input staging --------------------------------------------------------------------------------
     def _stage(self, input_feed, list_size):
+        from ..input_layer.resident import DeviceFeed
+        if isinstance(input_feed, DeviceFeed) and input_feed.L == list_size:
+            # the batch was assembled on the device (N1): nothing to pack or copy
+            self.letor_features = dict.__getitem__(input_feed, self.letor_features_name)
+            st = self.engine.stage_device_feed(input_feed)
+            self.last_h2d_bytes = 0
+            return st
         docids = [input_feed[self.docid_inputs_name[i]] for i in range(list_size)]
         labels = [input_feed[self.labels_name[i]] for i in range(list_size)]
         self.letor_features = input_feed[self.letor_features_name]
