@@ -143,6 +143,13 @@ UB200_API int ub200_pairdebias(const float* scores, const float* clicks, int B, 
 /* t <- (1-em_step)*t + em_step * (T_i / T_0)^(1/(reg_p+1)) for t+ (T = out[0..L)) and t- (T = out[L..2L));
  * safe_div != 0 uses the reference's _safe_div (LambdaRank, lambda_rank.py:136-140), 0 a plain division
  * (PairDebias, pairwise_debias.py:159-163). */
+/* PRSrank (prs_rank.py:94-151, N4): the same pair kernel on predicted ranks; pair (r ranked above s) weighted by
+ * delta-NDCG * ipw_r / ipw_s with ipw = ipw_table[min(display position, table_len - 1)]; loss = weighted binary
+ * cross-entropy of sigmoid(sigma (s_r - s_s)) against (1 + clamp(y_r - y_s)) / 2 (torch's -100 log clamp).  out as for
+ * ub200_lambdarank: [2L] = un-normalised loss, [2L+1] = batch IDCG partial (T+/T- slots are zero). */
+UB200_API int ub200_prsrank(const float* scores, const float* labels, int B, int L, float sigma, const float* ipw_table,
+                  int table_len, float* dscores_unnorm, float* out, void* workspace, size_t workspace_bytes,
+                  void* stream);
 UB200_API int ub200_em_update(float* t_plus, float* t_minus, const float* out, int L, float em_step, float reg_p,
                     int safe_div, void* stream);
 

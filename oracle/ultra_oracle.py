@@ -266,6 +266,49 @@ def lambdarank(scores, labels, t_plus, t_minus, sigma=1.0, em_step=0.05, reg_p=1
                 idcg=dt(idcg))
 
 
+def prsrank(scores, labels, ipw_table, sigma=1.0, dt=np.float32):
+    """PRSrank (prs_rank.py:94-151).  ipw_l = IPW_list[min(l, len-1)] for EVERY display position
+    (getPropensityForOneList(use_non_clicked_data=True), propensity_estimator.py:22-42), pw = _safe_div(1, ipw).
+    Sorted by predicted score: prs_rs = ipw_r * pw_s for r < s (triu, diagonal=1); p_rs = 1 / (exp(-sigma (s_r - s_s)) + 1);
+    loss = sum_{b, r<s} delta_NDCG_rs * prs_rs * BCE(p_rs, (1 + clamp(y_r - y_s)) / 2) with torch's BCE (both logs clamped
+    at -100); delta-NDCG with ONE batch-global natural-log IDCG (prs_rank.py:214-218, 228-231).  Gradient through
+    binary_cross_entropy's backward ((p - t) / max(p (1 - p), 1e-12)) and the sigmoid."""
+    s = scores.astype(dt)
+    y = labels.astype(dt)
+    B, L = s.shape
+    tab = np.asarray(ipw_table, dtype=dt)
+    ipw_pos = tab[np.minimum(np.arange(L), len(tab) - 1)]
+    order = np.argsort(-s, axis=1, kind="stable")
+    ps = np.take_along_axis(s, order, axis=1)
+    ys = np.take_along_axis(y, order, axis=1)
+    ipw = ipw_pos[order]                                        # ipw of the display position of the doc at rank r
+    pw = safe_div(np.ones_like(ipw), ipw)
+    tri = np.triu(np.ones((L, L), dtype=dt), k=1)
+    prs = (ipw[:, :, None] * pw[:, None, :] * tri[None]).astype(dt)
+    S = np.clip(ys[:, :, None] - ys[:, None, :], -1.0, 1.0).astype(dt)
+    T = (dt(0.5) * (dt(1.0) + S)).astype(dt)
+    sij = (ps[:, :, None] - ps[:, None, :]).astype(dt)
+    with np.errstate(over="ignore"):
+        p = (dt(1.0) / (np.exp(-dt(sigma) * sij) + dt(1.0))).astype(dt)
+    ideal = -np.sort(-y, axis=1)
+    pos = np.arange(1, L + 1, dtype=dt)
+    idcg = ((np.power(dt(2.0), ideal) - dt(1.0)) / np.log(pos + dt(1.0))[None, :]).sum(dtype=dt)   # ONE scalar
+    gains = ((np.power(dt(2.0), ys) - dt(1.0)) / idcg).astype(dt)
+    disc = (dt(1.0) / np.log2(np.arange(L, dtype=dt) + dt(2.0))).astype(dt)
+    delta = (np.abs(gains[:, :, None] - gains[:, None, :]) * np.abs(disc[None, :, None] - disc[None, None, :])).astype(dt)
+    w = (delta * prs).astype(dt)
+    with np.errstate(divide="ignore"):
+        lp = np.maximum(np.log(p), dt(-100.0))
+        l1p = np.maximum(np.log(dt(1.0) - p), dt(-100.0))
+    loss = (-w * (T * lp + (dt(1.0) - T) * l1p)).sum(dtype=dt)
+    pq = (p * (dt(1.0) - p)).astype(dt)
+    A = (w * dt(sigma) * (p - T) * (pq / np.maximum(pq, dt(1e-12)))).astype(dt)            # d loss / d (ps_r - ps_s)
+    dps = (A.sum(axis=2, dtype=dt) - A.sum(axis=1, dtype=dt)).astype(dt)
+    dscores = np.zeros_like(s)
+    np.put_along_axis(dscores, order, dps, axis=1)
+    return dict(loss=dt(loss), dscores=dscores, idcg=dt(idcg))
+
+
 # ----------------------------------------------------------------------------------------------
 # A7: clip_grad_norm_ + Adagrad / SGD  (base_algorithm.py:208-226, dla.py:141-166)
 # ----------------------------------------------------------------------------------------------
@@ -310,7 +353,7 @@ class OracleTrainer:
         self.state_sum = {n: np.zeros_like(self.params[n]) for n in self.names}
         self.F = feature_size
         self.L = L_train
-        defaults = {"na": 0.05, "ipw": 0.05, "dla": 0.05, "pairdebias": 0.005, "lambdarank": 0.05}
+        defaults = {"na": 0.05, "ipw": 0.05, "dla": 0.05, "pairdebias": 0.005, "lambdarank": 0.05, "prsrank": 0.05}
         self.lr = defaults[algo] if learning_rate is None else learning_rate
         self.max_norm = max_gradient_norm
         self.sigma, self.em_step, self.reg_p = sigma, em_step, reg_p
@@ -352,6 +395,9 @@ class OracleTrainer:
             r = lambdarank(s, y, self.t_plus, self.t_minus, self.sigma, self.em_step, self.reg_p, dt)
             loss, ds = r["loss"], r["dscores"]
             self.t_plus, self.t_minus = r["t_plus"], r["t_minus"]
+        elif self.algo == "prsrank":
+            r = prsrank(s, y, self.ipw_table, self.sigma, dt)
+            loss, ds = r["loss"], r["dscores"]
         else:
             raise ValueError(self.algo)
         grads = dnn_backward(scores_grad_to_rows(ds), cache, self.params, self.n_layers, dt)

@@ -32,6 +32,7 @@ ALGOS = {
     "dla": "ultra.learning_algorithm.DLA",
     "pairdebias": "ultra.learning_algorithm.PairDebias",
     "lambdarank": "ultra.learning_algorithm.LambdaRank",
+    "prsrank": "ultra.learning_algorithm.PRSrank",
 }
 
 # name, algo, F, L_train (selection_bias_cutoff), L_max (max_candidate_num), B, hidden, label kind, n_steps
@@ -48,6 +49,8 @@ CASES = [
     # hidden == [] selects the reference's Linear ranker (ultra/ranking_model/Linear.py: LayerNorm -> Linear(F, 1))
     ("ipw_linear", "ipw", 10, 6, 8, 8, [], "click", 3),
     ("lambdarank_linear", "lambdarank", 14, 7, 7, 6, [], "graded", 2),
+    ("prsrank_small", "prsrank", 10, 6, 8, 8, [16, 8], "graded", 3),
+    ("prsrank_click", "prsrank", 10, 7, 7, 6, [16, 8], "click", 2),
 ]
 
 
@@ -127,7 +130,7 @@ def run_case(ultra, name, algo, F, L_train, L_max, B, hidden, kind, n_steps):
     out.update(state_to_np(model.model.state_dict(), "init/"))
     if algo == "dla":
         out.update(state_to_np(model.propensity_model.state_dict(), "init_prop/"))
-    if algo == "ipw":
+    if algo in ("ipw", "prsrank"):
         out["ipw_table"] = np.asarray(model.propensity_estimator.IPW_list, dtype=np.float64)
 
     # validation on the initial parameters (forward only, L = max_candidate_num)

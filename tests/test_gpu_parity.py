@@ -19,7 +19,7 @@ from tests.helpers import assert_close, golden_names, grad_floor, load_golden, s
 pytestmark = pytest.mark.gpu
 
 ALGO_CLASS = {"na": "NavieAlgorithm", "ipw": "IPWrank", "dla": "DLA", "pairdebias": "PairDebias",
-              "lambdarank": "LambdaRank"}
+              "lambdarank": "LambdaRank", "prsrank": "PRSrank"}
 
 
 def _dev(x, dtype=torch.float32):
@@ -40,7 +40,7 @@ def build_from_golden(g, tmp_path):
     b200_metrics.MAX_LABEL = 4.0
     algo = str(g["meta_algo"])
     hp = ""
-    if algo == "ipw":
+    if algo in ("ipw", "prsrank"):
         p = os.path.join(str(tmp_path), "ipw.json")
         with open(p, "w") as f:
             json.dump({"IPW_list": [float(v) for v in g["ipw_table"]]}, f)
@@ -272,6 +272,31 @@ def test_pairwise_vs_oracle(B, L, kind):
     if np.isfinite(r["t_plus"]).all() and np.isfinite(r["t_minus"]).all():
         assert_close(tpd.cpu().numpy(), r["t_plus"], 1e-5, "t_plus after EM")
         assert_close(tmd.cpu().numpy(), r["t_minus"], 1e-5, "t_minus after EM")
+
+
+@pytest.mark.parametrize("B,L", [(3, 2), (8, 7), (64, 40), (32, 200), (4, 300)])
+def test_prsrank_vs_oracle(B, L):
+    from ultra_pytorch_b200.engine import RankerEngine
+    rs = np.random.RandomState(B * 5 + L)
+    eng = RankerEngine(4, [])
+    s = rs.randn(B, L).astype(np.float32)
+    y = rs.randint(0, 5, size=(B, L)).astype(np.float32)
+    table = (1.0 + 0.35 * np.arange(40)).astype(np.float32)       # lists longer than the table reuse its last entry
+    r = uo.prsrank(s, y, table, 1.0, np.float64)
+    dsc = torch.empty(B, L, device="cuda")
+    out = torch.zeros(2 * L + 2, device="cuda")
+    eng.prsrank(_dev(s), _dev(y), 1.0, _dev(table), dsc, out)
+    o = out.cpu().numpy()
+    idcg = o[2 * L + 1]
+    assert abs(idcg - r["idcg"]) <= 1e-5 * r["idcg"]
+    assert abs(o[2 * L] / idcg - r["loss"]) <= 1e-5 * abs(r["loss"]) + 1e-12
+    assert np.all(o[:2 * L] == 0)
+    assert_close(dsc.cpu().numpy() / idcg, r["dscores"], 1e-5, "dscores")
+    # deterministic
+    dsc2 = torch.empty(B, L, device="cuda")
+    out2 = torch.zeros(2 * L + 2, device="cuda")
+    eng.prsrank(_dev(s), _dev(y), 1.0, _dev(table), dsc2, out2)
+    assert torch.equal(dsc, dsc2) and torch.equal(out, out2)
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])

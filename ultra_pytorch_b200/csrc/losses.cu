@@ -364,8 +364,11 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return s;
 }
 
-// LAMBDA = true : LambdaRank (lambda_rank.py:116-135, 247-291) - positions are predicted ranks
-// LAMBDA = false: PairDebias (pairwise_debias.py:142-157)       - positions are display positions
+// KIND 0: PairDebias (pairwise_debias.py:142-157)       - positions are display positions
+// KIND 1: LambdaRank (lambda_rank.py:116-135, 247-291) - positions are predicted ranks (LAMBDA below)
+// KIND 2: PRSrank    (prs_rank.py:94-151)              - predicted ranks; pair (r < s) weighted by delta-NDCG * ipw_r / ipw_s
+//         (ipw = IPW table entry of the document's DISPLAY position; t_plus carries the table, t_minus is unused), loss =
+//         weighted binary cross-entropy of p_rs = sigmoid(sigma (s_r - s_s)) against P_rs = (1 + clamp(y_r - y_s)) / 2
 //
 // Every UNORDERED pair {i, j} is evaluated exactly once (the reference's [L, L] matrices hold each pair twice, as
 // (i, j) and (j, i), and both directions share every transcendental): thread i visits the partners j = (i + k) mod L
@@ -380,14 +383,16 @@ struct PairAcc {
     float Tp, Tm, g, ls;
 };
 
-template <bool LAMBDA>
+template <int KIND>
 __global__ void __launch_bounds__(512) pairwise_kernel(const float* __restrict__ scores,
                                                         const float* __restrict__ labels, int B, int L, float sigma,
                                                         const float* __restrict__ t_plus,
                                                         const float* __restrict__ t_minus,
                                                         float* __restrict__ dscores, float* __restrict__ out,
                                                         unsigned int* counter, float* __restrict__ partials,
-                                                        int n_groups) {
+                                                        int n_groups, int table_len) {
+    constexpr bool LAMBDA = KIND != 0;      // ranked by predicted score
+    constexpr bool PRS = KIND == 2;
     extern __shared__ float sm[];
     float* ps = sm;              // scores in position order (sorted for LAMBDA)
     float* ys = ps + L;          // labels in position order
@@ -416,11 +421,13 @@ __global__ void __launch_bounds__(512) pairwise_kernel(const float* __restrict__
     float* pTm = pTp + L;
 
     for (int i = threadIdx.x; i < L; i += blockDim.x) {
-        const float a = t_plus[i], b = t_minus[i];
-        tp[i] = a;
-        tm[i] = b;
-        rtp[i] = 1.f / a;
-        rtm[i] = 1.f / b;
+        if (!PRS) {
+            const float a = t_plus[i], b = t_minus[i];
+            tp[i] = a;
+            tm[i] = b;
+            rtp[i] = 1.f / a;
+            rtm[i] = 1.f / b;
+        }
         accp[i] = 0.f;
         accm[i] = 0.f;
         if (LAMBDA) dc[i] = 1.f / log2f((float)i + 2.f);
@@ -477,6 +484,13 @@ __global__ void __launch_bounds__(512) pairwise_kernel(const float* __restrict__
                 ys[r] = yi;
                 const float gain = exp2f(yi) - 1.f;
                 gn[r] = gain;
+                if (PRS) {
+                    // ipw of the document's display position i (getPropensityForOneList(use_non_clicked_data=True),
+                    // propensity_estimator.py:22-42) and pw = _safe_div(1, ipw) (prs_rank.py:126)
+                    const float w = t_plus[min(i, table_len - 1)];
+                    tp[r] = w;
+                    rtp[r] = w == 0.f ? 0.f : 1.f / w;
+                }
                 idcg_acc += gain / logf((float)ipos[i] + 2.f);
             }
         } else {
@@ -499,7 +513,27 @@ __global__ void __launch_bounds__(512) pairwise_kernel(const float* __restrict__
                 if (j >= L) j -= L;
                 // for even L the antipodal pair (k == L/2) would be met from both ends
                 const bool act = have && !(2 * k == L && i >= half);
-                if (LAMBDA) {
+                if (PRS) {
+                    const float delta = fabsf(gi - gn[j]) * fabsf(di - dc[j]);
+                    if (act && delta != 0.f) {
+                        // the pair counts once, as (a, b) with a ranked above b (triu(..., diagonal=1), prs_rank.py:131)
+                        const bool own_first = ii < j;
+                        const float sa = own_first ? si : ps[j], sb = own_first ? ps[j] : si;
+                        const float ya = own_first ? yi : ys[j], yb = own_first ? ys[j] : yi;
+                        const float w = delta * (own_first ? tpi * rtp[j] : tp[j] * rtpi);     // delta-NDCG * ipw_a * pw_b
+                        const float d = sigma * (sa - sb);
+                        const float p = 1.f / (expf(-d) + 1.f);                               // prs_rank.py:139
+                        const float t = 0.5f * (1.f + fminf(fmaxf(ya - yb, -1.f), 1.f));
+                        // F.binary_cross_entropy clamps both logarithms at -100 and divides by max(p (1 - p), 1e-12)
+                        // in its backward pass
+                        const float lp = fmaxf(logf(p), -100.f), l1p = fmaxf(logf(1.f - p), -100.f);
+                        ls -= w * (t * lp + (1.f - t) * l1p);
+                        const float pq = p * (1.f - p);
+                        const float ga = w * sigma * (p - t) * (pq / fmaxf(pq, 1e-12f));
+                        g += own_first ? ga : -ga;
+                        pg[j] += own_first ? -ga : ga;
+                    }
+                } else if (LAMBDA) {
                     const float delta = fabsf(gi - gn[j]) * fabsf(di - dc[j]);
                     if (act && delta != 0.f) {
                         const float d = sigma * (si - ps[j]);
@@ -714,12 +748,14 @@ extern "C" UB200_API int ub200_dla_loss(const float* scores, const float* clicks
     return 0;
 }
 
-template <bool LAMBDA>
+template <int KIND>
 static int launch_pairwise(const float* scores, const float* labels, int B, int L, float sigma, const float* t_plus,
                            const float* t_minus, float* dscores, float* out, void* workspace, size_t workspace_bytes,
-                           void* stream) {
+                           void* stream, int table_len = 0) {
     UB_CHECK(B > 0 && L > 0, 1, "pairwise: bad B=%d L=%d", B, L);
-    UB_CHECK(scores && labels && t_plus && t_minus && dscores && out && workspace, 2, "pairwise: null pointer");
+    UB_CHECK(scores && labels && t_plus && (t_minus || KIND == 2) && dscores && out && workspace, 2,
+             "pairwise: null pointer");
+    UB_CHECK(KIND != 2 || table_len > 0, 1, "prsrank: empty IPW table");
     UB_CHECK(workspace_bytes >= loss_ws_bytes(2 * L + 2), 3, "pairwise: workspace too small");
     LossWs w = loss_ws(workspace);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -739,10 +775,10 @@ static int launch_pairwise(const float* scores, const float* labels, int B, int 
     const size_t smem = sizeof(float) * (17 + 3 * (size_t)(threads / 32)) * (size_t)L;
     UB_CHECK(smem <= 200 * 1024, 4, "pairwise: list length %d too large", L);
     if (smem > 48 * 1024)
-        cudaFuncSetAttribute(pairwise_kernel<LAMBDA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(pairwise_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int grid = loss_grid(B, 1);
-    launch_k(pairwise_kernel<LAMBDA>, grid, threads, smem, st, scores, labels, B, L, sigma, t_plus, t_minus, dscores, out,
-             w.counter, w.partials, groups);
+    launch_k(pairwise_kernel<KIND>, grid, threads, smem, st, scores, labels, B, L, sigma, t_plus, t_minus, dscores, out,
+             w.counter, w.partials, groups, table_len);
     UB_LAUNCH_CHECK("pairwise_kernel");
     return 0;
 }
@@ -750,15 +786,22 @@ static int launch_pairwise(const float* scores, const float* labels, int B, int 
 extern "C" UB200_API int ub200_lambdarank(const float* scores, const float* labels, int B, int L, float sigma,
                                 const float* t_plus, const float* t_minus, float* dscores, float* out,
                                 void* workspace, size_t workspace_bytes, void* stream) {
-    return launch_pairwise<true>(scores, labels, B, L, sigma, t_plus, t_minus, dscores, out, workspace,
-                                 workspace_bytes, stream);
+    return launch_pairwise<1>(scores, labels, B, L, sigma, t_plus, t_minus, dscores, out, workspace,
+                              workspace_bytes, stream);
 }
 
 extern "C" UB200_API int ub200_pairdebias(const float* scores, const float* clicks, int B, int L, const float* t_plus,
                                 const float* t_minus, float* dscores, float* out, void* workspace,
                                 size_t workspace_bytes, void* stream) {
-    return launch_pairwise<false>(scores, clicks, B, L, 1.f, t_plus, t_minus, dscores, out, workspace,
-                                  workspace_bytes, stream);
+    return launch_pairwise<0>(scores, clicks, B, L, 1.f, t_plus, t_minus, dscores, out, workspace,
+                              workspace_bytes, stream);
+}
+
+extern "C" UB200_API int ub200_prsrank(const float* scores, const float* labels, int B, int L, float sigma,
+                             const float* ipw_table, int table_len, float* dscores, float* out, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+    return launch_pairwise<2>(scores, labels, B, L, sigma, ipw_table, nullptr, dscores, out, workspace,
+                              workspace_bytes, stream, table_len);
 }
 
 extern "C" UB200_API int ub200_em_update(float* t_plus, float* t_minus, const float* out, int L, float em_step, float reg_p,

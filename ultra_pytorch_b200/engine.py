@@ -362,6 +362,12 @@ class RankerEngine(object):
         check(lib.ub200_lambdarank(_ptr(scores), _ptr(labels), B, L, float(sigma), _ptr(t_plus), _ptr(t_minus),
                                    _ptr(dscores), _ptr(out), _ptr(ws), ws.numel(), _stream()), "ub200_lambdarank")
 
+    def prsrank(self, scores, labels, sigma, ipw_table, dscores, out):
+        B, L = scores.shape
+        ws = self.loss_ws(B, L)
+        check(lib.ub200_prsrank(_ptr(scores), _ptr(labels), B, L, float(sigma), _ptr(ipw_table), ipw_table.numel(),
+                                _ptr(dscores), _ptr(out), _ptr(ws), ws.numel(), _stream()), "ub200_prsrank")
+
     def pairdebias(self, scores, clicks, t_plus, t_minus, dscores, out):
         B, L = scores.shape
         ws = self.loss_ws(B, L)
