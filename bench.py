@@ -366,9 +366,34 @@ def main_b200(args):
         dist.destroy_process_group()
 
 
+class _JsonOnlyStdout(object):
+    """stdout carries exactly ONE line, the JSON result; everything the plugin classes print while they are being
+    constructed (they mirror the reference's prints) goes to stderr."""
+
+    def __init__(self):
+        self.real = sys.stdout
+        self.last = sys.stderr
+
+    def write(self, text):
+        if text.strip():
+            t = text.lstrip()
+            self.last = self.real if (t.startswith('{"metric"') or t.startswith('{"impl"')) else sys.stderr
+        self.last.write(text)
+        return len(text)
+
+    def flush(self):
+        self.real.flush()
+        sys.stderr.flush()
+
+
 if __name__ == "__main__":
     a = parse_args()
-    if a.impl == "reference":
-        main_reference(a)
-    else:
-        main_b200(a)
+    sys.stdout = _JsonOnlyStdout()
+    try:
+        if a.impl == "reference":
+            main_reference(a)
+        else:
+            main_b200(a)
+    finally:
+        sys.stdout.flush()
+        sys.stdout = sys.stdout.real
