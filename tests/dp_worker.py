@@ -38,7 +38,10 @@ def main():
     la.B200Algorithm.VERBOSE = False
     F, L, B, hidden = 136, 40, 64, [256, 128, 64]
     ok = True
-    for algo, wl in (("IPWrank", "c2_ipw_mslr10k"), ("LambdaRank", "c4_lambdarank_mslr30k")):
+    # DLA's update is lr * sign(g) (fresh Adagrad every step, dla.py:153-154): a gradient entry near zero may change
+    # sign between the sharded and the merged evaluation, so for DLA only the replica equality is asserted
+    for algo, wl, vs_single in (("IPWrank", "c2_ipw_mslr10k", True), ("LambdaRank", "c4_lambdarank_mslr30k", True),
+                                ("DLA", "c3_dla_yahoo", False)):
         settings = synth.exp_settings(wl)
         settings.update({"ranking_model_hparams": "hidden_layer_sizes=%s" % hidden, "selection_bias_cutoff": L,
                          "max_candidate_num": L})
@@ -55,7 +58,7 @@ def main():
         same = all(torch.equal(gathered[0], g) for g in gathered)
         # single-GPU reference on the merged batches (rank 0 only; same seeds)
         err = 0.0
-        if rank == 0:
+        if rank == 0 and vs_single:
             torch.manual_seed(0)
             # world_size() == 1 makes the reference model a plain single-GPU one (no symmetric-memory rendezvous, which
             # is collective, and no exchange in its steps)

@@ -152,3 +152,29 @@ def test_resident_feed_is_a_valid_reference_format_feed_with_global_ids(tmp_path
     # a second batch re-uses the same view object (the engine keys its device copy on it)
     fc, _ = res.get_next_batch(0, ds)
     assert fc["letor_features"] is fb["letor_features"]
+
+
+def test_device_feed_behaves_like_the_reference_dict_on_the_host():
+    """input_layer/resident.py DeviceFeed: consumers that are not B200 algorithms see a plain reference-format dict (the
+    first access to an id / label key copies the device batch to the host once).  CPU tensors stand in for the device."""
+    import torch
+    from ultra_pytorch_b200.input_layer.click_simulation_feed import _LazyInfo
+    from ultra_pytorch_b200.input_layer.resident import DeviceFeed, ResidentFeatures
+    L, B, F = 3, 4, 5
+    m = _model(L, F)
+    feats = ResidentFeatures(np.arange(50.0).reshape(10, F))
+    docid = torch.tensor([[0, 1, 2, 3], [4, 5, 10, 7], [8, 10, 10, 9]], dtype=torch.int32)       # [L, B], PAD id = 10
+    labels = torch.tensor([[1, 0, 0], [0, 1, 0], [1, 1, 0], [0, 0, 1]], dtype=torch.float32)     # [B, L]
+    qidx = torch.tensor([3, 1, 2, 0], dtype=torch.int32)
+    f = DeviceFeed(m, feats, docid, labels, qidx, 10)
+    assert not f._materialised and f["letor_features"] is feats and not f._materialised        # no copy needed
+    assert "docid_input1" in f and "label2" in f and len(f) == 1 + 2 * L
+    assert f["docid_input1"].dtype == np.float32 and f["docid_input1"].tolist() == [4.0, 5.0, 10.0, 7.0]
+    assert f._materialised and f["label0"].tolist() == [1.0, 0.0, 1.0, 0.0]
+    assert sorted(f.keys()) == sorted(["letor_features"] + m.docid_inputs_name + m.labels_name)
+    plain = dict(f.items())
+    assert set(plain) == set(f.keys()) and plain["label2"].tolist() == [0.0, 0.0, 0.0, 1.0]
+    info = _LazyInfo(f)
+    assert info["rank_list_idxs"] == [3, 1, 2, 0]
+    assert info["input_list"].tolist() == docid.numpy().T.tolist() and info["click_list"].shape == (B, L)
+    assert info["letor_features"] is feats
