@@ -164,6 +164,13 @@ UB200_API int ub200_em_update(float* t_plus, float* t_minus, const float* out, i
  * grads is overwritten with the clipped gradient (what p.grad holds after the reference's opt_step);
  * norm_out[0] receives the pre-clip norm.
  */
+/* Early read-back of a step's scalars (the reference's loss.item(), e.g. ipw_rank.py:181-182): copies n <= 32 floats
+ * from src (device) to host_dst and then stores the launch count (dev_counter, device, zero-initialised) into
+ * host_seq; host_dst / host_seq are MAPPED PINNED host memory (UVA: the host pointer is valid on the device).  The
+ * host polls host_seq instead of synchronising the stream, so train() returns while the backward pass and the optimizer
+ * step of the batch are still running; everything later on the stream stays ordered behind them. */
+UB200_API int ub200_publish(const float* src, int n, float* host_dst, unsigned int* host_seq, unsigned int* dev_counter,
+                  void* stream);
 UB200_API size_t ub200_opt_workspace_bytes(size_t n);
 UB200_API int ub200_clip_update(float* params, float* grads, float* state_sum, size_t n, const float* den, float scale_const,
                       float max_norm, float lr, int mode, float* norm_out,

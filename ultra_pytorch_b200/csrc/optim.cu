@@ -172,6 +172,24 @@ __global__ void __launch_bounds__(256) clip_update_fused_kernel(float* __restric
     }
 }
 
+// Early read-back of a step's scalars: copies n floats into MAPPED PINNED host memory and then bumps a sequence number
+// there, so that train() can return the loss as soon as the loss kernel has run while the backward pass and the
+// optimizer step of the same batch are still executing (the host spins on the sequence number instead of
+// synchronising the stream).  dev_counter counts the launches (CUDA-graph replays included).
+__global__ void publish_kernel(const float* __restrict__ src, int n, float* host_dst, unsigned int* host_seq,
+                               unsigned int* dev_counter) {
+    griddep_launch();
+    griddep_wait();
+    if (threadIdx.x < n) host_dst[threadIdx.x] = src[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int c = dev_counter[0] + 1u;
+        dev_counter[0] = c;
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned int*>(host_seq) = c;
+    }
+}
+
 static int env_flag(const char* name, int dflt) {
     const char* v = getenv(name);
     return v ? (v[0] != '0') : dflt;
@@ -196,6 +214,14 @@ using namespace ub200;
 extern "C" UB200_API const char* ub200_last_error(void) { return g_err; }
 extern "C" UB200_API int ub200_abi_version(void) { return 1; }
 extern "C" UB200_API unsigned long long ub200_launch_count(void) { return g_launches.load(); }
+
+extern "C" UB200_API int ub200_publish(const float* src, int n, float* host_dst, unsigned int* host_seq,
+                                       unsigned int* dev_counter, void* stream) {
+    UB_CHECK(src && host_dst && host_seq && dev_counter && n > 0 && n <= 32, 2, "publish: bad arguments");
+    launch_k(publish_kernel, 1, 32, 0, static_cast<cudaStream_t>(stream), src, n, host_dst, host_seq, dev_counter);
+    UB_LAUNCH_CHECK("publish_kernel");
+    return 0;
+}
 
 extern "C" UB200_API size_t ub200_opt_workspace_bytes(size_t n) {
     (void)n;

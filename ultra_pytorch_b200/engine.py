@@ -387,6 +387,50 @@ class RankerEngine(object):
                                   _ptr(perm), _stream()), "ub200_pl_sample")
         return perm
 
+    # ---- early read-back of the loss scalars -----------------------------------------------------------------
+    def publish(self, scalars):
+        """Enqueues the copy of `scalars` (<= 32 floats, device) into mapped pinned host memory + a sequence number
+        (csrc/optim.cu: publish_kernel) on a side stream forked from the current one; returns nothing - read with
+        `read_published()` after the step has been launched."""
+        if getattr(self, "_pub_host", None) is None:
+            self._pub_host = torch.zeros(64, dtype=torch.float32, pin_memory=True)          # [0, 32) values, [32] seq
+            self._pub_np = self._pub_host.numpy()
+            self._pub_seq_np = self._pub_np[32:33].view(np.uint32)
+            self._pub_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._pub_stream = torch.cuda.Stream(device=self.device)
+            self._pub_launched = 0
+        cur = torch.cuda.current_stream()
+        self._pub_stream.wait_stream(cur)
+        with torch.cuda.stream(self._pub_stream):
+            check(lib.ub200_publish(_ptr(scalars), scalars.numel(), self._pub_host.data_ptr(),
+                                    self._pub_host.data_ptr() + 128, _ptr(self._pub_counter),
+                                    self._pub_stream.cuda_stream), "ub200_publish")
+        self._pub_n = scalars.numel()
+
+    def join_publish(self):
+        """The side stream must re-join before the step ends (CUDA-graph capture needs a single sink)."""
+        if getattr(self, "_pub_host", None) is not None:
+            torch.cuda.current_stream().wait_stream(self._pub_stream)
+
+    def read_published(self, timeout_s=20.0):
+        """Waits (spinning on the host-visible sequence number) for the publish of the step launched last and returns
+        its scalars as a numpy array."""
+        import time
+        want = self._pub_launched & 0xFFFFFFFF          # the step launched last (B200Algorithm.run_step counts them)
+        seq = self._pub_seq_np
+        spins = 0
+        t0 = None
+        while int(seq[0]) != want:
+            spins += 1
+            if (spins & 0xFFF) == 0:
+                if t0 is None:
+                    t0 = time.perf_counter()
+                elif time.perf_counter() - t0 > timeout_s:
+                    torch.cuda.synchronize()          # surfaces a CUDA error if there is one
+                    raise _capi.UltraB200Error("early loss read-back timed out (sequence %d, expected %d)"
+                                               % (int(seq[0]), want))
+        return self._pub_np[:self._pub_n].copy()
+
     # ---- optimizer ------------------------------------------------------------------------------------
     def clip_update(self, params, grads, state_sum, den, scale_const, max_norm, lr, mode, norm_out=None):
         n = params.numel()

@@ -85,6 +85,12 @@ class B200Algorithm(_reference_base()):
 
     def run_step(self, st):
         """device_step(st), replayed from CUDA graphs once the (B, L, buffer) combination has been seen twice."""
+        out = self._run_step(st)
+        if getattr(self, "_early", False):
+            self.engine._pub_launched += 1          # one execution of the publish kernel per launched step
+        return out
+
+    def _run_step(self, st):
         # data parallel over peer memory: the exchange is one of OUR kernels, so the whole step is one graph again
         dp = self.world_size() > 1 and self.engine.peer is None
         if not self.USE_GRAPH or (dp and not self.USE_GRAPH_DP):
@@ -182,8 +188,28 @@ class B200Algorithm(_reference_base()):
         self.last_h2d_bytes = st.h2d_bytes
         return st
 
+    # train() returns the loss as soon as the loss kernel has produced it (single GPU): the scalars are published into
+    # mapped pinned host memory right after the loss kernel, the backward pass and the optimizer step of the batch keep
+    # running while the host already packs the next batch; every later use of the parameters is ordered behind them on
+    # the stream.  UB200_EARLY_LOSS=0 restores the blocking read after the whole step.
+    EARLY_LOSS = os.environ.get("UB200_EARLY_LOSS", "1") != "0"
+
+    def _publish_early(self, scalars):
+        """Called by device_step right after the loss kernel; False when the scalars are only final at the end of the
+        step (data parallel: they are summed by the exchange)."""
+        if not self.EARLY_LOSS or self.world_size() > 1:
+            self._early = False
+            return False
+        self.engine.publish(scalars)
+        self._early = True
+        return True
+
     def _read_scalars(self, t):
-        """The one D2H sync of a step (the reference's loss.item())."""
+        """The one D2H read of a step (the reference's loss.item())."""
+        if getattr(self, "_early", False):
+            host = self.engine.read_published()
+            self.last_d2h_bytes = host.size * 4
+            return host
         host = t.detach().to("cpu", non_blocking=False)
         self.last_d2h_bytes = host.numel() * 4
         return host.numpy()

@@ -42,10 +42,12 @@ class NavieAlgorithm(B200Algorithm):
             scores = eng.forward(st.feats, docid, L, B, training=True)
             dscores = eng.dscores_buf(B, L)
             eng.softmax_ce(scores, st.labels, self.WEIGHT_MODE, self._table, dscores, sums)
+            self._publish_early(sums)
             eng.backward(st.feats, docid, L, B, dscores)
         if self._phase == "pre":
             return None
         self._exchange_and_update(eng.state_sum, sums[1:2], 1.0, self.learning_rate, self._opt_mode(), eng.norm)
+        eng.join_publish()
         return sums
 
     def train(self, input_feed):

@@ -47,6 +47,7 @@ class PairDebias(B200Algorithm):
             scores = eng.forward(st.feats, docid, L, B, training=True)
             dscores = eng.dscores_buf(B, L)
             self._pair_kernel(scores, st.labels, dscores, out)
+            self._publish_early(out[2 * L:2 * L + 2])         # loss (+ idcg) are final here on a single GPU
             eng.backward(st.feats, docid, L, B, dscores)
         if self._phase == "pre":
             return None
@@ -54,6 +55,7 @@ class PairDebias(B200Algorithm):
         self._scal.copy_(out[2 * L:2 * L + 2])          # loss (+ idcg) before anything reuses the buffer
         eng.em_update(self.t_plus, self.t_minus, out, self.hparams.EM_step_size, self.hparams.regulation_p,
                       self.SAFE_DIV)
+        eng.join_publish()
         return self._scal
 
     def _update(self, out, L, B):

@@ -41,6 +41,7 @@ class PRSrank(B200Algorithm):
             scores = eng.forward(st.feats, docid, L, B, training=True)
             dscores = eng.dscores_buf(B, L)
             eng.prsrank(scores, st.labels, self.sigma, self._table, dscores, out)
+            self._publish_early(out[2 * L:2 * L + 2])
             eng.backward(st.feats, docid, L, B, dscores)
         if self._phase == "pre":
             return None
@@ -48,6 +49,7 @@ class PRSrank(B200Algorithm):
         self._exchange_and_update(eng.state_sum, out[2 * L + 1:2 * L + 2], 1.0, self.learning_rate, self._opt_mode(),
                                   eng.norm)
         self._scal.copy_(out[2 * L:2 * L + 2])
+        eng.join_publish()
         return self._scal
 
     def train(self, input_feed):
