@@ -73,7 +73,8 @@ class DLA(B200Algorithm):
         self.propensity_model.linear_layer.bias.grad = self._dprop[L:].view(1)
         self._norms = torch.zeros(2, dtype=torch.float32, device=eng.device)
         self._scal = torch.zeros(6, dtype=torch.float32, device=eng.device)
-        self.norm = None
+        self._norm = None
+        self._norm_pending = False
 
     def device_step(self, st):
         eng = self.engine
@@ -84,6 +85,7 @@ class DLA(B200Algorithm):
             scores = eng.forward(st.feats, docid, L, B, training=True)
             dscores = eng.dscores_buf(B, L)
             eng.dla_loss(scores, st.labels, flat[:L], flat[L:], dscores, self._dprop, self._sums)
+            self._publish_early(self._sums)                 # both losses are final here on a single GPU
             eng.backward(st.feats, docid, L, B, dscores)
         if self._phase == "pre":
             return None
@@ -98,7 +100,22 @@ class DLA(B200Algorithm):
                         self._norms[0:1])
         self._scal[:4].copy_(self._sums)
         self._scal[4:6].copy_(self._norms)
+        eng.join_publish()
         return self._scal
+
+    def _post_clip_norm(self, norms):
+        mg = self.hparams.max_gradient_norm
+        post = [float(n) * min(1.0, mg / (float(n) + 1e-6)) if mg > 0 else float(n) for n in norms]
+        return (post[0] ** 2 + post[1] ** 2) ** 0.5               # dla.py:166-177
+
+    @property
+    def norm(self):
+        """Norm of the clipped gradients of the last step (dla.py:166-177; the reference spends 18 host syncs per step
+        on it and never reads it).  With the early loss read-back it is fetched on first use."""
+        if self._norm_pending:
+            self._norm = self._post_clip_norm(self._norms.cpu().numpy())
+            self._norm_pending = False
+        return self._norm
 
     def train(self, input_feed):
         """dla.py:179-266 + separate_gradient_update dla.py:141-177."""
@@ -107,12 +124,14 @@ class DLA(B200Algorithm):
             self.model.train()
         st = self._stage(input_feed, self.rank_list_size)
         s = self._read_scalars(self.run_step(st))
-        mg = self.hparams.max_gradient_norm
         self.rank_loss = float(s[0] / s[1])
         self.exam_loss = float(s[2] / s[3])
         self.loss = self.exam_loss + self.hparams.ranker_loss_weight * self.rank_loss
-        post = [float(n) * min(1.0, mg / (float(n) + 1e-6)) if mg > 0 else float(n) for n in s[4:6]]
-        self.norm = (post[0] ** 2 + post[1] ** 2) ** 0.5          # dla.py:166-177
+        if len(s) >= 6:
+            self._norm = self._post_clip_norm(s[4:6])
+            self._norm_pending = False
+        else:                       # early read-back: the gradient norms arrive with the end of the step -> lazily
+            self._norm_pending = True
         self._say(self.loss)
         self.global_step += 1
         return self.loss, None, self.train_summary
