@@ -178,3 +178,46 @@ def test_device_feed_behaves_like_the_reference_dict_on_the_host():
     assert info["rank_list_idxs"] == [3, 1, 2, 0]
     assert info["input_list"].tolist() == docid.numpy().T.tolist() and info["click_list"].shape == (B, L)
     assert info["letor_features"] is feats
+
+
+@pytest.mark.parametrize("use_max", [True, False])
+def test_direct_label_feed_is_bit_identical_to_the_reference(use_max):
+    """input_layer/direct_label_feed.py vs ultra.input_layer.DirectLabelFeed: get_batch (same random.seed),
+    get_next_batch and get_data_by_index, with and without check_validation."""
+    if not ref_shim.available():
+        pytest.skip("oracle/_ref not installed")
+    ultra = ref_shim.load()
+    from ultra_pytorch_b200.input_layer import DirectLabelFeed
+    L_train, L_max, F, B = 5, 9, 6, 8
+    ds = FakeData(30, L_max, F, seed=4)
+    ds.labels[3] = [0.0] * len(ds.labels[3])            # a list without any relevant document
+    m = _model(L_max, F)
+    m.rank_list_size, m.max_candidate_num = L_train, L_max
+    hp = "use_max_candidate_num=%s" % use_max
+    ours, ref = DirectLabelFeed(m, B, hp), ultra.input_layer.DirectLabelFeed(m, B, hp)
+    assert ours.rank_list_size == ref.rank_list_size
+
+    def same(a, b):
+        assert sorted(a.keys()) == sorted(b.keys())
+        for k in a:
+            assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape and np.array_equal(a[k], b[k]), k
+
+    for cv in (False, True):
+        for seed in (0, 1, 2):
+            random.seed(seed)
+            a, ia = ours.get_batch(ds, check_validation=cv)
+            random.seed(seed)
+            b, ib = ref.get_batch(ds, check_validation=cv)
+            same(a, b)
+            assert ia["rank_list_idxs"] == ib["rank_list_idxs"]
+        for index in (0, 3, 24):
+            same(ours.get_next_batch(index, ds, check_validation=cv)[0], ref.get_next_batch(index, ds, check_validation=cv)[0])
+    # the reference's get_data_by_index raises (it calls a method that does not exist, direct_label_feed.py:247); ours is
+    # the one-list case of get_next_batch
+    with pytest.raises(AttributeError):
+        ref.get_data_by_index(ds, 5)
+    one, _ = ours.get_data_by_index(ds, 5)
+    ours_b1 = DirectLabelFeed(m, 1, hp)
+    same(one, ours_b1.get_next_batch(5, ds)[0])
+    with pytest.raises(NotImplementedError):
+        ours.get_batch(ds, data_format="ULTRE")

@@ -27,6 +27,9 @@ SETTINGS = {
                            "ultra.input_layer.StochasticOnlineSimulationFeed"),
     "dla_online_b200feed": ("ultra_pytorch_b200.learning_algorithm.DLA",
                             "ultra_pytorch_b200.input_layer.StochasticOnlineSimulationFeed"),
+    # every feed replaced by its drop-in, data sets resident in HBM (train: batches assembled on the device)
+    "ipw_all_b200feeds": ("ultra_pytorch_b200.learning_algorithm.IPWrank",
+                          "ultra_pytorch_b200.input_layer.ClickSimulationFeed"),
     # the Linear ranker
     "ipw_linear": ("ultra_pytorch_b200.learning_algorithm.IPWrank", "ultra.input_layer.ClickSimulationFeed"),
 }
@@ -45,10 +48,12 @@ def test_unmodified_main_py_drives_the_plugin(algo, tmp_path):
     if not ref_shim.available():
         pytest.skip("oracle/_ref not installed (python oracle/install_ref.py needs /root/reference)")
     cls, feed = SETTINGS[algo]
+    all_ours = algo == "ipw_all_b200feeds"
+    eval_feed = "ultra_pytorch_b200.input_layer.DirectLabelFeed" if all_ours else "ultra.input_layer.DirectLabelFeed"
     settings = {
-        "train_input_feed": feed, "train_input_hparams": "",
-        "valid_input_feed": "ultra.input_layer.DirectLabelFeed", "valid_input_hparams": "",
-        "test_input_feed": "ultra.input_layer.DirectLabelFeed", "test_input_hparams": "",
+        "train_input_feed": feed, "train_input_hparams": "device_batches=True" if all_ours else "",
+        "valid_input_feed": eval_feed, "valid_input_hparams": "resident_features=True" if all_ours else "",
+        "test_input_feed": eval_feed, "test_input_hparams": "resident_features=True" if all_ours else "",
         "ranking_model": "ultra_pytorch_b200.ranking_model.%s" % ("Linear" if algo.endswith("_linear") else "DNN"),
         "ranking_model_hparams": "" if algo.endswith("_linear") else "hidden_layer_sizes=[64, 32]",
         "learning_algorithm": cls, "learning_algorithm_hparams": "",
