@@ -2,8 +2,6 @@
 (reference: ultra/learning_algorithm/lambda_rank.py:22-291): pairwise-debiased LambdaRank with delta-NDCG weights.
 The ~12 materialised [B, L, L] temporaries of the reference are never formed: one CTA per list evaluates the pair
 tile from shared memory."""
-import torch
-
 from .base_algorithm import HParams
 from .pairwise_debias import PairDebias
 

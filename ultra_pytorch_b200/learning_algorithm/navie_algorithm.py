@@ -1,7 +1,5 @@
 """B200-native drop-in for `ultra.learning_algorithm.NavieAlgorithm`
 (reference: ultra/learning_algorithm/navie_algorithm.py:24-149): listwise softmax loss on the raw labels."""
-import torch
-
 from .base_algorithm import B200Algorithm, HParams
 
 
