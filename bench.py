@@ -367,11 +367,15 @@ def main_b200(args):
 
 
 class _JsonOnlyStdout(object):
-    """stdout carries exactly ONE line, the JSON result; everything the plugin classes print while they are being
-    constructed (they mirror the reference's prints) goes to stderr."""
+    """stdout carries exactly ONE line, the JSON result.  Everything the plugin classes print while they are being
+    constructed (they mirror the reference's prints) goes to stderr, and so does whatever C libraries write to file
+    descriptor 1 directly (NCCL prints its version there): fd 1 is pointed at stderr for the whole run and the JSON
+    line is written to a duplicate of the original stdout."""
 
     def __init__(self):
-        self.real = sys.stdout
+        sys.stdout.flush()
+        self.real = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         self.last = sys.stderr
 
     def write(self, text):
@@ -396,4 +400,3 @@ if __name__ == "__main__":
             main_b200(a)
     finally:
         sys.stdout.flush()
-        sys.stdout = sys.stdout.real
