@@ -144,3 +144,28 @@ def test_host_packer_pool_is_exact_for_any_size_and_thread_count():
     assert np.array_equal(hf[:n], feats.astype(np.float32)) and not hf[n].any()
     assert np.array_equal(out[:4 * L * B].view(np.int32).reshape(L, B), np.stack(d).astype(np.int32))
     assert np.array_equal(out[4 * L * B:8 * L * B].view(np.float32).reshape(B, L), np.stack(y).T)
+
+
+def test_column_ptrs_address_the_same_data_as_the_individual_arrays():
+    """engine.column_ptrs: the stacked-block pointer array packs exactly like one pointer per feed array, for the
+    homogeneous fast path and for the ragged / mixed-dtype fallback."""
+    import ctypes
+    from ultra_pytorch_b200 import _capi
+    from ultra_pytorch_b200.engine import column_ptrs
+    lib = _capi.lib
+    rs = np.random.RandomState(1)
+    L, B = 9, 37
+    d = [rs.randint(0, 500, B).astype(np.float32) for _ in range(L)]
+    y = [rs.rand(B).astype(np.float32) for _ in range(L)]
+    ref = np.zeros(8 * L * B, np.uint8)
+    P = ctypes.c_void_p * L
+    assert lib.ub200_pack_ids_host(P(*[x.ctypes.data for x in d]), P(*[x.ctypes.data for x in y]), L, B,
+                                   ref.ctypes.data, ref.size) == 0
+    for dd, yy in ((d, y), ([x.astype(np.float64) for x in d], [list(map(float, x)) for x in y])):
+        out = np.full(8 * L * B, 7, np.uint8)
+        dp, kd = column_ptrs(dd, B)
+        lp, kl = column_ptrs(yy, B)
+        assert lib.ub200_pack_ids_host(dp, lp, L, B, out.ctypes.data, out.size) == 0
+        assert np.array_equal(out, ref)
+    with pytest.raises(Exception):
+        column_ptrs([d[0], d[1][:5]], B)          # ragged arrays are not a valid feed

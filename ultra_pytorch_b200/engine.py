@@ -24,6 +24,25 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def column_ptrs(arrays, B):
+    """ctypes array of the data pointers of L per-position feed arrays (f32 [B] each) + an object to keep alive.
+
+    Asking 80 numpy arrays for `.ctypes.data` costs ~2 us each; stacking them into one [L, B] block (a 40 KB copy) and
+    deriving the row addresses arithmetically is ~6x cheaper, which matters on the host path of a 0.36 ms step."""
+    L = len(arrays)
+    try:
+        block = np.array(arrays, dtype=np.float32)
+    except ValueError:
+        block = None
+    if block is None or block.shape != (L, B):
+        keep = [np.ascontiguousarray(x, dtype=np.float32) for x in arrays]
+        if any(x.shape != (B,) for x in keep):
+            raise ValueError("every docid_input / label array of a feed must have shape (%d,)" % B)
+        return (ctypes.c_void_p * L)(*[x.ctypes.data for x in keep]), keep
+    addr = block.ctypes.data + np.arange(L, dtype=np.uint64) * np.uint64(4 * B)
+    return (ctypes.c_void_p * L).from_buffer(addr), (block, addr)
+
+
 class Staged(object):
     """Device views of one staged input_feed."""
     __slots__ = ("feats", "docid", "labels", "B", "L", "n_docs", "h2d_bytes")
@@ -221,9 +240,8 @@ class RankerEngine(object):
             # ONE C call: ids/labels + the f64 -> f32 conversion of the feature rows on the persistent host thread pool,
             # straight into pinned memory, with the H2D copy of every finished group of rows enqueued on the current
             # stream while the rest is still being converted (csrc/hostpack.cpp).
-            PtrArr = ctypes.c_void_p * L
-            dptr = PtrArr(*[x.ctypes.data for x in docid_arrays])
-            lptr = PtrArr(*[x.ctypes.data for x in label_arrays])
+            dptr, keep_d = column_ptrs(docid_arrays, B)
+            lptr, keep_l = column_ptrs(label_arrays, B)
             check(lib.ub200_stage_feed(feats.ctypes.data, n_docs, self.F, dptr, lptr, L, B, self._pin.data_ptr(),
                                        self._pin.numel(), self._dev.data_ptr(), self._pack_threads, self._pack_chunks,
                                        _stream()), "ub200_stage_feed")
@@ -257,11 +275,10 @@ class RankerEngine(object):
             self._pin = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
             self._dev = torch.empty(cap, dtype=torch.uint8, device=self.device)
             self._pin_np = self._pin.numpy()
-        PtrArr = ctypes.c_void_p * L
-        d = [np.ascontiguousarray(x, dtype=np.float32) for x in docid_arrays]
-        y = [np.ascontiguousarray(x, dtype=np.float32) for x in label_arrays]
-        check(lib.ub200_pack_ids_host(PtrArr(*[x.ctypes.data for x in d]), PtrArr(*[x.ctypes.data for x in y]), L, B,
-                                      self._pin.data_ptr(), self._pin.numel()), "ub200_pack_ids_host")
+        dptr, keep_d = column_ptrs(docid_arrays, B)
+        lptr, keep_l = column_ptrs(label_arrays, B)
+        check(lib.ub200_pack_ids_host(dptr, lptr, L, B, self._pin.data_ptr(), self._pin.numel()),
+              "ub200_pack_ids_host")
         self._dev[:nbytes].copy_(self._pin[:nbytes], non_blocking=True)
         st = Staged()
         st.docid = self._dev[:4 * L * B].view(torch.int32).view(L, B)
