@@ -169,3 +169,33 @@ def test_column_ptrs_address_the_same_data_as_the_individual_arrays():
         assert np.array_equal(out, ref)
     with pytest.raises(Exception):
         column_ptrs([d[0], d[1][:5]], B)          # ragged arrays are not a valid feed
+
+
+def test_staged_views_layout_and_cache():
+    """engine.make_staged / StagedCache: the three views alias the staging buffer at the documented offsets, the same
+    (buffer, L, B, n_docs) returns the same object, anything else a fresh one."""
+    from ultra_pytorch_b200.engine import StagedCache, make_staged
+    L, B, n_docs, F = 5, 7, 11, 3
+    off_f = (8 * L * B + 255) // 256 * 256
+    total = off_f + 4 * (n_docs + 1) * F
+    buf = torch.zeros(total + 100, dtype=torch.uint8)
+    raw = buf.numpy()
+    raw[:4 * L * B].view(np.int32)[:] = np.arange(L * B)
+    raw[4 * L * B:8 * L * B].view(np.float32)[:] = np.arange(L * B) + 0.5
+    raw[off_f:total].view(np.float32)[:] = -np.arange((n_docs + 1) * F)
+    st = make_staged(buf, L, B, n_docs, F)
+    assert st.docid.dtype == torch.int32 and tuple(st.docid.shape) == (L, B) and st.docid[2, 3].item() == 2 * B + 3
+    assert tuple(st.labels.shape) == (B, L) and st.labels[4, 1].item() == 4 * L + 1 + 0.5
+    assert tuple(st.feats.shape) == (n_docs + 1, F) and st.feats[n_docs, F - 1].item() == -((n_docs + 1) * F - 1)
+    assert (st.B, st.L, st.n_docs, st.h2d_bytes) == (B, L, n_docs, total)
+    assert st.docid.data_ptr() == buf.data_ptr() and st.feats.data_ptr() == buf.data_ptr() + off_f
+    cache = StagedCache(limit=3)
+    a = cache.get(buf, L, B, n_docs, F)
+    assert cache.get(buf, L, B, n_docs, F) is a
+    b = cache.get(buf, L, B, n_docs - 1, F)
+    assert b is not a and b.n_docs == n_docs - 1
+    other = torch.zeros(total + 100, dtype=torch.uint8)
+    c = cache.get(other, L, B, n_docs, F)
+    assert c is not a and c.docid.data_ptr() == other.data_ptr()
+    cache.get(buf, L, B, n_docs - 2, F)                 # 4th entry: the cache starts over
+    assert len(cache.entries) == 1 and cache.get(buf, L, B, n_docs, F) is not a

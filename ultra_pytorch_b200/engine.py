@@ -48,6 +48,38 @@ class Staged(object):
     __slots__ = ("feats", "docid", "labels", "B", "L", "n_docs", "h2d_bytes")
 
 
+def make_staged(dev, L, B, n_docs, F):
+    """Views of a staging buffer laid out as docid i32 [L, B] | labels f32 [B, L] | pad to 256 B | feats f32 [n_docs+1, F]."""
+    off_l = 4 * L * B
+    off_f = (8 * L * B + 255) // 256 * 256
+    total = off_f + 4 * (n_docs + 1) * F
+    st = Staged()
+    st.docid = dev[:off_l].view(torch.int32).view(L, B)
+    st.labels = dev[off_l:2 * off_l].view(torch.float32).view(B, L)
+    st.feats = dev[off_f:total].view(torch.float32).view(n_docs + 1, F)
+    st.B, st.L, st.n_docs, st.h2d_bytes = B, L, n_docs, total
+    return st
+
+
+class StagedCache(object):
+    """Building the three tensor views costs ~10-20 us of Python per step; the same (buffer, L, B, n_docs) combination
+    recurs every step of a fixed-shape run.  Keyed on the buffer's address: a cached entry keeps its buffer alive, so
+    the address cannot be handed to another tensor while the entry exists."""
+
+    def __init__(self, limit=64):
+        self.limit = limit
+        self.entries = {}
+
+    def get(self, dev, L, B, n_docs, F):
+        key = (dev.data_ptr(), dev.numel(), L, B, n_docs, F)
+        st = self.entries.get(key)
+        if st is None:
+            if len(self.entries) >= self.limit:
+                self.entries.clear()
+            st = self.entries[key] = make_staged(dev, L, B, n_docs, F)
+        return st
+
+
 class RankerEngine(object):
     def __init__(self, feature_size, hidden, device=None, extra_floats=0):
         if not torch.cuda.is_available():
@@ -72,6 +104,7 @@ class RankerEngine(object):
         self.state_sum = torch.zeros(self.P, **f32)
         self.norm = torch.zeros(1, **f32)
         self._ws = {}
+        self._staged_cache = StagedCache()
         self._opt_ws = torch.zeros(int(lib.ub200_opt_workspace_bytes(self.P)), dtype=torch.uint8, device=self.device)
         self._loss_ws = None
         self._pin = None
@@ -230,6 +263,7 @@ class RankerEngine(object):
             self._pin = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
             self._dev = torch.empty(cap, dtype=torch.uint8, device=self.device)
             self._pin_np = self._pin.numpy()
+            self._staged_cache.entries.clear()       # views of the previous staging buffer
         def _f32_vec(x):
             return isinstance(x, np.ndarray) and x.dtype == np.float32 and x.flags.c_contiguous and x.shape == (B,)
         # feeds emit homogeneous per-position arrays (click_simulation_feed.py:141-150): checking the ends is enough
@@ -275,6 +309,7 @@ class RankerEngine(object):
             self._pin = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
             self._dev = torch.empty(cap, dtype=torch.uint8, device=self.device)
             self._pin_np = self._pin.numpy()
+            self._staged_cache.entries.clear()       # views of the previous staging buffer
         dptr, keep_d = column_ptrs(docid_arrays, B)
         lptr, keep_l = column_ptrs(label_arrays, B)
         check(lib.ub200_pack_ids_host(dptr, lptr, L, B, self._pin.data_ptr(), self._pin.numel()),
@@ -331,15 +366,7 @@ class RankerEngine(object):
             self._resident_host = feats                              # keeps the address alive while it is the key
 
     def staged_views(self, dev, L, B, n_docs):
-        off_l = 4 * L * B
-        off_f = (8 * L * B + 255) // 256 * 256
-        total = off_f + 4 * (n_docs + 1) * self.F
-        st = Staged()
-        st.docid = dev[:off_l].view(torch.int32).view(L, B)
-        st.labels = dev[off_l:2 * off_l].view(torch.float32).view(B, L)
-        st.feats = dev[off_f:total].view(torch.float32).view(n_docs + 1, self.F)
-        st.B, st.L, st.n_docs, st.h2d_bytes = B, L, n_docs, total
-        return st
+        return self._staged_cache.get(dev, L, B, n_docs, self.F)
 
     # ---- K1 ---------------------------------------------------------------------------------------
     def forward(self, feats, docid, L, B, training, scores=None):
