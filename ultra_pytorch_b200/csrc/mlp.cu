@@ -13,20 +13,47 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "mlp_f16.cuh"
 #include "mlp_tc.cuh"
 
 namespace ub200 {
 
 // Bit mask: which GEMMs of the tensor-core friendly hidden layers run on tcgen05 (3xTF32): 1 = forward,
 // 2 = data gradient, 4 = weight gradient; 0 = CUDA-core fp32 kernels everywhere.  Default 7 (env UB200_TC overrides).
-enum { TC_FWD = 1, TC_DGRAD = 2, TC_WGRAD = 4, TC_FUSED_FWD = 8 };
+// 16 = forward as fused fp16-split launches (mlp_f16.cu), 32 = fused fp16-split data-gradient chain, 64 = fp16-split
+// weight gradients of all hidden layers in one launch (needs 32).
+enum { TC_FWD = 1, TC_DGRAD = 2, TC_WGRAD = 4, TC_FUSED_FWD = 8, TC_F16_FWD = 16, TC_F16_BWD = 32, TC_F16_WGRAD = 64,
+       TC_ALL = 127 };
 static int g_tc_mode = -1;
 static int tc_mode() {
     if (g_tc_mode < 0) {
         const char* e = getenv("UB200_TC");
-        g_tc_mode = e ? atoi(e) & 15 : 15;
+        g_tc_mode = e ? atoi(e) & TC_ALL : TC_ALL;
     }
     return g_tc_mode;
+}
+// fp16-split path: every hidden width a multiple of 64 and at most 512, feature width a multiple of 4
+static bool f16_net_ok(const LayerDims& d) {
+    const int nh = d.n_layers - 1;
+    if (nh < 1 || d.K[0] % 4 != 0) return false;
+    for (int j = 0; j < nh; ++j)
+        if (d.N[j] % 64 != 0 || d.N[j] > 512) return false;
+    return true;
+}
+static bool f16_bwd_ok(const LayerDims& d) {
+    return f16_net_ok(d) && f16::bwd_shape_ok(d.N, d.n_layers - 1);
+}
+// tile / row-split plan of the one-launch weight-gradient kernel (shapes only; pointers are filled in by the caller)
+static void plan_wgrad16(const LayerDims& d, int M, f16::WgArgs* a) {
+    memset(a, 0, sizeof(*a));
+    a->n = d.n_layers - 1;
+    a->M = M;
+    for (int j = 0; j < a->n; ++j) {
+        a->l[j].N = d.N[j];
+        a->l[j].K = d.K[j];
+        a->l[j].ldp = (d.K[j] + 1 + 3) / 4 * 4;
+    }
+    f16::wgrad_plan(a, kNumSMs);
 }
 static bool use_tc(int j, int K, int N, int what = 7) { return (tc_mode() & what) != 0 && tc_layer_ok(j, K, N); }
 
@@ -84,6 +111,13 @@ struct MlpWorkspace {
     float* wf_lo[UB200_MAX_LAYERS];
     float* wd_hi[UB200_MAX_LAYERS];    // data-gradient operand [K][Npad] = (W * gamma)^T
     float* wd_lo[UB200_MAX_LAYERS];
+    // fp16-split path (mlp_f16.cu)
+    uint16_t* wf16[UB200_MAX_LAYERS];  // forward operand images of 2^8 W gamma
+    uint16_t* wd16[UB200_MAX_LAYERS];  // data-gradient operand images (layers >= 1, training)
+    float* bias2[UB200_MAX_LAYERS];    // b + W beta
+    float* wf2;                        // final layer: gamma_F w_F [K_F] followed by c_F + beta_F . w_F [1]
+    float* dz16[UB200_MAX_LAYERS];     // dZ_j [M, N_j] of every hidden layer (the fused chain produces all of them)
+    unsigned int* dzmax;               // [UB200_MAX_LAYERS] running max |dZ_j| (float bits)
     size_t total_bytes;
 };
 
@@ -127,6 +161,12 @@ static void carve(const LayerDims& d, int M, int training, char* base, MlpWorksp
                 pf = (size_t)wgrad_splits(M, d.N[j], d.K[j] + 1) * d.N[j] * (d.K[j] + 1);
                 const size_t need_tc = (size_t)tc_wgrad_splits(M, d.N[j], d.K[j]) * d.N[j] * round_up(d.K[j] + 1, 4);
                 pf = need_tc > pf ? need_tc : pf;
+                if (f16_bwd_ok(d)) {
+                    f16::WgArgs plan;
+                    plan_wgrad16(d, M, &plan);
+                    const size_t need16 = (size_t)plan.l[j].splits * d.N[j] * plan.l[j].ldp;
+                    pf = need16 > pf ? need16 : pf;
+                }
             }
             w->partials[j] = reinterpret_cast<float*>(base + off);
             off = align_up(off + sizeof(float) * pf, 256);
@@ -164,7 +204,61 @@ static void carve(const LayerDims& d, int M, int training, char* base, MlpWorksp
             off = align_up(off + sizeof(float) * nd, 256);
         }
     }
+    for (int j = 0; j < UB200_MAX_LAYERS; ++j) {
+        w->wf16[j] = w->wd16[j] = nullptr;
+        w->bias2[j] = w->dz16[j] = nullptr;
+    }
+    w->wf2 = nullptr;
+    w->dzmax = nullptr;
+    if (f16_net_ok(d)) {
+        const int nh = d.n_layers - 1;
+        for (int j = 0; j < nh; ++j) {
+            w->wf16[j] = reinterpret_cast<uint16_t*>(base + off);
+            off = align_up(off + f16::prep_bytes_wf(d.K[j], d.N[j]), 1024);
+            if (training && j > 0) {
+                w->wd16[j] = reinterpret_cast<uint16_t*>(base + off);
+                off = align_up(off + f16::prep_bytes_wd(d.K[j], d.N[j]), 1024);
+            }
+            w->bias2[j] = reinterpret_cast<float*>(base + off);
+            off = align_up(off + sizeof(float) * d.N[j], 256);
+            if (training) {
+                w->dz16[j] = reinterpret_cast<float*>(base + off);
+                off = align_up(off + sizeof(float) * (size_t)M * d.N[j], 256);
+            }
+        }
+        w->wf2 = reinterpret_cast<float*>(base + off);
+        off = align_up(off + sizeof(float) * (d.K[nh] + 1), 256);
+        w->dzmax = reinterpret_cast<unsigned int*>(base + off);
+        off = align_up(off + sizeof(unsigned int) * UB200_MAX_LAYERS, 256);
+    }
     w->total_bytes = off;
+}
+
+// fp16-split operand images + folded biases for this step's parameters
+static int prep_f16_weights(const LayerDims& d, const MlpWorkspace& w, const float* params, int training,
+                            cudaStream_t st) {
+    const int nh = d.n_layers - 1;
+    f16::PrepArgs t{};
+    t.n = nh;
+    for (int j = 0; j < nh; ++j) {
+        t.W[j] = params + d.off_w[j];
+        t.gamma[j] = params + d.off_g[j];
+        t.beta[j] = params + d.off_b[j];
+        t.bias[j] = params + d.off_c[j];
+        t.wf[j] = w.wf16[j];
+        t.wd[j] = training ? w.wd16[j] : nullptr;
+        t.bias2[j] = w.bias2[j];
+        t.K[j] = d.K[j];
+        t.N[j] = d.N[j];
+    }
+    t.gF = params + d.off_g[nh];
+    t.bF = params + d.off_b[nh];
+    t.wF = params + d.off_w[nh];
+    t.cF = params + d.off_c[nh];
+    t.KF = d.K[nh];
+    t.wf2 = w.wf2;
+    t.cf2 = w.wf2 + d.K[nh];
+    return f16::prep(t, st);
 }
 
 // split the weights of the tensor-core layers into (hi, lo) TF32 operands for this step
@@ -614,13 +708,68 @@ static void launch_gemm(const GemmArgs& a, int splits, cudaStream_t st) {
     }
 }
 
+// forward pass as fused fp16-split launches: maximal runs of layers with N <= 256 are chained in one kernel (the final
+// ->1 layer rides on the last run); a wider layer runs alone, split into column tiles, and hands its activations to
+// the next run through HBM/L2
+static int forward_f16(const LayerDims& d, const MlpWorkspace& w, const float* feats, const int32_t* docid, int L, int B,
+                       const float* params, float* scores, int training, cudaStream_t st) {
+    const int nh = d.n_layers - 1, M = L * B;
+    if (int rc = prep_f16_weights(d, w, params, training, st)) return rc;
+    const float* X = feats;
+    const int32_t* idx = docid;
+    bool final_done = false;
+    int j = 0;
+    while (j < nh) {
+        f16::FwdArgs a{};
+        a.M = M; a.L = L; a.B = B;
+        a.K0 = d.K[j];
+        a.X = X; a.docid = idx;
+        a.write_acts = training ? 1 : 0;
+        a.scores = scores;
+        a.wf2 = w.wf2;
+        a.cf2 = w.wf2 + d.K[nh];
+        int run = 1;
+        if (d.N[j] > 256) {
+            const int N = d.N[j];
+            a.bn0 = N % 256 == 0 ? 256 : (N % 192 == 0 ? 192 : (N % 128 == 0 ? 128 : 64));
+        } else {
+            while (j + run < nh && run < f16::MAXF && d.N[j + run] <= 256) ++run;
+            a.bn0 = d.N[j];
+            a.has_final = (j + run == nh) ? 1 : 0;
+        }
+        a.nl = run;
+        for (int q = 0; q < run; ++q) {
+            a.N[q] = d.N[j + q];
+            a.dual[q] = d.K[j + q] > 256 ? 1 : 0;
+            a.wimg[q] = w.wf16[j + q];
+            a.bias2[q] = w.bias2[j + q];
+            a.Y[q] = w.Y[j + q];
+            if (training || (run == 1 && !a.has_final))
+                if (int rc = f16::make_tmap_f32(&a.ymap[q], w.Y[j + q], (size_t)M, (size_t)d.N[j + q])) return rc;
+        }
+        for (int q = 0; q <= run; ++q) a.stats[q] = w.stats[j + q];
+        if (int rc = f16::fwd(a, st)) return rc;
+        final_done = a.has_final != 0;
+        X = w.Y[j + run - 1];
+        idx = nullptr;
+        j += run;
+    }
+    if (!final_done) {
+        const int K = d.K[nh];
+        launch_k(final_fwd_kernel, (M + 7) / 8, 256, 0, st, X, idx, M, K, params + d.off_g[nh], params + d.off_b[nh],
+                 params + d.off_w[nh], params + d.off_c[nh], w.stats[nh], scores, L, B);
+        UB_LAUNCH_CHECK("final_fwd_kernel");
+    }
+    return 0;
+}
+
 }  // namespace ub200
 
 using namespace ub200;
 
 extern "C" UB200_API int ub200_set_tc_mode(int mode) {
     const int old = tc_mode();
-    g_tc_mode = mode & 15;
+    g_tc_mode = mode & TC_ALL;
     return old;
 }
 
@@ -654,7 +803,14 @@ extern "C" UB200_API int ub200_mlp_forward(const float* feats, const int32_t* do
     const int row_blocks = (M + 7) / 8;
     const float* X = feats;
     const int32_t* idx = docid;
+    if ((tc_mode() & TC_F16_FWD) && f16_net_ok(d)) {
+        if (training && !((tc_mode() & TC_F16_BWD) && f16_bwd_ok(d)))
+            if (int rc = prep_tc_weights(d, w, params, training, st)) return rc;      // TF32 images for the old backward
+        return forward_f16(d, w, feats, docid, L, B, params, scores, training, st);
+    }
     if (int rc = prep_tc_weights(d, w, params, training, st)) return rc;
+    if (training && (tc_mode() & TC_F16_BWD) && f16_bwd_ok(d))
+        if (int rc = prep_f16_weights(d, w, params, training, st)) return rc;        // fp16 images for the new backward
     // Fused tail: from the first layer j0 whose successors fit the tensor-memory plan (N_j0 <= 256, later N <= 128),
     // ONE kernel runs the rest of the forward pass with the activations staying in tensor memory.  j0 = 0 for
     // DNN[256,128,64]; j0 = 1 for the reference default DNN[512,256,128] (layer 0 runs as a per-layer GEMM).
@@ -768,7 +924,9 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
         if (ss) cudaStreamWaitEvent(st, ss->done_ev[j], 0);
     };
 
-    // final layer (N = 1): dZ_{nl-2} goes to dz[(nl-2) % 3]
+    const bool chain16 = (tc_mode() & TC_F16_BWD) && f16_bwd_ok(d);
+    // final layer (N = 1): parameter-gradient partials (+ dZ_{nl-2} into dz[(nl-2) % 3] on the per-layer path).  With the
+    // fused chain this kernel only feeds the final layer's own gradients, so it runs on a side stream next to the chain.
     {
         const int j = nl - 1, K = d.K[j];
         const float* X = (j == 0) ? feats : w.Y[j - 1];
@@ -779,11 +937,15 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
         UB_CHECK(smem <= 200 * 1024, 4, "mlp_backward: final-layer width %d too large", K);
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(final_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        launch_k(final_bwd_kernel, blocks, 256, smem, st, X, idx, w.stats[j], M, K, params + d.off_g[j],
-                                                    params + d.off_w[j], dscores, L, B,
-                                                    (j == 0) ? nullptr : w.dz[(j - 1) % 3], w.partials[j]);
-        UB_LAUNCH_CHECK("final_bwd_kernel");
-        cudaStream_t sb = fork(j);
+        cudaStream_t sf = chain16 ? fork(j) : st;
+        {
+            PriorityScope p(chain16 && ss ? prio_lo : launch_priority());
+            launch_k(final_bwd_kernel, blocks, 256, smem, sf, X, idx, w.stats[j], M, K, params + d.off_g[j],
+                     params + d.off_w[j], dscores, L, B, (j == 0 || chain16) ? nullptr : w.dz[(j - 1) % 3],
+                     w.partials[j]);
+            UB_LAUNCH_CHECK("final_bwd_kernel");
+        }
+        cudaStream_t sb = chain16 ? sf : fork(j);
         PriorityScope side_priority(ss ? prio_lo : 0);
         launch_k(final_finalize_kernel, (K + 31) / 32, 256, 0, sb, w.partials[j], blocks, K, params + d.off_w[j],
                                                              params + d.off_g[j], params + d.off_b[j],
@@ -791,6 +953,54 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
                                                              grads + d.off_g[j], grads + d.off_b[j]);
         UB_LAUNCH_CHECK("final_finalize_kernel");
         branch_done(j);
+    }
+    if (chain16) {
+        // fused data-gradient chain (mlp_f16.cu): ONE launch produces dZ_j of every hidden layer; the weight-gradient
+        // branches below then only need their own dZ_j
+        f16::BwdArgs b{};
+        const int nh = nl - 1;
+        b.M = M; b.L = L; b.B = B; b.nl = nh; b.KF = d.K[nh];
+        b.dscores = dscores;
+        b.wf2 = w.wf2;
+        for (int q = 0; q < nh; ++q) {
+            b.N[q] = d.N[q];
+            b.Y[q] = w.Y[q];
+            b.wd[q] = w.wd16[q];
+            b.dZ[q] = w.dz16[q];
+            b.dzmax[q] = w.dzmax + q;
+        }
+        for (int q = 0; q <= nh; ++q) b.stats[q] = w.stats[q];
+        if (int rc = f16::bwd(b, st)) return rc;
+    }
+    const bool wgrad16 = chain16 && (tc_mode() & TC_F16_WGRAD);
+    if (wgrad16) {
+        // ONE launch for the weight-gradient partials of every hidden layer, then the per-layer finalize kernels side
+        // by side (caller's stream + the two side streams)
+        f16::WgArgs wa;
+        plan_wgrad16(d, M, &wa);
+        for (int j = 0; j < nl - 1; ++j) {
+            f16::WgLayer& l = wa.l[j];
+            l.dZ = w.dz16[j];
+            l.X = (j == 0) ? feats : w.Y[j - 1];
+            l.docid = (j == 0) ? docid : nullptr;
+            l.stats = w.stats[j];
+            l.dzmax = w.dzmax + j;
+            l.out = w.partials[j];
+        }
+        if (int rc = f16::wgrad(wa, st)) return rc;
+        for (int j = nl - 2; j >= 0; --j) {
+            const int K = d.K[j], N = d.N[j];
+            cudaStream_t sb = (j == 0) ? st : fork(j);
+            launch_k(wgrad_finalize_kernel, dim3((K + 31) / 32, (N + 7) / 8), 256, 0, sb, w.partials[j], wa.l[j].splits, N,
+                     K, wa.l[j].ldp, params + d.off_w[j], params + d.off_g[j], params + d.off_b[j], grads + d.off_w[j],
+                     grads + d.off_c[j], grads + d.off_g[j], grads + d.off_b[j], w.fin_scratch[j], w.fin_counters[j]);
+            UB_LAUNCH_CHECK("wgrad_finalize_kernel");
+            if (j > 0) branch_done(j);
+        }
+        cudaMemsetAsync(w.dzmax, 0, sizeof(unsigned int) * UB200_MAX_LAYERS, st);     // running maxima of the next step
+        wait_branch(nl - 1);
+        for (int j = 1; j < nl - 1; ++j) wait_branch(j);
+        return 0;
     }
     // hidden layers, last to first; dz[j % 3] holds dZ_j [M, N_j]
     for (int j = nl - 2; j >= 0; --j) {
@@ -800,7 +1010,7 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
         const float* g = params + d.off_g[j];
         const float* bt = params + d.off_b[j];
         const float* W = params + d.off_w[j];
-        const float* dz = w.dz[j % 3];
+        const float* dz = chain16 ? w.dz16[j] : w.dz[j % 3];
         // ---- weight-gradient branch (side stream): G[n, k] (k == K -> db) split over row chunks, then finalize ----
         cudaStream_t sb = fork(j);
         int S_eff, ldp;
@@ -836,7 +1046,7 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
         }
         branch_done(j);
         // ---- data-gradient chain (caller's stream) ----
-        if (j > 0) {
+        if (j > 0 && !chain16) {
             // dZ_{j-1} goes to dz[(j-1) % 3], the buffer dZ_{j+2} lived in: that layer's weight-gradient branch (forked
             // two layers ago) must have finished reading it
             const bool tc_d = use_tc(j, K, N, TC_DGRAD);

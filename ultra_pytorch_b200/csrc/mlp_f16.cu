@@ -1,0 +1,1284 @@
+// K1 on tcgen05 with fp16-split operands: fused forward and fused data-gradient chain of the DNN ranker.
+//
+// Replaces (reference): the [LayerNorm -> Linear -> ELU] x n + LayerNorm -> Linear(1) stack ultra/ranking_model/DNN.py:43-55,77
+// and the data-gradient half of its autograd backward.
+//
+// One CTA owns a tile of 128 rows and walks the whole layer chain with the activations staying on chip:
+//
+//   warps 0-15  workers.  Thread = (row, column group): TMEM lane quadrant q4 = warp % 4 gives the row, cg = warp / 4
+//               the 16-column slice of every 64-column block.  They (a) build the first A operand from global memory
+//               (row gather + LayerNorm + fp16 hi/lo split into the 128B-swizzled ring), (b) run every layer's epilogue
+//               out of tensor memory - bias + ELU + row statistics (forward) or LayerNorm-backward . ELU' (backward) -
+//               holding the 128 x N tile in REGISTERS across the row-statistics exchange, and (c) write the next
+//               layer's A operand straight into the ring (normalised / scaled, split), so an activation tile goes
+//               TMEM -> registers -> shared memory -> tensor core without touching TMEM or HBM again.
+//   warp 16     one thread issues  hi*hi + lo*hi + hi*lo  as three tcgen05.mma.kind::f16 per K = 16 step.
+//   warp 17     one thread streams the pre-split, pre-swizzled weight images (prep_kernel) through the TMA engine
+//               (cp.async.bulk + mbarrier expect_tx), running ahead of the MMAs by the depth of the B ring.
+//
+// Operand scaling (exact powers of two, undone in the epilogues): weights x 2^8; data-gradient rows by 2^(10 - E) with
+// E the exponent of the row's max |dZ| (the contraction runs along the row, so the factor commutes with the GEMM).
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "mlp_f16.cuh"
+#include "tc_ptx.cuh"
+
+namespace ub200 {
+namespace f16 {
+
+using namespace ub200::tc;
+
+constexpr int NW = 16;                        // worker warps
+constexpr int NWT = NW * 32;                  // 512 worker threads
+constexpr int MMA_WARP = 16, TMA_WARP = 17;
+constexpr int NTHREADS = 20 * 32;          // 4 worker warpgroups + 1 control warpgroup (warps 18, 19 idle)
+constexpr int A_STAGES = 3;
+constexpr int A_HALF = 128 * 128;             // one (hi | lo) A tile: 128 rows x 64 fp16
+constexpr int A_STAGE = 2 * A_HALF;           // 32 KB
+constexpr int A_BYTES = A_STAGES * A_STAGE;   // 96 KB
+constexpr int B_BYTES = 128 * 1024;           // weight ring: stages of 2 * BN * 128 B, at most 4
+constexpr int B_MAX_STAGES = 4;
+constexpr int CTL_BYTES = 1024;
+constexpr int SMEM_BYTES = A_BYTES + B_BYTES + CTL_BYTES + 1024;
+constexpr float W_SCALE = 256.f, W_UNSCALE = 1.f / 256.f;
+
+#ifdef UB200_F16_TIMELINE
+// in-kernel timeline of CTA 0 (SM clock): row 0 = worker thread 0, row 1 = MMA thread, row 2 = TMA thread
+__device__ long long g_tl[3][64];
+#define TL(role, i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (role == 0 || (threadIdx.x & 31) == 0)) g_tl[role][i] = clock64(); } while (0)
+#else
+#define TL(role, i) do { } while (0)
+#endif
+
+__host__ __device__ inline int b_stage_bytes(int bn) { return 2 * bn * 128; }
+__host__ __device__ inline int b_stages(int bn) {
+    const int s = B_BYTES / b_stage_bytes(bn);
+    return s > B_MAX_STAGES ? B_MAX_STAGES : s;
+}
+
+__device__ __forceinline__ float elu_fast(float z) { return z > 0.f ? z : __expf(z) - 1.f; }
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+struct Bars {
+    uint64_t a_full[MAXF][A_STAGES];
+    uint64_t a_empty[MAXF][A_STAGES];
+    uint64_t b_full[MAXF][B_MAX_STAGES];
+    uint64_t b_empty[MAXF][B_MAX_STAGES];
+    uint64_t accum[MAXF];
+    uint32_t tmem_slot;
+};
+static_assert(sizeof(Bars) <= CTL_BYTES, "control block too large");
+
+// register re-allocation between the warpgroups (the compile-time cap for 640 threads is 96): the control warpgroup
+// gives up what it does not need, the workers take 112 to hold a 128 x 256 tile slice (64 values) without spilling
+#ifndef UB200_REGS_CTRL
+#define UB200_REGS_CTRL 32
+#define UB200_REGS_WORK 112
+#endif
+#define UB200_STR2(x) #x
+#define UB200_STR(x) UB200_STR2(x)
+__device__ __forceinline__ void regs_control() { asm volatile("setmaxnreg.dec.sync.aligned.u32 " UB200_STR(UB200_REGS_CTRL) ";"); }
+__device__ __forceinline__ void regs_worker() { asm volatile("setmaxnreg.inc.sync.aligned.u32 " UB200_STR(UB200_REGS_WORK) ";"); }
+
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NWT) : "memory"); }
+
+// 16 fp32 values (columns 16 cg .. + 15 of a 64-column chunk of row `trow`) -> fp16 hi / lo, two 16-byte stores each
+__device__ __forceinline__ void store_split16(uint8_t* stage, int trow, int cg, const float* v) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) split_h2(v[h * 8 + 2 * p], v[h * 8 + 2 * p + 1], hi[p], lo[p]);
+        const uint32_t off = swz128((uint32_t)trow, (uint32_t)(cg * 2 + h));
+        *reinterpret_cast<uint4*>(stage + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(stage + A_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// A operand of the first layer from global memory: rows (optionally gathered) x K0, LayerNorm statistics with shifted
+// sums, then chunk by chunk (64 columns) normalise + split into the ring.  All 512 worker threads; thread = float4 `c`
+// (0..15) of rows r0 + 32 e.  NCH > 0: the row slice (NCH chunks, K0 <= 64 NCH) stays in registers between the
+// statistics and the conversion, so the features are read once and every load of the tile is in flight together.
+template <int NCH>
+__device__ __forceinline__ void produce_first(const float* __restrict__ X, const int32_t* __restrict__ docid, int M,
+                                              int K0, int i0, uint8_t* a_ring, uint64_t* a_full, uint64_t* a_empty,
+                                              float2* stats_out, int tid, int lane) {
+    const int c = tid & 15, r0 = tid >> 4;
+    constexpr int NV = NCH > 0 ? NCH : 1;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* xrow[4];
+    float4 xv[4][NV];
+    float mu[4], rs[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int m = i0 + r0 + 32 * e;
+        xrow[e] = (m < M) ? X + (size_t)(docid ? docid[m] : m) * K0 : nullptr;
+    }
+    if (NCH > 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const int cc = j * 64 + c * 4;
+                xv[e][j] = (cc < K0 && xrow[e]) ? ld4(xrow[e] + cc) : zero4;
+            }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int m = i0 + r0 + 32 * e;
+        float s1 = 0.f, s2 = 0.f;
+        float shift;
+        if (NCH > 0) {
+            shift = __shfl_sync(0xffffffffu, xv[e][0].x, lane & 16);        // the row's first element (lane c == 0)
+#pragma unroll
+            for (int j = 0; j < NV; ++j)
+                if (j * 64 + c * 4 < K0) {
+                    const float4 v = xv[e][j];
+                    const float dx = v.x - shift, dy = v.y - shift, dz = v.z - shift, dw = v.w - shift;
+                    s1 += (dx + dy) + (dz + dw);
+                    s2 += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+                }
+        } else {
+            shift = xrow[e] ? xrow[e][0] : 0.f;
+            if (xrow[e])
+                for (int cc = c * 4; cc < K0; cc += 64) {
+                    const float4 v = ld4(xrow[e] + cc);
+                    const float dx = v.x - shift, dy = v.y - shift, dz = v.z - shift, dw = v.w - shift;
+                    s1 += (dx + dy) + (dz + dw);
+                    s2 += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+                }
+        }
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        const float mean = shift + s1 / (float)K0;
+        const float var = fmaxf(s2 - s1 * s1 / (float)K0, 0.f) / (float)K0;
+        mu[e] = mean;
+        rs[e] = 1.0f / sqrtf(var + kLnEps);
+        if (stats_out && xrow[e] && c == 0) stats_out[m] = make_float2(mean, rs[e]);
+    }
+    if (tid == 0) TL(0, 5);
+    const int nch = (K0 + 63) >> 6;
+    float4 cur[4], nxt[4];
+    auto load_chunk = [&](int it, float4* v) {
+        const int cc = it * 64 + c * 4;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = (cc < K0 && xrow[e]) ? ld4(xrow[e] + cc) : zero4;
+    };
+    auto convert_store = [&](int it, const float4* v4) {
+        const int s = it % A_STAGES;
+        const uint32_t ph = (uint32_t)(it / A_STAGES) & 1u;
+        mbar_wait(&a_empty[s], ph ^ 1u);
+        uint8_t* stage = a_ring + s * A_STAGE;
+        const bool kv = it * 64 + c * 4 < K0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float4 v = v4[e];
+            const float nb = -mu[e] * rs[e];
+            v.x = fmaf(v.x, rs[e], nb);
+            v.y = fmaf(v.y, rs[e], nb);
+            v.z = fmaf(v.z, rs[e], nb);
+            v.w = fmaf(v.w, rs[e], nb);
+            if (!kv || !xrow[e]) v = zero4;
+            uint32_t h0, h1, l0, l1;
+            split_h2(v.x, v.y, h0, l0);
+            split_h2(v.z, v.w, h1, l1);
+            const uint32_t off = swz128((uint32_t)(r0 + 32 * e), (uint32_t)(c >> 1)) + (uint32_t)(c & 1) * 8u;
+            *reinterpret_cast<uint2*>(stage + off) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(stage + A_HALF + off) = make_uint2(l0, l1);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[s]);
+    };
+    if (NCH > 0) {
+#pragma unroll
+        for (int it = 0; it < NV; ++it) {
+            if (it < nch) {
+                const float4 v4[4] = {xv[0][it], xv[1][it], xv[2][it], xv[3][it]};
+                convert_store(it, v4);
+            }
+        }
+    } else {
+        load_chunk(0, cur);
+        for (int it = 0; it < nch; ++it) {
+            if (it + 1 < nch) load_chunk(it + 1, nxt);
+            convert_store(it, cur);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) cur[e] = nxt[e];
+        }
+    }
+}
+
+// streams the B (weight image) tiles of one layer: chunk it, column half h -> ring stage (it * nh + h) % nst
+__device__ __forceinline__ void tma_layer(const uint16_t* img, int rows_total, int row0, int bn, int nh, int nch,
+                                          uint8_t* b_ring, uint64_t* b_full, uint64_t* b_empty) {
+    const int sb = b_stage_bytes(bn), nst = b_stages(bn);
+    const uint32_t half_bytes = (uint32_t)bn * 128u;
+    int g = 0;
+    for (int it = 0; it < nch; ++it)
+        for (int h = 0; h < nh; ++h, ++g) {
+            const int s = g % nst;
+            const uint32_t ph = (uint32_t)(g / nst) & 1u;
+            mbar_wait(&b_empty[s], ph ^ 1u);
+            uint8_t* dst = b_ring + s * sb;
+            const uint16_t* hi = img + ((size_t)(it * 2 + 0) * rows_total + row0 + h * bn) * 64;
+            const uint16_t* lo = img + ((size_t)(it * 2 + 1) * rows_total + row0 + h * bn) * 64;
+            mbar_arrive_expect_tx(&b_full[s], 2 * half_bytes);
+            bulk_g2s(dst, hi, half_bytes, &b_full[s]);
+            bulk_g2s(dst + half_bytes, lo, half_bytes, &b_full[s]);
+        }
+}
+
+// issues the MMAs of one layer: D[h] (+)= A[it] * B[it][h]^T over the contraction chunks; kc = contraction length.
+// ONE thread runs this; the other lanes of its warp wait at the final block barrier.  (Running the loop warp-converged
+// with an elected lane issuing - the usual CUTLASS shape - dead-locked on hardware in two different formulations, and
+// the compiler's uniform-operand "waterfall" code around the unrolled form below produced out-of-range descriptors in
+// the backward kernel (compute-sanitizer), so the backward pass keeps the plain loop.)  FAST = the K = 16 steps
+// unrolled with descriptors advanced by adds and no memory clobber on the MMA asm: every instruction's latency is
+// exposed in a single-threaded loop, and the plain form pays ~160 cycles per tcgen05.mma (in-kernel timeline) against
+// ~80 for the unrolled one; the tensor core itself needs 32 - 128.
+template <bool DUAL, bool FAST>
+__device__ __forceinline__ void mma_layer_impl(uint32_t tmem_base, int kc, int bn, int nh, uint8_t* a_ring,
+                                               uint8_t* b_ring, uint64_t* a_full, uint64_t* a_empty, uint64_t* b_full,
+                                               uint64_t* b_empty, uint64_t* accum, int tl_base) {
+    const int nch = (kc + 63) >> 6;
+    const int sb = b_stage_bytes(bn), nst = b_stages(bn);
+    const uint32_t idesc = make_idesc_f16(bn, 0, 0);
+    const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_ring);
+    int g = 0;
+    for (int it = 0; it < nch; ++it) {
+        const int sa = it % A_STAGES;
+        mbar_wait(&a_full[sa], (uint32_t)(it / A_STAGES) & 1u);
+        const uint32_t a_hi = a_base + sa * A_STAGE, a_lo = a_hi + A_HALF;
+        const int rem = kc - it * 64;
+        const int nk = rem >= 64 ? 4 : (rem + 15) >> 4;
+        for (int h = 0; h < nh; ++h, ++g) {
+            const int s = g % nst;
+            mbar_wait(&b_full[s], (uint32_t)(g / nst) & 1u);
+            tc_fence_after();
+            TL(1, 16 + 2 * (tl_base + it));
+            const uint32_t b_hi = b_base + s * sb, b_lo = b_hi + (uint32_t)bn * 128u;
+            const uint32_t d_main = tmem_base + (uint32_t)h * 256u;
+            const uint32_t d_corr = DUAL ? tmem_base + 256u : d_main;
+            if (FAST) {
+                const uint64_t dah0 = make_smem_desc(a_hi, 16, 1024), dal0 = make_smem_desc(a_lo, 16, 1024);
+                const uint64_t dbh0 = make_smem_desc(b_hi, 16, 1024), dbl0 = make_smem_desc(b_lo, 16, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k < nk) {
+                        const uint64_t dah = desc_advance(dah0, k * 32), dal = desc_advance(dal0, k * 32);
+                        const uint64_t dbh = desc_advance(dbh0, k * 32), dbl = desc_advance(dbl0, k * 32);
+                        const uint32_t acc = (it | k) != 0 ? 1u : 0u;
+                        if (DUAL) {
+                            mma_f16(d_corr, dal, dbh, idesc, acc);
+                            mma_f16(d_corr, dah, dbl, idesc, 1u);
+                            mma_f16(d_main, dah, dbh, idesc, acc);
+                        } else {
+                            mma_f16(d_main, dah, dbh, idesc, acc);
+                            mma_f16(d_main, dal, dbh, idesc, 1u);
+                            mma_f16(d_main, dah, dbl, idesc, 1u);
+                        }
+                    }
+                }
+            } else {
+                for (int k = 0; k < nk; ++k) {
+                    const uint64_t dah = make_smem_desc(a_hi + k * 32, 16, 1024), dal = make_smem_desc(a_lo + k * 32, 16, 1024);
+                    const uint64_t dbh = make_smem_desc(b_hi + k * 32, 16, 1024), dbl = make_smem_desc(b_lo + k * 32, 16, 1024);
+                    const uint32_t acc = (it | k) != 0 ? 1u : 0u;
+                    if (DUAL) {
+                        mma_f16_sync(d_corr, dal, dbh, idesc, acc);
+                        mma_f16_sync(d_corr, dah, dbl, idesc, 1u);
+                        mma_f16_sync(d_main, dah, dbh, idesc, acc);
+                    } else {
+                        mma_f16_sync(d_main, dah, dbh, idesc, acc);
+                        mma_f16_sync(d_main, dal, dbh, idesc, 1u);
+                        mma_f16_sync(d_main, dah, dbl, idesc, 1u);
+                    }
+                }
+            }
+            mma_commit(&b_empty[s]);
+            TL(1, 17 + 2 * (tl_base + it));
+        }
+        mma_commit(&a_empty[sa]);
+    }
+    mma_commit(accum);
+}
+template <bool FAST>
+__device__ __forceinline__ void mma_layer(uint32_t tmem_base, int kc, int bn, int nh, int dual, uint8_t* a_ring,
+                                          uint8_t* b_ring, uint64_t* a_full, uint64_t* a_empty, uint64_t* b_full,
+                                          uint64_t* b_empty, uint64_t* accum, int tl_base = 0) {
+    if (dual) mma_layer_impl<true, FAST>(tmem_base, kc, bn, nh, a_ring, b_ring, a_full, a_empty, b_full, b_empty, accum, tl_base);
+    else mma_layer_impl<false, FAST>(tmem_base, kc, bn, nh, a_ring, b_ring, a_full, a_empty, b_full, b_empty, accum, tl_base);
+}
+
+// combine the 4 column groups' (mean, M2) partials of a row (each over `cnt` values) in fixed order -> (mean, rstd)
+__device__ __forceinline__ float2 combine_stats(const float2* part, int trow, float cnt, int n_total) {
+    float n = 0.f, mean = 0.f, M2 = 0.f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const float2 p = part[g * 128 + trow];
+        const float dlt = p.x - mean, tot = n + cnt;
+        mean += dlt * cnt / tot;
+        M2 += p.y + dlt * dlt * n * cnt / tot;
+        n = tot;
+    }
+    return make_float2(mean, 1.0f / sqrtf(fmaxf(M2, 0.f) / (float)n_total + kLnEps));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------------
+// epilogue of forward layer q for this thread's 16 * NQ columns: bias + ELU out of tensor memory into registers, row
+// statistics, then either the next layer's A operand, the fused final layer, or nothing (single-layer launch).
+template <int NQ>
+__device__ __forceinline__ void fwd_epilogue(const FwdArgs& a, int q, int n0, uint32_t tlane, int trow, int cg, int grow,
+                                             int lane, uint8_t* a_ring, Bars* bars) {
+    const int Nfull = a.N[q];
+    const bool last = (q + 1 == a.nl);
+    const bool need_stats = !last || a.has_final;
+    const bool row_ok = grow < a.M;
+    const bool store_y = a.write_acts || (last && !a.has_final);   // a lone layer hands its output on through memory
+    const int i0 = grow - trow, col0 = n0;
+    float y[16 * NQ];
+    float shift = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < NQ; ++it) {
+        uint32_t r[16];
+        tmem_ld16_nowait(tlane + it * 64 + cg * 16, r);
+        const int col = n0 + it * 64 + cg * 16;
+        float bias[16];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const float4 b = ldg4(a.bias2[q] + col + 4 * p);
+            bias[4 * p] = b.x; bias[4 * p + 1] = b.y; bias[4 * p + 2] = b.z; bias[4 * p + 3] = b.w;
+        }
+        if (a.dual[q]) {
+            uint32_t rc[16];
+            tmem_ld16_nowait(tlane + 256 + it * 64 + cg * 16, rc);
+            tmem_wait_ld16(rc);
+            tmem_wait_ld16(r);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                y[it * 16 + i] = elu_fast(fmaf(__uint_as_float(r[i]) + __uint_as_float(rc[i]), W_UNSCALE, bias[i]));
+        } else {
+            tmem_wait_ld16(r);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y[it * 16 + i] = elu_fast(fmaf(__uint_as_float(r[i]), W_UNSCALE, bias[i]));
+        }
+        if (it == 0) shift = y[0];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float d = y[it * 16 + i] - shift;
+            s1 += d;
+            s2 = fmaf(d, d, s2);
+        }
+        if (store_y) {
+            // Y chunk (128 rows x 64 columns) -> shared-memory staging in the TMA box layout (two [128][32] fp32 halves,
+            // 128B swizzle; 32 rows x 16 B per store instruction = 4 wavefronts, the minimum), then ONE thread issues the
+            // tensor stores: full 128-byte lines leave the SM instead of 32 scattered 16-byte pieces per instruction
+            // (a thread-per-row global store cost 3.3 us of the layer-0 epilogue, in-kernel timeline).  Rows >= M are
+            // clipped by the tensor map.  Buffers alternate (it & 1) inside the idle A ring.
+            uint8_t* stg = a_ring + (it & 1) * A_STAGE + (cg >> 1) * 16384 + trow * 128;
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+                *reinterpret_cast<float4*>(stg + ((((cg & 1) * 4 + p) ^ (trow & 7)) << 4)) =
+                    make_float4(y[it * 16 + 4 * p], y[it * 16 + 4 * p + 1], y[it * 16 + 4 * p + 2], y[it * 16 + 4 * p + 3]);
+            fence_proxy_async();
+            if (threadIdx.x == 0) bulk_wait_read0();      // the store issued from the buffer written next has drained
+            worker_bar();
+            if (threadIdx.x == 0) {
+                const uint8_t* src = a_ring + (it & 1) * A_STAGE;
+                tma_store_2d(&a.ymap[q], src, col0 + it * 64, i0);
+                tma_store_2d(&a.ymap[q], src + 16384, col0 + it * 64 + 32, i0);
+                bulk_commit();
+            }
+        }
+    }
+    tc_fence_before();          // the accumulator columns may be overwritten by the next layer's MMAs from here on
+    if (threadIdx.x == 0) TL(0, 9 + 4 * q);
+    if (store_y && threadIdx.x == 0) bulk_wait_read0();          // staging buffers free before the ring is reused / exit
+    if (!need_stats) return;
+    constexpr float cnt = 16.f * NQ;
+    float2* part = reinterpret_cast<float2*>(a_ring + 2 * A_STAGE);   // the A ring is idle between layers (stages 0, 1: Y staging)
+    part[cg * 128 + trow] = make_float2(shift + s1 / cnt, s2 - s1 * s1 / cnt);
+    worker_bar();
+    const float2 st = combine_stats(part, trow, cnt, Nfull);
+    if (a.write_acts && row_ok && cg == 0) a.stats[q + 1][grow] = st;
+    worker_bar();               // everybody has read the partials before the ring is written again
+    if (threadIdx.x == 0) TL(0, 10 + 4 * q);
+    const float rs = st.y, nb = -st.x * st.y;
+    if (!last) {
+        uint64_t* a_full = bars->a_full[q + 1];
+        uint64_t* a_empty = bars->a_empty[q + 1];
+#pragma unroll
+        for (int it = 0; it < NQ; ++it) {
+            const int s = it % A_STAGES;
+            mbar_wait(&a_empty[s], ((uint32_t)(it / A_STAGES) & 1u) ^ 1u);
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = row_ok ? fmaf(y[it * 16 + i], rs, nb) : 0.f;
+            store_split16(a_ring + s * A_STAGE, trow, cg, v);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[s]);
+        }
+        if (threadIdx.x == 0) TL(0, 11 + 4 * q);
+    } else {
+        // final layer: score = sum_n xhat_n (gamma_n w_n) + (c + beta . w)
+        float acc = 0.f;
+#pragma unroll
+        for (int it = 0; it < NQ; ++it) {
+            const int col = it * 64 + cg * 16;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const float4 w = ldg4(a.wf2 + col + 4 * p);
+                acc = fmaf(fmaf(y[it * 16 + 4 * p], rs, nb), w.x, acc);
+                acc = fmaf(fmaf(y[it * 16 + 4 * p + 1], rs, nb), w.y, acc);
+                acc = fmaf(fmaf(y[it * 16 + 4 * p + 2], rs, nb), w.z, acc);
+                acc = fmaf(fmaf(y[it * 16 + 4 * p + 3], rs, nb), w.w, acc);
+            }
+        }
+        float* sp = reinterpret_cast<float*>(a_ring);
+        sp[cg * 128 + trow] = acc;
+        worker_bar();
+        if (cg == 0 && row_ok) {
+            const float sc = ((sp[trow] + sp[128 + trow]) + (sp[256 + trow] + sp[384 + trow])) + a.cf2[0];
+            const int l = grow / a.B, b = grow - l * a.B;
+            a.scores[(size_t)b * a.L + l] = sc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) fwd16_kernel(const __grid_constant__ FwdArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = smem + A_BYTES;
+    Bars* bars = reinterpret_cast<Bars*>(smem + A_BYTES + B_BYTES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    griddep_launch();
+    if (tid == 0) TL(0, 0);
+    const int i0 = blockIdx.x * 128;
+    const int n0 = blockIdx.y * a.bn0;
+    if (tid == 0) {
+        for (int q = 0; q < MAXF; ++q) {
+            for (int s = 0; s < A_STAGES; ++s) {
+                mbar_init(&bars->a_full[q][s], NW);
+                mbar_init(&bars->a_empty[q][s], 1);
+            }
+            for (int s = 0; s < B_MAX_STAGES; ++s) {
+                mbar_init(&bars->b_full[q][s], 1);
+                mbar_init(&bars->b_empty[q][s], 1);
+            }
+            mbar_init(&bars->accum[q], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == MMA_WARP) tmem_alloc(&bars->tmem_slot, 512);
+    griddep_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_slot;
+    if (tid == 0) TL(0, 1);
+
+    if (warp >= NW) {
+      regs_control();
+      if (warp == TMA_WARP) {
+        if (lane == 0)
+            for (int q = 0; q < a.nl; ++q) {
+                const int K = q == 0 ? a.K0 : a.N[q - 1];
+                const int bn = q == 0 ? a.bn0 : a.N[q];
+                if (q > 0) mbar_wait(&bars->accum[q - 1], 0);        // the previous layer's MMAs have left the ring
+                TL(2, 2 * q);
+                tma_layer(a.wimg[q], a.N[q], q == 0 ? n0 : 0, bn, 1, (K + 63) >> 6, b_ring, bars->b_full[q],
+                          bars->b_empty[q]);
+                TL(2, 2 * q + 1);
+            }
+    } else if (warp == MMA_WARP) {
+        if (lane == 0)
+            for (int q = 0; q < a.nl; ++q) {
+                const int K = q == 0 ? a.K0 : a.N[q - 1];
+                const int bn = q == 0 ? a.bn0 : a.N[q];
+                TL(1, 2 * q);
+                mma_layer<true>(tmem_base, K, bn, 1, a.dual[q], a_ring, b_ring, bars->a_full[q], bars->a_empty[q],
+                                bars->b_full[q], bars->b_empty[q], &bars->accum[q], 4 * q);
+                TL(1, 2 * q + 1);
+            }
+      }
+    } else {
+        regs_worker();
+        const int q4 = warp & 3, cg = warp >> 2;
+        const int trow = q4 * 32 + lane, grow = i0 + trow;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        if (tid == 0) TL(0, 2);
+        {
+            float2* st0 = (a.write_acts && blockIdx.y == 0) ? a.stats[0] : nullptr;
+            if (a.K0 <= 192)
+                produce_first<3>(a.X, a.docid, a.M, a.K0, i0, a_ring, bars->a_full[0], bars->a_empty[0], st0, tid, lane);
+            else
+                produce_first<0>(a.X, a.docid, a.M, a.K0, i0, a_ring, bars->a_full[0], bars->a_empty[0], st0, tid, lane);
+        }
+        if (tid == 0) TL(0, 3);
+        for (int q = 0; q < a.nl; ++q) {
+            const int bn = q == 0 ? a.bn0 : a.N[q];
+            mbar_wait(&bars->accum[q], 0);
+            __syncwarp();
+            tc_fence_after();
+            if (tid == 0) TL(0, 8 + 4 * q);
+            const int nq0 = q == 0 ? n0 : 0;
+            if (bn == 64) fwd_epilogue<1>(a, q, nq0, tlane, trow, cg, grow, lane, a_ring, bars);
+            else if (bn == 128) fwd_epilogue<2>(a, q, nq0, tlane, trow, cg, grow, lane, a_ring, bars);
+            else if (bn == 192) fwd_epilogue<3>(a, q, nq0, tlane, trow, cg, grow, lane, a_ring, bars);
+            else fwd_epilogue<4>(a, q, nq0, tlane, trow, cg, grow, lane, a_ring, bars);
+        }
+    }
+    if (tid == 0) TL(0, 4);
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward (data-gradient chain)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float pow2_scale_from_max(float mx, float& inv) {
+    // scale = 2^(10 - E), E = exponent of mx (so that mx * scale is in [2^10, 2^11)); exact powers of two
+    int eb = (int)((__float_as_uint(mx) >> 23) & 255u);
+    eb = eb < 24 ? 24 : (eb > 230 ? 230 : eb);
+    inv = __uint_as_float((uint32_t)(eb - 10) << 23);
+    return __uint_as_float((uint32_t)(264 - eb) << 23);
+}
+
+// tail shared by the final-layer step and every data-gradient epilogue: dz[] (this thread's 16 * NQ columns of dZ_q) ->
+// global (for the weight-gradient kernels), running max, and - when another data gradient follows - the row-scaled
+// fp16 A operand of that GEMM.  Returns the inverse row scale.
+template <int NQ>
+__device__ __forceinline__ float emit_dz(const BwdArgs& a, int q, float* dz, int trow, int cg, int grow, int lane,
+                                         uint8_t* a_ring, Bars* bars) {
+    const int N = a.N[q];
+    const bool row_ok = grow < a.M;
+    float mx = 0.f;
+#pragma unroll
+    for (int it = 0; it < NQ; ++it) {
+        if (!row_ok) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dz[it * 16 + i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, fabsf(dz[it * 16 + i]));
+        if (row_ok) {
+            float* dst = a.dZ[q] + (size_t)grow * N + it * 64 + cg * 16;
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+                *reinterpret_cast<float4*>(dst + 4 * p) = make_float4(dz[it * 16 + 4 * p], dz[it * 16 + 4 * p + 1],
+                                                                      dz[it * 16 + 4 * p + 2], dz[it * 16 + 4 * p + 3]);
+        }
+    }
+    {   // tensor-wide max for the weight-gradient operand scale: max is order independent, so the atomic is deterministic
+        const float wm = warp_max(mx);
+        if (lane == 0 && wm > 0.f) atomicMax(a.dzmax[q], __float_as_uint(wm));
+    }
+    if (q == 0) return 1.f;
+    float* part = reinterpret_cast<float*>(a_ring);
+    part[cg * 128 + trow] = mx;
+    worker_bar();
+    const float rmx = fmaxf(fmaxf(part[trow], part[128 + trow]), fmaxf(part[256 + trow], part[384 + trow]));
+    worker_bar();
+    float inv;
+    const float sc = pow2_scale_from_max(rmx, inv);
+    uint64_t* a_full = bars->a_full[q];
+    uint64_t* a_empty = bars->a_empty[q];
+#pragma unroll
+    for (int it = 0; it < NQ; ++it) {
+        const int s = it % A_STAGES;
+        mbar_wait(&a_empty[s], ((uint32_t)(it / A_STAGES) & 1u) ^ 1u);
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = dz[it * 16 + i] * sc;
+        store_split16(a_ring + s * A_STAGE, trow, cg, v);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[s]);
+    }
+    return inv;
+}
+
+// final layer backward for this thread's columns: dZ_last = LNbwd(ds * gamma_F w_F) . ELU'(y)
+template <int NQ>
+__device__ __forceinline__ float bwd_final(const BwdArgs& a, int trow, int cg, int grow, int lane, uint8_t* a_ring,
+                                           Bars* bars) {
+    const int q = a.nl - 1, N = a.N[q];
+    const bool row_ok = grow < a.M;
+    float y[16 * NQ];
+    float ds = 0.f;
+    float2 st = make_float2(0.f, 1.f);
+    if (row_ok) {
+        const int l = grow / a.B, b = grow - l * a.B;
+        ds = a.dscores[(size_t)b * a.L + l];
+        st = a.stats[a.nl][grow];
+    }
+    const float rs = st.y, nb = -st.x * st.y;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < NQ; ++it) {
+        const int col = it * 64 + cg * 16;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const float4 v = row_ok ? ld4(a.Y[q] + (size_t)grow * N + col + 4 * p) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 w = ldg4(a.wf2 + col + 4 * p);
+            y[it * 16 + 4 * p] = v.x; y[it * 16 + 4 * p + 1] = v.y; y[it * 16 + 4 * p + 2] = v.z; y[it * 16 + 4 * p + 3] = v.w;
+            s1 += (w.x + w.y) + (w.z + w.w);
+            s2 = fmaf(w.x, fmaf(v.x, rs, nb), s2);
+            s2 = fmaf(w.y, fmaf(v.y, rs, nb), s2);
+            s2 = fmaf(w.z, fmaf(v.z, rs, nb), s2);
+            s2 = fmaf(w.w, fmaf(v.w, rs, nb), s2);
+        }
+    }
+    float2* part = reinterpret_cast<float2*>(a_ring);
+    part[cg * 128 + trow] = make_float2(s1, s2);
+    worker_bar();
+    {
+        const float2 p0 = part[trow], p1 = part[128 + trow], p2 = part[256 + trow], p3 = part[384 + trow];
+        s1 = ((p0.x + p1.x) + (p2.x + p3.x)) / (float)N;
+        s2 = ((p0.y + p1.y) + (p2.y + p3.y)) / (float)N;
+    }
+    worker_bar();
+    const float f = ds * rs;
+#pragma unroll
+    for (int it = 0; it < NQ; ++it) {
+        const int col = it * 64 + cg * 16;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const float4 w = ldg4(a.wf2 + col + 4 * p);
+            const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float yv = y[it * 16 + 4 * p + i];
+                const float xh = fmaf(yv, rs, nb);
+                y[it * 16 + 4 * p + i] = f * (wv[i] - s1 - xh * s2) * elu_grad_from_out(yv);
+            }
+        }
+    }
+    return emit_dz<NQ>(a, q, y, trow, cg, grow, lane, a_ring, bars);
+}
+
+// epilogue of the data gradient of layer q: dXhat (tensor memory, NQ x 64 columns = width of layer q-1) ->
+// dZ_{q-1} = LNbwd(dXhat) . ELU'(Y_{q-1})
+template <int NQ>
+__device__ __forceinline__ float bwd_epilogue(const BwdArgs& a, int q, float inv_prev, uint32_t tlane, int trow, int cg,
+                                              int grow, int lane, uint8_t* a_ring, Bars* bars) {
+    const int N = a.N[q - 1];
+    const bool row_ok = grow < a.M;
+    const float2 st = row_ok ? a.stats[q][grow] : make_float2(0.f, 1.f);
+    const float rs = st.y, nb = -st.x * st.y;
+    const float unscale = inv_prev * W_UNSCALE;
+    const float* yrow = a.Y[q - 1] + (size_t)(row_ok ? grow : 0) * N;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < NQ; ++it) {
+        uint32_t r[16];
+        tmem_ld16_nowait(tlane + it * 64 + cg * 16, r);
+        float yv[16];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const float4 v = ld4(yrow + it * 64 + cg * 16 + 4 * p);
+            yv[4 * p] = v.x; yv[4 * p + 1] = v.y; yv[4 * p + 2] = v.z; yv[4 * p + 3] = v.w;
+        }
+        tmem_wait_ld16(r);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float d = __uint_as_float(r[i]) * unscale;
+            s1 += d;
+            s2 = fmaf(d, fmaf(yv[i], rs, nb), s2);
+        }
+    }
+    float2* part = reinterpret_cast<float2*>(a_ring);
+    part[cg * 128 + trow] = make_float2(s1, s2);
+    worker_bar();
+    {
+        const float2 p0 = part[trow], p1 = part[128 + trow], p2 = part[256 + trow], p3 = part[384 + trow];
+        s1 = ((p0.x + p1.x) + (p2.x + p3.x)) / (float)N;
+        s2 = ((p0.y + p1.y) + (p2.y + p3.y)) / (float)N;
+    }
+    worker_bar();
+    if (q - 1 == 0 || NQ > 4) {
+        // last tensor of the chain (no further data gradient; also the only place a tile wider than 256 occurs):
+        // stream dZ_0 to global without holding it
+        float mx = 0.f;
+#pragma unroll 1
+        for (int it = 0; it < NQ; ++it) {
+            uint32_t r[16];
+            tmem_ld16_nowait(tlane + it * 64 + cg * 16, r);
+            float yv[16];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const float4 v = ld4(yrow + it * 64 + cg * 16 + 4 * p);
+                yv[4 * p] = v.x; yv[4 * p + 1] = v.y; yv[4 * p + 2] = v.z; yv[4 * p + 3] = v.w;
+            }
+            tmem_wait_ld16(r);
+            float o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float d = __uint_as_float(r[i]) * unscale;
+                const float xh = fmaf(yv[i], rs, nb);
+                o[i] = row_ok ? rs * (d - s1 - xh * s2) * elu_grad_from_out(yv[i]) : 0.f;
+                mx = fmaxf(mx, fabsf(o[i]));
+            }
+            if (row_ok) {
+                float* dst = a.dZ[q - 1] + (size_t)grow * N + it * 64 + cg * 16;
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+                    *reinterpret_cast<float4*>(dst + 4 * p) = make_float4(o[4 * p], o[4 * p + 1], o[4 * p + 2], o[4 * p + 3]);
+            }
+        }
+        tc_fence_before();
+        const float wm = warp_max(mx);
+        if (lane == 0 && wm > 0.f) atomicMax(a.dzmax[q - 1], __float_as_uint(wm));
+        return 1.f;
+    } else {
+        constexpr int NR = NQ > 4 ? 1 : NQ;            // (NQ > 4 never reaches this branch)
+        float dz[16 * NR];
+#pragma unroll
+        for (int it = 0; it < NR; ++it) {
+            uint32_t r[16];
+            tmem_ld16_nowait(tlane + it * 64 + cg * 16, r);
+            float yv[16];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const float4 v = ld4(yrow + it * 64 + cg * 16 + 4 * p);
+                yv[4 * p] = v.x; yv[4 * p + 1] = v.y; yv[4 * p + 2] = v.z; yv[4 * p + 3] = v.w;
+            }
+            tmem_wait_ld16(r);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float d = __uint_as_float(r[i]) * unscale;
+                const float xh = fmaf(yv[i], rs, nb);
+                dz[it * 16 + i] = rs * (d - s1 - xh * s2) * elu_grad_from_out(yv[i]);
+            }
+        }
+        tc_fence_before();      // accumulator free for the next data gradient
+        return emit_dz<NR>(a, q - 1, dz, trow, cg, grow, lane, a_ring, bars);
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) bwd16_kernel(BwdArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = smem + A_BYTES;
+    Bars* bars = reinterpret_cast<Bars*>(smem + A_BYTES + B_BYTES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    griddep_launch();
+    const int i0 = blockIdx.x * 128;
+    if (tid == 0) {
+        for (int q = 0; q < MAXF; ++q) {
+            for (int s = 0; s < A_STAGES; ++s) {
+                mbar_init(&bars->a_full[q][s], NW);
+                mbar_init(&bars->a_empty[q][s], 1);
+            }
+            for (int s = 0; s < B_MAX_STAGES; ++s) {
+                mbar_init(&bars->b_full[q][s], 1);
+                mbar_init(&bars->b_empty[q][s], 1);
+            }
+            mbar_init(&bars->accum[q], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == MMA_WARP) tmem_alloc(&bars->tmem_slot, 512);
+    griddep_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_slot;
+
+    // data gradient of layer q (q = nl-1 .. 1): dXhat[128, Kq] = dZ_q[128, N_q] (W_q gamma_q), Kq = N[q-1];
+    // output tiles wider than 256 columns run as two column halves sharing every A chunk
+    if (warp >= NW) {
+      regs_control();
+      if (warp == TMA_WARP) {
+        if (lane == 0)
+            for (int q = a.nl - 1; q >= 1; --q) {
+                const int kq = a.N[q - 1];
+                const int nh = kq > 256 ? 2 : 1, bn = kq / nh;
+                if (q < a.nl - 1) mbar_wait(&bars->accum[q + 1], 0);
+                tma_layer(a.wd[q], kq, 0, bn, nh, a.N[q] >> 6, b_ring, bars->b_full[q], bars->b_empty[q]);
+            }
+    } else if (warp == MMA_WARP) {
+        if (lane == 0)
+            for (int q = a.nl - 1; q >= 1; --q) {
+                const int kq = a.N[q - 1];
+                const int nh = kq > 256 ? 2 : 1, bn = kq / nh;
+                mma_layer<false>(tmem_base, a.N[q], bn, nh, 0, a_ring, b_ring, bars->a_full[q], bars->a_empty[q],
+                                 bars->b_full[q], bars->b_empty[q], &bars->accum[q]);
+            }
+      }
+    } else {
+        regs_worker();
+        const int q4 = warp & 3, cg = warp >> 2;
+        const int trow = q4 * 32 + lane, grow = i0 + trow;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        float inv;
+        const int nqf = a.N[a.nl - 1] >> 6;
+        if (nqf == 1) inv = bwd_final<1>(a, trow, cg, grow, lane, a_ring, bars);
+        else if (nqf == 2) inv = bwd_final<2>(a, trow, cg, grow, lane, a_ring, bars);
+        else if (nqf == 3) inv = bwd_final<3>(a, trow, cg, grow, lane, a_ring, bars);
+        else inv = bwd_final<4>(a, trow, cg, grow, lane, a_ring, bars);
+        for (int q = a.nl - 1; q >= 1; --q) {
+            mbar_wait(&bars->accum[q], 0);
+            __syncwarp();
+            tc_fence_after();
+            const int nq = a.N[q - 1] >> 6;
+            if (nq == 1) inv = bwd_epilogue<1>(a, q, inv, tlane, trow, cg, grow, lane, a_ring, bars);
+            else if (nq == 2) inv = bwd_epilogue<2>(a, q, inv, tlane, trow, cg, grow, lane, a_ring, bars);
+            else if (nq == 3) inv = bwd_epilogue<3>(a, q, inv, tlane, trow, cg, grow, lane, a_ring, bars);
+            else if (nq == 4) inv = bwd_epilogue<4>(a, q, inv, tlane, trow, cg, grow, lane, a_ring, bars);
+            else inv = bwd_epilogue<8>(a, q, inv, tlane, trow, cg, grow, lane, a_ring, bars);
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight gradients: G_j[n, k] = sum_m dZ_j[m, n] xhat_j[m, k] (+ db[n] = sum_m dZ_j[m, n]) for ALL hidden layers, one launch
+// ---------------------------------------------------------------------------------------------------------------
+// Both operands are "MN-major" for the tensor core (the contraction index m is the slow one in memory), so the row-major
+// activations are converted in place: a CTA owns one 128(n) x bn(k) tile of one layer and one slice of the rows; per
+// 64-row chunk its 512 worker threads load dZ and the layer input (coalesced 16-byte loads; thread = one row, every 8th
+// float4), normalise / scale, split into fp16 hi + lo and store them into 128B-swizzled MN-major tiles (8-row x 128-byte
+// atoms, LBO = next 64 MN elements, SBO = next 8 rows); warp 16 issues the three products per K = 16 rows into a main
+// and a correction accumulator; the epilogue writes the partial plane that wgrad_finalize_kernel (mlp.cu) reduces in
+// fixed order.  The bias gradient rides along as register column sums of the dZ loads.
+template <typename KernelT>
+static int set_smem(KernelT kern, const char* name) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    UB_CHECK(e == cudaSuccess, 100, "%s attribute: %s", name, cudaGetErrorString(e));
+    return 0;
+}
+
+constexpr int WG_STAGES = 2;
+constexpr int WG_A_HALF = 64 * 128 * 2;                // one (hi | lo) A tile: 64 rows x 128 n fp16 = 16 KB
+
+struct WgBars {
+    uint64_t full[WG_STAGES];
+    uint64_t empty[WG_STAGES];
+    uint64_t accum;
+    uint32_t tmem_slot;
+};
+
+// byte offset of fp16 element (row m of the contraction chunk, MN index x) in an MN-major tile with `atoms` 64-wide atoms
+__device__ __forceinline__ uint32_t mn_off(uint32_t m, uint32_t x, uint32_t atoms) {
+    return (m >> 3) * (atoms * 1024u) + (x >> 6) * 1024u + (m & 7u) * 128u + ((((x & 63u) >> 3) ^ (m & 7u)) << 4) +
+           (x & 7u) * 2u;
+}
+
+template <int BN>
+__device__ __forceinline__ void wgrad_worker(const WgLayer& L, int n0, int k0, int r_begin, int r_end, float sc,
+                                             uint8_t* ring, WgBars* bars, int tid, int lane, float* csum) {
+    constexpr int ATOMS_B = BN / 64;
+    constexpr int STAGE = 2 * WG_A_HALF + 2 * BN * 128;
+    constexpr int EB = BN / 32;                          // float4 per thread per chunk of the B operand
+    const int ml = tid >> 3, r8 = tid & 7;
+    const int n_chunks = (r_end - r_begin + 63) >> 6;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 av[4], bv[EB], av_n[4], bv_n[EB];
+    float nb = 0.f, rs = 0.f, nb_n = 0.f, rs_n = 0.f;
+    auto load_chunk = [&](int it, float4* a4, float4* b4, float& nbo, float& rso) {
+        const int m = r_begin + it * 64 + ml;
+        const bool ok = m < r_end;
+        const float* zrow = L.dZ + (size_t)m * L.N + n0;
+        const float* xrow = L.X + (size_t)(ok ? (L.docid ? L.docid[m] : m) : 0) * L.K + k0;
+        const float2 st = ok ? L.stats[m] : make_float2(0.f, 0.f);
+        rso = st.y;
+        nbo = -st.x * st.y;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int n = (r8 + 8 * e) * 4;
+            a4[e] = (ok && n0 + n < L.N) ? ld4(zrow + n) : zero4;
+        }
+#pragma unroll
+        for (int e = 0; e < EB; ++e) {
+            const int k = (r8 + 8 * e) * 4;
+            b4[e] = (ok && k0 + k < L.K) ? ld4(xrow + k) : make_float4(st.x, st.x, st.x, st.x);   // -> xhat = 0
+        }
+    };
+    if (n_chunks > 0) load_chunk(0, av, bv, nb, rs);
+    for (int it = 0; it < n_chunks; ++it) {
+        const int s = it % WG_STAGES;
+        const uint32_t ph = (uint32_t)(it / WG_STAGES) & 1u;
+        if (it + 1 < n_chunks) load_chunk(it + 1, av_n, bv_n, nb_n, rs_n);
+        mbar_wait(&bars->empty[s], ph ^ 1u);
+        uint8_t* a_hi = ring + s * STAGE;
+        uint8_t* b_hi = a_hi + 2 * WG_A_HALF;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float4 v = av[e];
+            csum[4 * e] += v.x; csum[4 * e + 1] += v.y; csum[4 * e + 2] += v.z; csum[4 * e + 3] += v.w;
+            uint32_t h0, h1, l0, l1;
+            split_h2(v.x * sc, v.y * sc, h0, l0);
+            split_h2(v.z * sc, v.w * sc, h1, l1);
+            const uint32_t off = mn_off((uint32_t)ml, (uint32_t)((r8 + 8 * e) * 4), 2);
+            *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(a_hi + WG_A_HALF + off) = make_uint2(l0, l1);
+        }
+#pragma unroll
+        for (int e = 0; e < EB; ++e) {
+            const float4 v = bv[e];
+            uint32_t h0, h1, l0, l1;
+            split_h2(fmaf(v.x, rs, nb), fmaf(v.y, rs, nb), h0, l0);
+            split_h2(fmaf(v.z, rs, nb), fmaf(v.w, rs, nb), h1, l1);
+            const uint32_t off = mn_off((uint32_t)ml, (uint32_t)((r8 + 8 * e) * 4), ATOMS_B);
+            *reinterpret_cast<uint2*>(b_hi + off) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(b_hi + BN * 128 + off) = make_uint2(l0, l1);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->full[s]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) av[e] = av_n[e];
+#pragma unroll
+        for (int e = 0; e < EB; ++e) bv[e] = bv_n[e];
+        nb = nb_n;
+        rs = rs_n;
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) wgrad16_kernel(WgArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = smem;
+    WgBars* bars = reinterpret_cast<WgBars*>(smem + A_BYTES + B_BYTES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    griddep_launch();
+    // which layer / tile / row slice
+    int li = 0;
+    for (int i = 1; i < a.n; ++i)
+        if ((int)blockIdx.x >= a.l[i].cta_begin) li = i;
+    const WgLayer& L = a.l[li];
+    const int local = blockIdx.x - L.cta_begin;
+    const int tiles = L.m_tiles * L.col_tiles;
+    const int split = local / tiles, tile = local - split * tiles;
+    const int mt = tile / L.col_tiles, ct = tile - mt * L.col_tiles;
+    const int n0 = mt * 128, k0 = ct * L.bn;
+    const int r_begin = split * L.rows_per_split;
+    const int r_end = min(a.M, r_begin + L.rows_per_split);
+    const int n_chunks = (r_end - r_begin + 63) >> 6;
+    const int kvalid = min(L.bn, L.K - k0);
+    const int n_mma = (kvalid + 15) & ~15;
+
+    if (tid == 0) {
+        for (int s = 0; s < WG_STAGES; ++s) {
+            mbar_init(&bars->full[s], NW);
+            mbar_init(&bars->empty[s], 1);
+        }
+        mbar_init(&bars->accum, 1);
+        fence_mbar_init();
+    }
+    if (warp == MMA_WARP) tmem_alloc(&bars->tmem_slot, 512);
+    griddep_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_slot;
+
+    if (warp >= NW) {
+        regs_control();
+        if (warp == MMA_WARP && lane == 0) {
+            const int stage = 2 * WG_A_HALF + 2 * L.bn * 128;
+            const uint32_t sbo_b = (uint32_t)(L.bn / 64) * 1024u;
+            const uint32_t idesc = make_idesc_f16(n_mma, 1, 1);
+            const uint32_t ring_base = smem_u32(ring);
+            for (int it = 0; it < n_chunks; ++it) {
+                const int s = it % WG_STAGES;
+                mbar_wait(&bars->full[s], (uint32_t)(it / WG_STAGES) & 1u);
+                tc_fence_after();
+                // MN-major tiles: LBO = next 64 MN elements (1024 B), SBO = next 8 contraction rows
+                const uint32_t a_hi = ring_base + s * stage, a_lo = a_hi + WG_A_HALF;
+                const uint32_t b_hi = a_hi + 2 * WG_A_HALF, b_lo = b_hi + (uint32_t)L.bn * 128u;
+                const int rem = r_end - (r_begin + it * 64);
+                const int nk = rem >= 64 ? 4 : (rem + 15) >> 4;
+                for (int k = 0; k < nk; ++k) {
+                    // one K = 16 step = two 8-row groups
+                    const uint64_t dah = make_smem_desc(a_hi + k * 4096, 1024, 2048), dal = make_smem_desc(a_lo + k * 4096, 1024, 2048);
+                    const uint64_t dbh = make_smem_desc(b_hi + k * 2 * sbo_b, 1024, sbo_b), dbl = make_smem_desc(b_lo + k * 2 * sbo_b, 1024, sbo_b);
+                    const uint32_t acc = (it | k) != 0 ? 1u : 0u;
+                    mma_f16_sync(tmem_base + 256, dal, dbh, idesc, acc);
+                    mma_f16_sync(tmem_base + 256, dah, dbl, idesc, 1u);
+                    mma_f16_sync(tmem_base, dah, dbh, idesc, acc);
+                }
+                mma_commit(&bars->empty[s]);
+            }
+            mma_commit(&bars->accum);
+        }
+    } else {
+        regs_worker();
+        float inv;
+        const float sc = pow2_scale_from_max(__uint_as_float(*L.dzmax), inv);
+        float csum[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) csum[i] = 0.f;
+        if (L.bn == 64) wgrad_worker<64>(L, n0, k0, r_begin, r_end, sc, ring, bars, tid, lane, csum);
+        else if (L.bn == 128) wgrad_worker<128>(L, n0, k0, r_begin, r_end, sc, ring, bars, tid, lane, csum);
+        else if (L.bn == 192) wgrad_worker<192>(L, n0, k0, r_begin, r_end, sc, ring, bars, tid, lane, csum);
+        else wgrad_worker<256>(L, n0, k0, r_begin, r_end, sc, ring, bars, tid, lane, csum);
+        // ---- epilogue: accumulator (main + correction) * 1/scale -> partial plane; thread = row n, 16-column slices ----
+        mbar_wait(&bars->accum, 0);
+        __syncwarp();
+        tc_fence_after();
+        float* plane = L.out + (size_t)split * L.N * L.ldp;
+        if (ct == 0) {
+            // bias-gradient partial: the 64 threads with the same r8 hold disjoint rows of the same 16 columns
+            float* cs = reinterpret_cast<float*>(ring);           // [64][128]; the ring is idle now
+            const int ml = tid >> 3, r8 = tid & 7;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                *reinterpret_cast<float4*>(cs + ml * 128 + (r8 + 8 * e) * 4) =
+                    make_float4(csum[4 * e], csum[4 * e + 1], csum[4 * e + 2], csum[4 * e + 3]);
+            worker_bar();
+            if (tid < 128 && n0 + tid < L.N) {
+                float t = 0.f;
+#pragma unroll 8
+                for (int r = 0; r < 64; ++r) t += cs[r * 128 + tid];
+                float* orow = plane + (size_t)(n0 + tid) * L.ldp;
+                orow[L.K] = t;
+                for (int k = L.K + 1; k < L.ldp; ++k) orow[k] = 0.f;
+            }
+        }
+        if (n_chunks > 0) {
+            const int q4 = warp & 3, cg = warp >> 2;
+            const int nrow = n0 + q4 * 32 + lane;
+            const uint32_t tlane = tmem_base + ((uint32_t)(q4 * 32) << 16);
+            for (int c0 = cg * 16; c0 < kvalid; c0 += 64) {
+                uint32_t r[16], rc[16];
+                tmem_ld16_nowait(tlane + c0, r);
+                tmem_ld16_nowait(tlane + 256 + c0, rc);
+                tmem_wait_ld16(rc);
+                tmem_wait_ld16(r);
+                if (nrow < L.N) {
+                    float* dst = plane + (size_t)nrow * L.ldp + k0 + c0;
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+                        if (c0 + 4 * p < kvalid)
+                            *reinterpret_cast<float4*>(dst + 4 * p) =
+                                make_float4((__uint_as_float(r[4 * p]) + __uint_as_float(rc[4 * p])) * inv,
+                                            (__uint_as_float(r[4 * p + 1]) + __uint_as_float(rc[4 * p + 1])) * inv,
+                                            (__uint_as_float(r[4 * p + 2]) + __uint_as_float(rc[4 * p + 2])) * inv,
+                                            (__uint_as_float(r[4 * p + 3]) + __uint_as_float(rc[4 * p + 3])) * inv);
+                }
+            }
+        } else {
+            // empty row slice (cannot happen with wgrad_plan, kept for safety): zero plane tile
+            for (int idx = tid; idx < 128 * (kvalid / 4); idx += NWT) {
+                const int r = idx / (kvalid / 4), c4 = idx - r * (kvalid / 4);
+                if (n0 + r < L.N)
+                    *reinterpret_cast<float4*>(plane + (size_t)(n0 + r) * L.ldp + k0 + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+void wgrad_plan(WgArgs* a, int sm_budget) {
+    // cost of one CTA of layer i per contraction row ~ producer work ~ (128 + bn) columns
+    double cost[UB200_MAX_LAYERS], total = 0.0;
+    int tiles[UB200_MAX_LAYERS];
+    for (int i = 0; i < a->n; ++i) {
+        WgLayer& L = a->l[i];
+        L.bn = L.K > 192 ? 256 : (L.K > 128 ? 192 : (L.K > 64 ? 128 : 64));
+        L.col_tiles = (L.K + L.bn - 1) / L.bn;
+        L.m_tiles = (L.N + 127) / 128;
+        tiles[i] = L.m_tiles * L.col_tiles;
+        cost[i] = (double)tiles[i] * (128 + L.bn);
+        total += cost[i];
+    }
+    int begin = 0;
+    const int max_splits = (a->M + 127) / 128;          // >= 128 rows per split
+    const int min_splits = (a->M + 2047) / 2048;        // <= 2048 rows per accumulator
+    for (int i = 0; i < a->n; ++i) {
+        WgLayer& L = a->l[i];
+        int s = (int)(sm_budget * cost[i] / total) / tiles[i];
+        if (s > max_splits) s = max_splits;
+        if (s < min_splits) s = min_splits;
+        if (s < 1) s = 1;
+        int rps = (a->M + s - 1) / s;
+        rps = (rps + 63) / 64 * 64;
+        L.rows_per_split = rps;
+        L.splits = (a->M + rps - 1) / rps;
+        L.cta_begin = begin;
+        begin += L.splits * tiles[i];
+    }
+    a->total_ctas = begin;
+}
+
+int wgrad(const WgArgs& a, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        if (int rc = set_smem(wgrad16_kernel, "wgrad16_kernel")) return rc;
+        configured = true;
+    }
+    launch_k(wgrad16_kernel, dim3(a.total_ctas), NTHREADS, SMEM_BYTES, st, a);
+    UB_LAUNCH_CHECK("wgrad16_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight images (once per step)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_hl(uint16_t* img, size_t tile_hi, size_t tile_stride, uint32_t row, uint32_t kk,
+                                         float w) {
+    const __half h = __float2half_rn(w);
+    const __half l = __float2half_rn(w - __half2float(h));
+    const size_t o = (swz128(row, kk >> 3) >> 1) + (kk & 7u);
+    img[tile_hi + o] = __half_as_ushort(h);
+    img[tile_hi + tile_stride + o] = __half_as_ushort(l);
+}
+
+__global__ void __launch_bounds__(256) prep16_kernel(PrepArgs t) {
+    griddep_launch();
+    griddep_wait();
+    const int j = blockIdx.y;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    if (j == t.n) {
+        // final layer fold: wf2 = gamma_F w_F, cf2 = c_F + beta_F . w_F (one warp, fixed order)
+        for (int k = gtid; k < t.KF; k += gsz) t.wf2[k] = t.gF[k] * t.wF[k];
+        if (blockIdx.x == 0 && threadIdx.x < 32) {
+            float s = 0.f;
+            for (int k = threadIdx.x; k < t.KF; k += 32) s = fmaf(t.bF[k], t.wF[k], s);
+            s = warp_sum(s);
+            if (threadIdx.x == 0) t.cf2[0] = t.cF[0] + s;
+        }
+        return;
+    }
+    const int K = t.K[j], N = t.N[j];
+    const float* W = t.W[j];
+    const float* gamma = t.gamma[j];
+    const int kch = (K + 63) >> 6, Kpad = kch * 64;
+    const size_t nf = (size_t)N * Kpad;
+    const size_t nd = t.wd[j] ? (size_t)N * K : 0;
+    for (size_t i = gtid; i < nf + nd; i += gsz) {
+        if (i < nf) {
+            const int n = (int)(i / Kpad), k = (int)(i % Kpad);
+            const float w = k < K ? W[(size_t)n * K + k] * gamma[k] * W_SCALE : 0.f;
+            store_hl(t.wf[j], (size_t)(k >> 6) * 2 * N * 64, (size_t)N * 64, (uint32_t)n, (uint32_t)(k & 63), w);
+        } else {
+            const size_t q = i - nf;
+            const int n = (int)(q / K), k = (int)(q % K);
+            const float w = W[(size_t)n * K + k] * gamma[k] * W_SCALE;
+            store_hl(t.wd[j], (size_t)(n >> 6) * 2 * K * 64, (size_t)K * 64, (uint32_t)k, (uint32_t)(n & 63), w);
+        }
+    }
+    // bias2[n] = b[n] + sum_k W[n, k] beta[k]: one warp per n, lane-strided partials + butterfly (fixed order)
+    const int gw = gtid >> 5, nw = gsz >> 5, ln = threadIdx.x & 31;
+    for (int n = gw; n < N; n += nw) {
+        float s = 0.f;
+        for (int k = ln; k < K; k += 32) s = fmaf(W[(size_t)n * K + k], t.beta[j][k], s);
+        s = warp_sum(s);
+        if (ln == 0) t.bias2[j][n] = t.bias[j][n] + s;
+    }
+}
+
+}  // namespace f16
+}  // namespace ub200
+#ifdef UB200_F16_TIMELINE
+extern "C" UB200_API int ub200_f16_timeline(long long* out192) {
+    return (int)cudaMemcpyFromSymbol(out192, ub200::f16::g_tl, sizeof(long long) * 192);
+}
+#endif
+namespace ub200 {
+namespace f16 {
+
+int make_tmap_f32(CUtensorMap* m, const float* base, size_t rows, size_t cols) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)cols * sizeof(float)};
+    const cuuint32_t box[2] = {32, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = cuTensorMapEncodeTiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride,
+                                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    UB_CHECK(r == CUDA_SUCCESS, 101, "cuTensorMapEncodeTiled failed (%d) for [%zu, %zu] at %p", (int)r, rows, cols,
+             (const void*)base);
+    return 0;
+}
+
+size_t prep_bytes_wf(int K, int N) { return (size_t)((K + 63) / 64) * 2 * N * 64 * sizeof(uint16_t); }
+size_t prep_bytes_wd(int K, int N) { return (size_t)((N + 63) / 64) * 2 * K * 64 * sizeof(uint16_t); }
+
+int prep(const PrepArgs& a, cudaStream_t st) {
+    int max_elems = 1;
+    for (int j = 0; j < a.n; ++j) {
+        const int e = a.N[j] * ((a.K[j] + 63) / 64 * 64) + (a.wd[j] ? a.N[j] * a.K[j] : 0);
+        max_elems = e > max_elems ? e : max_elems;
+    }
+    int bx = (max_elems + 256 * 4 - 1) / (256 * 4);
+    if (bx > 2 * kNumSMs) bx = 2 * kNumSMs;
+    if (bx < 1) bx = 1;
+    launch_k(prep16_kernel, dim3(bx, a.n + 1), 256, 0, st, a);
+    UB_LAUNCH_CHECK("prep16_kernel");
+    return 0;
+}
+
+bool fwd_shape_ok(int K0, const int* N, int nl) {
+    if (nl < 1 || nl > MAXF || K0 % 4 != 0 || K0 < 4) return false;
+    for (int q = 0; q < nl; ++q)
+        if (N[q] % 64 != 0 || N[q] > 256) return false;
+    return true;
+}
+
+int fwd(const FwdArgs& a, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        if (int rc = set_smem(fwd16_kernel, "fwd16_kernel")) return rc;
+        configured = true;
+    }
+    const int ytiles = a.N[0] / a.bn0;
+    launch_k(fwd16_kernel, dim3((a.M + 127) / 128, ytiles), NTHREADS, SMEM_BYTES, st, a);
+    UB_LAUNCH_CHECK("fwd16_kernel");
+    return 0;
+}
+
+bool bwd_shape_ok(const int* N, int nl) {
+    if (nl < 1 || nl > MAXF) return false;
+    for (int q = 0; q < nl; ++q) {
+        if (N[q] % 64 != 0) return false;
+        if (N[q] > (q == 0 ? 512 : 256)) return false;      // only the chain's last output may be wider than 256
+        if (q == 0 && N[q] > 256 && N[q] != 512) return false;
+    }
+    return true;
+}
+
+int bwd_grid(int M) { return (M + 127) / 128; }
+
+int bwd(const BwdArgs& a, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        if (int rc = set_smem(bwd16_kernel, "bwd16_kernel")) return rc;
+        configured = true;
+    }
+    launch_k(bwd16_kernel, dim3(bwd_grid(a.M)), NTHREADS, SMEM_BYTES, st, a);
+    UB_LAUNCH_CHECK("bwd16_kernel");
+    return 0;
+}
+
+}  // namespace f16
+}  // namespace ub200
