@@ -61,5 +61,24 @@ for c in range(12):
     if t[1, 16 + 2 * c] > 0:
         ev.append((us(t[1, 16 + 2 * c]), "mma:   chunk L%d.%d operands ready" % (c // 4, c % 4)))
         ev.append((us(t[1, 17 + 2 * c]), "mma:   chunk L%d.%d issued" % (c // 4, c % 4)))
+if "--wgrad" in sys.argv:
+    dsc = torch.randn(B, L, device="cuda")
+    for rep in range(3):
+        eng.forward(feats, docid, L, B, training=True)
+        eng.backward(feats, docid, L, B, dsc)
+        torch.cuda.synchronize()
+    lib.ub200_f16_timeline(buf)
+    t = np.array(list(buf), dtype=np.int64).reshape(3, 64)
+    t0 = t[0, 38]
+    ev = [(us(t[0, 38]), "wgrad worker: start"), (us(t[0, 39]), "wgrad worker: setup done"),
+          (us(t[0, 54]), "wgrad worker: all chunks produced"), (us(t[0, 55]), "wgrad worker: accumulator ready"),
+          (us(t[0, 56]), "wgrad worker: column sums written"), (us(t[0, 57]), "wgrad worker: end")]
+    for c in range(6):
+        if t[0, 40 + 2 * c] > t0:
+            ev.append((us(t[0, 40 + 2 * c]), "wgrad worker: chunk %d slot free, loads of chunk %d issued" % (c, c + 1)))
+            ev.append((us(t[0, 41 + 2 * c]), "wgrad worker: chunk %d stored" % c))
+        if t[1, 40 + 2 * c] > t0:
+            ev.append((us(t[1, 40 + 2 * c]), "wgrad mma: chunk %d operands ready" % c))
+            ev.append((us(t[1, 41 + 2 * c]), "wgrad mma: chunk %d issued" % c))
 for tt, n in sorted(ev):
     print("%8.2f us  %s" % (tt, n))

@@ -258,6 +258,7 @@ static int prep_f16_weights(const LayerDims& d, const MlpWorkspace& w, const flo
     t.KF = d.K[nh];
     t.wf2 = w.wf2;
     t.cf2 = w.wf2 + d.K[nh];
+    t.dzmax = training ? w.dzmax : nullptr;
     return f16::prep(t, st);
 }
 
@@ -968,6 +969,8 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
             b.wd[q] = w.wd16[q];
             b.dZ[q] = w.dz16[q];
             b.dzmax[q] = w.dzmax + q;
+            if (int rc = f16::make_tmap_f32(&b.ymap[q], w.Y[q], (size_t)M, (size_t)d.N[q])) return rc;
+            if (int rc = f16::make_tmap_f32(&b.dzmap[q], w.dz16[q], (size_t)M, (size_t)d.N[q])) return rc;
         }
         for (int q = 0; q <= nh; ++q) b.stats[q] = w.stats[q];
         if (int rc = f16::bwd(b, st)) return rc;
@@ -997,7 +1000,6 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
             UB_LAUNCH_CHECK("wgrad_finalize_kernel");
             if (j > 0) branch_done(j);
         }
-        cudaMemsetAsync(w.dzmax, 0, sizeof(unsigned int) * UB200_MAX_LAYERS, st);     // running maxima of the next step
         wait_branch(nl - 1);
         for (int j = 1; j < nl - 1; ++j) wait_branch(j);
         return 0;

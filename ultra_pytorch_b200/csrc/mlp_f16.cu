@@ -31,7 +31,7 @@ using namespace ub200::tc;
 
 constexpr int NW = 16;                        // worker warps
 constexpr int NWT = NW * 32;                  // 512 worker threads
-constexpr int MMA_WARP = 16, TMA_WARP = 17;
+constexpr int MMA_WARP = 16, TMA_WARP = 17, Y_WARP = 18;
 constexpr int NTHREADS = 20 * 32;          // 4 worker warpgroups + 1 control warpgroup (warps 18, 19 idle)
 constexpr int A_STAGES = 3;
 constexpr int A_HALF = 128 * 128;             // one (hi | lo) A tile: 128 rows x 64 fp16
@@ -67,6 +67,8 @@ struct Bars {
     uint64_t b_full[MAXF][B_MAX_STAGES];
     uint64_t b_empty[MAXF][B_MAX_STAGES];
     uint64_t accum[MAXF];
+    uint64_t y_full[2];           // backward: activation chunks staged by the loader warp
+    uint64_t y_empty[2];
     uint32_t tmem_slot;
 };
 static_assert(sizeof(Bars) <= CTL_BYTES, "control block too large");
@@ -559,14 +561,52 @@ __device__ __forceinline__ float pow2_scale_from_max(float mx, float& inv) {
     return __uint_as_float((uint32_t)(264 - eb) << 23);
 }
 
+// Global traffic of the backward chain goes through the TMA engine: the activations Y_q arrive as 128-row x 64-column
+// chunks in shared memory (tensor loads issued by warp 18, two buffers, y_full / y_empty mbarriers) and the gradients
+// dZ_q leave through staging buffers + tensor stores, both in the 128B-swizzled box layout, so that the thread-per-row
+// accesses the TMEM lane mapping forces are shared-memory accesses at the minimum of 4 wavefronts per instruction.
+// Thread-per-row GLOBAL accesses touch 32 lines per instruction: ~650 KB of them per 128-row tile made the LSU the
+// limiter of this kernel (47 us per tile at config 2 against ~4 us of tensor-core work).
+struct YPipe {
+    uint64_t* full;      // [2]
+    uint64_t* empty;     // [2]
+    uint32_t count;      // chunks consumed so far (same sequence as the loader's)
+};
+
+// this thread's 16 columns (cg) of chunk `buf` row `trow`, from the swizzled box layout
+__device__ __forceinline__ void lds_chunk16(const uint8_t* buf, int trow, int cg, float* v) {
+    const uint8_t* base = buf + (cg >> 1) * 16384 + trow * 128;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const float4 t = *reinterpret_cast<const float4*>(base + ((((cg & 1) * 4 + p) ^ (trow & 7)) << 4));
+        v[4 * p] = t.x; v[4 * p + 1] = t.y; v[4 * p + 2] = t.z; v[4 * p + 3] = t.w;
+    }
+}
+__device__ __forceinline__ void sts_chunk16(uint8_t* buf, int trow, int cg, const float* v) {
+    uint8_t* base = buf + (cg >> 1) * 16384 + trow * 128;
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+        *reinterpret_cast<float4*>(base + ((((cg & 1) * 4 + p) ^ (trow & 7)) << 4)) =
+            make_float4(v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]);
+}
+// next Y chunk of the loader's sequence -> v[16]; releases the buffer
+__device__ __forceinline__ void take_y_chunk(YPipe& yp, const uint8_t* ybase, int trow, int cg, int lane, float* v) {
+    const uint32_t b = yp.count & 1u;
+    mbar_wait(&yp.full[b], (yp.count >> 1) & 1u);
+    lds_chunk16(ybase + b * A_STAGE, trow, cg, v);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&yp.empty[b]);
+    ++yp.count;
+}
+
 // tail shared by the final-layer step and every data-gradient epilogue: dz[] (this thread's 16 * NQ columns of dZ_q) ->
-// global (for the weight-gradient kernels), running max, and - when another data gradient follows - the row-scaled
-// fp16 A operand of that GEMM.  Returns the inverse row scale.
+// global (for the weight-gradient kernel; staged, tensor stores), running max, and - when another data gradient
+// follows - the row-scaled fp16 A operand of that GEMM.  Returns the inverse row scale.  The A ring is idle here.
 template <int NQ>
 __device__ __forceinline__ float emit_dz(const BwdArgs& a, int q, float* dz, int trow, int cg, int grow, int lane,
                                          uint8_t* a_ring, Bars* bars) {
-    const int N = a.N[q];
     const bool row_ok = grow < a.M;
+    const int i0 = grow - trow;
     float mx = 0.f;
 #pragma unroll
     for (int it = 0; it < NQ; ++it) {
@@ -576,22 +616,26 @@ __device__ __forceinline__ float emit_dz(const BwdArgs& a, int q, float* dz, int
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) mx = fmaxf(mx, fabsf(dz[it * 16 + i]));
-        if (row_ok) {
-            float* dst = a.dZ[q] + (size_t)grow * N + it * 64 + cg * 16;
-#pragma unroll
-            for (int p = 0; p < 4; ++p)
-                *reinterpret_cast<float4*>(dst + 4 * p) = make_float4(dz[it * 16 + 4 * p], dz[it * 16 + 4 * p + 1],
-                                                                      dz[it * 16 + 4 * p + 2], dz[it * 16 + 4 * p + 3]);
+        sts_chunk16(a_ring + (it & 1) * A_STAGE, trow, cg, dz + it * 16);
+        fence_proxy_async();
+        if (threadIdx.x == 0) bulk_wait_read0();          // the store issued from the buffer written next has drained
+        worker_bar();
+        if (threadIdx.x == 0) {
+            const uint8_t* src = a_ring + (it & 1) * A_STAGE;
+            tma_store_2d(&a.dzmap[q], src, it * 64, i0);
+            tma_store_2d(&a.dzmap[q], src + 16384, it * 64 + 32, i0);
+            bulk_commit();
         }
     }
+    if (threadIdx.x == 0) bulk_wait_read0();
     {   // tensor-wide max for the weight-gradient operand scale: max is order independent, so the atomic is deterministic
         const float wm = warp_max(mx);
         if (lane == 0 && wm > 0.f) atomicMax(a.dzmax[q], __float_as_uint(wm));
     }
     if (q == 0) return 1.f;
-    float* part = reinterpret_cast<float*>(a_ring);
+    float* part = reinterpret_cast<float*>(a_ring + 2 * A_STAGE);
     part[cg * 128 + trow] = mx;
-    worker_bar();
+    worker_bar();                                         // (also: the staging buffers have drained, see above)
     const float rmx = fmaxf(fmaxf(part[trow], part[128 + trow]), fmaxf(part[256 + trow], part[384 + trow]));
     worker_bar();
     float inv;
@@ -615,8 +659,8 @@ __device__ __forceinline__ float emit_dz(const BwdArgs& a, int q, float* dz, int
 
 // final layer backward for this thread's columns: dZ_last = LNbwd(ds * gamma_F w_F) . ELU'(y)
 template <int NQ>
-__device__ __forceinline__ float bwd_final(const BwdArgs& a, int trow, int cg, int grow, int lane, uint8_t* a_ring,
-                                           Bars* bars) {
+__device__ __forceinline__ float bwd_final(const BwdArgs& a, YPipe& yp, int trow, int cg, int grow, int lane,
+                                           uint8_t* a_ring, Bars* bars) {
     const int q = a.nl - 1, N = a.N[q];
     const bool row_ok = grow < a.M;
     float y[16 * NQ];
@@ -631,20 +675,19 @@ __device__ __forceinline__ float bwd_final(const BwdArgs& a, int trow, int cg, i
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int it = 0; it < NQ; ++it) {
+        take_y_chunk(yp, a_ring, trow, cg, lane, y + it * 16);
         const int col = it * 64 + cg * 16;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            const float4 v = row_ok ? ld4(a.Y[q] + (size_t)grow * N + col + 4 * p) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 w = ldg4(a.wf2 + col + 4 * p);
-            y[it * 16 + 4 * p] = v.x; y[it * 16 + 4 * p + 1] = v.y; y[it * 16 + 4 * p + 2] = v.z; y[it * 16 + 4 * p + 3] = v.w;
             s1 += (w.x + w.y) + (w.z + w.w);
-            s2 = fmaf(w.x, fmaf(v.x, rs, nb), s2);
-            s2 = fmaf(w.y, fmaf(v.y, rs, nb), s2);
-            s2 = fmaf(w.z, fmaf(v.z, rs, nb), s2);
-            s2 = fmaf(w.w, fmaf(v.w, rs, nb), s2);
+            s2 = fmaf(w.x, fmaf(y[it * 16 + 4 * p], rs, nb), s2);
+            s2 = fmaf(w.y, fmaf(y[it * 16 + 4 * p + 1], rs, nb), s2);
+            s2 = fmaf(w.z, fmaf(y[it * 16 + 4 * p + 2], rs, nb), s2);
+            s2 = fmaf(w.w, fmaf(y[it * 16 + 4 * p + 3], rs, nb), s2);
         }
     }
-    float2* part = reinterpret_cast<float2*>(a_ring);
+    float2* part = reinterpret_cast<float2*>(a_ring + 2 * A_STAGE);
     part[cg * 128 + trow] = make_float2(s1, s2);
     worker_bar();
     {
@@ -673,27 +716,29 @@ __device__ __forceinline__ float bwd_final(const BwdArgs& a, int trow, int cg, i
 }
 
 // epilogue of the data gradient of layer q: dXhat (tensor memory, NQ x 64 columns = width of layer q-1) ->
-// dZ_{q-1} = LNbwd(dXhat) . ELU'(Y_{q-1})
+// dZ_{q-1} = LNbwd(dXhat) . ELU'(Y_{q-1}).  NQ <= 4: Y_{q-1} is read once and held in registers, dZ is formed in place.
+// NQ == 8 (only the chain's last tensor can be that wide): Y is streamed twice (buffers in the idle B ring).
 template <int NQ>
-__device__ __forceinline__ float bwd_epilogue(const BwdArgs& a, int q, float inv_prev, uint32_t tlane, int trow, int cg,
-                                              int grow, int lane, uint8_t* a_ring, Bars* bars) {
+__device__ __forceinline__ float bwd_epilogue(const BwdArgs& a, int q, float inv_prev, YPipe& yp, uint32_t tlane,
+                                              int trow, int cg, int grow, int lane, uint8_t* a_ring, uint8_t* b_ring,
+                                              Bars* bars) {
     const int N = a.N[q - 1];
     const bool row_ok = grow < a.M;
     const float2 st = row_ok ? a.stats[q][grow] : make_float2(0.f, 1.f);
     const float rs = st.y, nb = -st.x * st.y;
     const float unscale = inv_prev * W_UNSCALE;
-    const float* yrow = a.Y[q - 1] + (size_t)(row_ok ? grow : 0) * N;
+    constexpr bool HOLD = NQ <= 4;
+    constexpr int NR = HOLD ? NQ : 1;
+    const uint8_t* ybase = HOLD ? a_ring : b_ring;
+    float y[16 * NR];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int it = 0; it < NQ; ++it) {
         uint32_t r[16];
         tmem_ld16_nowait(tlane + it * 64 + cg * 16, r);
-        float yv[16];
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const float4 v = ld4(yrow + it * 64 + cg * 16 + 4 * p);
-            yv[4 * p] = v.x; yv[4 * p + 1] = v.y; yv[4 * p + 2] = v.z; yv[4 * p + 3] = v.w;
-        }
+        float yt[16];
+        float* yv = HOLD ? y + it * 16 : yt;
+        take_y_chunk(yp, ybase, trow, cg, lane, yv);
         tmem_wait_ld16(r);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -702,7 +747,7 @@ __device__ __forceinline__ float bwd_epilogue(const BwdArgs& a, int q, float inv
             s2 = fmaf(d, fmaf(yv[i], rs, nb), s2);
         }
     }
-    float2* part = reinterpret_cast<float2*>(a_ring);
+    float2* part = reinterpret_cast<float2*>(a_ring + 2 * A_STAGE);
     part[cg * 128 + trow] = make_float2(s1, s2);
     worker_bar();
     {
@@ -711,20 +756,15 @@ __device__ __forceinline__ float bwd_epilogue(const BwdArgs& a, int q, float inv
         s2 = ((p0.y + p1.y) + (p2.y + p3.y)) / (float)N;
     }
     worker_bar();
-    if (q - 1 == 0 || NQ > 4) {
-        // last tensor of the chain (no further data gradient; also the only place a tile wider than 256 occurs):
-        // stream dZ_0 to global without holding it
+    if (!HOLD) {
+        const int i0 = grow - trow;
         float mx = 0.f;
 #pragma unroll 1
         for (int it = 0; it < NQ; ++it) {
             uint32_t r[16];
             tmem_ld16_nowait(tlane + it * 64 + cg * 16, r);
             float yv[16];
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                const float4 v = ld4(yrow + it * 64 + cg * 16 + 4 * p);
-                yv[4 * p] = v.x; yv[4 * p + 1] = v.y; yv[4 * p + 2] = v.z; yv[4 * p + 3] = v.w;
-            }
+            take_y_chunk(yp, ybase, trow, cg, lane, yv);
             tmem_wait_ld16(r);
             float o[16];
 #pragma unroll
@@ -734,44 +774,42 @@ __device__ __forceinline__ float bwd_epilogue(const BwdArgs& a, int q, float inv
                 o[i] = row_ok ? rs * (d - s1 - xh * s2) * elu_grad_from_out(yv[i]) : 0.f;
                 mx = fmaxf(mx, fabsf(o[i]));
             }
-            if (row_ok) {
-                float* dst = a.dZ[q - 1] + (size_t)grow * N + it * 64 + cg * 16;
-#pragma unroll
-                for (int p = 0; p < 4; ++p)
-                    *reinterpret_cast<float4*>(dst + 4 * p) = make_float4(o[4 * p], o[4 * p + 1], o[4 * p + 2], o[4 * p + 3]);
+            sts_chunk16(a_ring + (it & 1) * A_STAGE, trow, cg, o);
+            fence_proxy_async();
+            if (threadIdx.x == 0) bulk_wait_read0();
+            worker_bar();
+            if (threadIdx.x == 0) {
+                const uint8_t* src = a_ring + (it & 1) * A_STAGE;
+                tma_store_2d(&a.dzmap[q - 1], src, it * 64, i0);
+                tma_store_2d(&a.dzmap[q - 1], src + 16384, it * 64 + 32, i0);
+                bulk_commit();
             }
         }
+        if (threadIdx.x == 0) bulk_wait_read0();
         tc_fence_before();
         const float wm = warp_max(mx);
         if (lane == 0 && wm > 0.f) atomicMax(a.dzmax[q - 1], __float_as_uint(wm));
         return 1.f;
     } else {
-        constexpr int NR = NQ > 4 ? 1 : NQ;            // (NQ > 4 never reaches this branch)
-        float dz[16 * NR];
 #pragma unroll
         for (int it = 0; it < NR; ++it) {
             uint32_t r[16];
             tmem_ld16_nowait(tlane + it * 64 + cg * 16, r);
-            float yv[16];
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                const float4 v = ld4(yrow + it * 64 + cg * 16 + 4 * p);
-                yv[4 * p] = v.x; yv[4 * p + 1] = v.y; yv[4 * p + 2] = v.z; yv[4 * p + 3] = v.w;
-            }
             tmem_wait_ld16(r);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const float d = __uint_as_float(r[i]) * unscale;
-                const float xh = fmaf(yv[i], rs, nb);
-                dz[it * 16 + i] = rs * (d - s1 - xh * s2) * elu_grad_from_out(yv[i]);
+                const float yv = y[it * 16 + i];
+                const float xh = fmaf(yv, rs, nb);
+                y[it * 16 + i] = rs * (d - s1 - xh * s2) * elu_grad_from_out(yv);
             }
         }
         tc_fence_before();      // accumulator free for the next data gradient
-        return emit_dz<NR>(a, q - 1, dz, trow, cg, grow, lane, a_ring, bars);
+        return emit_dz<NR>(a, q - 1, y, trow, cg, grow, lane, a_ring, bars);
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) bwd16_kernel(BwdArgs a) {
+__global__ void __launch_bounds__(NTHREADS, 1) bwd16_kernel(const __grid_constant__ BwdArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_ring = smem;
@@ -791,6 +829,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd16_kernel(BwdArgs a) {
                 mbar_init(&bars->b_empty[q][s], 1);
             }
             mbar_init(&bars->accum[q], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bars->y_full[s], 1);
+            mbar_init(&bars->y_empty[s], NW);
         }
         fence_mbar_init();
     }
@@ -813,7 +855,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd16_kernel(BwdArgs a) {
                 if (q < a.nl - 1) mbar_wait(&bars->accum[q + 1], 0);
                 tma_layer(a.wd[q], kq, 0, bn, nh, a.N[q] >> 6, b_ring, bars->b_full[q], bars->b_empty[q]);
             }
-    } else if (warp == MMA_WARP) {
+      } else if (warp == MMA_WARP) {
         if (lane == 0)
             for (int q = a.nl - 1; q >= 1; --q) {
                 const int kq = a.N[q - 1];
@@ -821,28 +863,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd16_kernel(BwdArgs a) {
                 mma_layer<false>(tmem_base, a.N[q], bn, nh, 0, a_ring, b_ring, bars->a_full[q], bars->a_empty[q],
                                  bars->b_full[q], bars->b_empty[q], &bars->accum[q]);
             }
+      } else if (warp == Y_WARP) {
+        // activation loader: the chunk sequence the workers consume - Y_{nl-1} for the final-layer step, then for every
+        // data gradient q the input activations Y_{q-1} of its LayerNorm-backward (twice when they are streamed)
+        if (lane == 0) {
+            uint32_t c = 0;
+            auto load_chunks = [&](int yq, int nchunks, uint8_t* base) {
+                for (int it = 0; it < nchunks; ++it, ++c) {
+                    const uint32_t b = c & 1u;
+                    mbar_wait(&bars->y_empty[b], ((c >> 1) & 1u) ^ 1u);
+                    uint8_t* dst = base + b * A_STAGE;
+                    mbar_arrive_expect_tx(&bars->y_full[b], 2 * 16384);
+                    tma_load_2d(dst, &a.ymap[yq], it * 64, i0, &bars->y_full[b]);
+                    tma_load_2d(dst + 16384, &a.ymap[yq], it * 64 + 32, i0, &bars->y_full[b]);
+                }
+            };
+            load_chunks(a.nl - 1, a.N[a.nl - 1] >> 6, a_ring);
+            for (int q = a.nl - 1; q >= 1; --q) {
+                const int nq = a.N[q - 1] >> 6;
+                mbar_wait(&bars->accum[q], 0);            // the MMAs of this data gradient have left the A / B rings
+                if (nq <= 4) load_chunks(q - 1, nq, a_ring);
+                else {
+                    load_chunks(q - 1, nq, b_ring);
+                    load_chunks(q - 1, nq, b_ring);
+                }
+            }
+        }
       }
     } else {
         regs_worker();
         const int q4 = warp & 3, cg = warp >> 2;
         const int trow = q4 * 32 + lane, grow = i0 + trow;
         const uint32_t tlane = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        YPipe yp{bars->y_full, bars->y_empty, 0u};
         float inv;
         const int nqf = a.N[a.nl - 1] >> 6;
-        if (nqf == 1) inv = bwd_final<1>(a, trow, cg, grow, lane, a_ring, bars);
-        else if (nqf == 2) inv = bwd_final<2>(a, trow, cg, grow, lane, a_ring, bars);
-        else if (nqf == 3) inv = bwd_final<3>(a, trow, cg, grow, lane, a_ring, bars);
-        else inv = bwd_final<4>(a, trow, cg, grow, lane, a_ring, bars);
+        if (nqf == 1) inv = bwd_final<1>(a, yp, trow, cg, grow, lane, a_ring, bars);
+        else if (nqf == 2) inv = bwd_final<2>(a, yp, trow, cg, grow, lane, a_ring, bars);
+        else if (nqf == 3) inv = bwd_final<3>(a, yp, trow, cg, grow, lane, a_ring, bars);
+        else inv = bwd_final<4>(a, yp, trow, cg, grow, lane, a_ring, bars);
         for (int q = a.nl - 1; q >= 1; --q) {
             mbar_wait(&bars->accum[q], 0);
             __syncwarp();
             tc_fence_after();
             const int nq = a.N[q - 1] >> 6;
-            if (nq == 1) inv = bwd_epilogue<1>(a, q, inv, tlane, trow, cg, grow, lane, a_ring, bars);
-            else if (nq == 2) inv = bwd_epilogue<2>(a, q, inv, tlane, trow, cg, grow, lane, a_ring, bars);
-            else if (nq == 3) inv = bwd_epilogue<3>(a, q, inv, tlane, trow, cg, grow, lane, a_ring, bars);
-            else if (nq == 4) inv = bwd_epilogue<4>(a, q, inv, tlane, trow, cg, grow, lane, a_ring, bars);
-            else inv = bwd_epilogue<8>(a, q, inv, tlane, trow, cg, grow, lane, a_ring, bars);
+            if (nq == 1) inv = bwd_epilogue<1>(a, q, inv, yp, tlane, trow, cg, grow, lane, a_ring, b_ring, bars);
+            else if (nq == 2) inv = bwd_epilogue<2>(a, q, inv, yp, tlane, trow, cg, grow, lane, a_ring, b_ring, bars);
+            else if (nq == 3) inv = bwd_epilogue<3>(a, q, inv, yp, tlane, trow, cg, grow, lane, a_ring, b_ring, bars);
+            else if (nq == 4) inv = bwd_epilogue<4>(a, q, inv, yp, tlane, trow, cg, grow, lane, a_ring, b_ring, bars);
+            else inv = bwd_epilogue<8>(a, q, inv, yp, tlane, trow, cg, grow, lane, a_ring, b_ring, bars);
         }
     }
     __syncwarp();
@@ -965,6 +1034,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad16_kernel(WgArgs a) {
     WgBars* bars = reinterpret_cast<WgBars*>(smem + A_BYTES + B_BYTES);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     griddep_launch();
+    if (tid == 0) TL(0, 38);
     // which layer / tile / row slice
     int li = 0;
     for (int i = 1; i < a.n; ++i)
@@ -995,6 +1065,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad16_kernel(WgArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_slot;
+    if (tid == 0) TL(0, 39);
 
     if (warp >= NW) {
         regs_control();
@@ -1022,6 +1093,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad16_kernel(WgArgs a) {
                     mma_f16_sync(tmem_base, dah, dbh, idesc, acc);
                 }
                 mma_commit(&bars->empty[s]);
+                if (it < 6) TL(1, 41 + 2 * it);
             }
             mma_commit(&bars->accum);
         }
@@ -1037,9 +1109,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad16_kernel(WgArgs a) {
         else if (L.bn == 192) wgrad_worker<192>(L, n0, k0, r_begin, r_end, sc, ring, bars, tid, lane, csum);
         else wgrad_worker<256>(L, n0, k0, r_begin, r_end, sc, ring, bars, tid, lane, csum);
         // ---- epilogue: accumulator (main + correction) * 1/scale -> partial plane; thread = row n, 16-column slices ----
+        if (tid == 0) TL(0, 54);
         mbar_wait(&bars->accum, 0);
         __syncwarp();
         tc_fence_after();
+        if (tid == 0) TL(0, 55);
         float* plane = L.out + (size_t)split * L.N * L.ldp;
         if (ct == 0) {
             // bias-gradient partial: the 64 threads with the same r8 hold disjoint rows of the same 16 columns
@@ -1059,6 +1133,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad16_kernel(WgArgs a) {
                 for (int k = L.K + 1; k < L.ldp; ++k) orow[k] = 0.f;
             }
         }
+        if (tid == 0) TL(0, 56);
         if (n_chunks > 0) {
             const int q4 = warp & 3, cg = warp >> 2;
             const int nrow = n0 + q4 * 32 + lane;
@@ -1090,6 +1165,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad16_kernel(WgArgs a) {
             }
         }
     }
+    if (tid == 0) TL(0, 57);
     __syncwarp();
     tc_fence_before();
     __syncthreads();
@@ -1162,6 +1238,7 @@ __global__ void __launch_bounds__(256) prep16_kernel(PrepArgs t) {
     if (j == t.n) {
         // final layer fold: wf2 = gamma_F w_F, cf2 = c_F + beta_F . w_F (one warp, fixed order)
         for (int k = gtid; k < t.KF; k += gsz) t.wf2[k] = t.gF[k] * t.wF[k];
+        if (t.dzmax && gtid < UB200_MAX_LAYERS) t.dzmax[gtid] = 0u;
         if (blockIdx.x == 0 && threadIdx.x < 32) {
             float s = 0.f;
             for (int k = threadIdx.x; k < t.KF; k += 32) s = fmaf(t.bF[k], t.wF[k], s);

@@ -32,6 +32,7 @@ struct PrepArgs {
     int KF;
     float* wf2;                                 // [KF] gamma_F * w_F
     float* cf2;                                 // [1]  c_F + beta_F . w_F
+    unsigned int* dzmax;                        // [UB200_MAX_LAYERS] running maxima of this step's backward pass: reset here
 };
 
 struct FwdArgs {
@@ -71,6 +72,8 @@ struct BwdArgs {
     const uint16_t* wd[MAXF];                   // data-gradient images of layers 1 .. nl-1 (index q)
     float* dZ[MAXF];                            // out: dZ_q [M, N_q] fp32
     unsigned int* dzmax[MAXF];                  // out: running max |dZ_q| (float bits, atomicMax) for the weight-gradient scale
+    CUtensorMap ymap[MAXF];                     // Y[q] / dZ[q] as [M, N_q] fp32, 32-column x 128-row boxes, 128B swizzle
+    CUtensorMap dzmap[MAXF];
 };
 
 size_t prep_bytes_wf(int K, int N);
