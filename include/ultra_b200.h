@@ -67,9 +67,11 @@ UB200_API int ub200_pack_feed_host(const double* feats_host, int n_docs, int F, 
                          int n_threads);
 
 /* the same packing in two pieces, for a pipelined pack (convert a chunk of rows, start its H2D copy, convert the
- * next chunk): ids/labels part of the layout above, and a plain multi-threaded f64 -> f32 conversion */
+ * next chunk): ids/labels part of the layout above, and a plain multi-threaded f64 -> f32 conversion.
+ * Every packer validates the document ids: an id outside [0, max_id] (max_id = n_docs, the PAD row) is error 5 - the
+ * kernels gather feats[id] unchecked, where the reference's np.take raises IndexError (base_algorithm.py:150). */
 UB200_API int ub200_pack_ids_host(const float* const* docid_cols_host, const float* const* label_cols_host, int L, int B,
-                        void* dst_host, size_t dst_bytes);
+                        int max_id, void* dst_host, size_t dst_bytes);
 UB200_API int ub200_convert_f64_f32_host(const double* src_host, float* dst_host, size_t n, int n_threads);
 
 /* ub200_pack_feed_host into the PINNED buffer `pinned_host` + the H2D copy to `device_dst` on `stream`, pipelined: the

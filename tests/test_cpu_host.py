@@ -159,14 +159,25 @@ def test_column_ptrs_address_the_same_data_as_the_individual_arrays():
     y = [rs.rand(B).astype(np.float32) for _ in range(L)]
     ref = np.zeros(8 * L * B, np.uint8)
     P = ctypes.c_void_p * L
-    assert lib.ub200_pack_ids_host(P(*[x.ctypes.data for x in d]), P(*[x.ctypes.data for x in y]), L, B,
+    assert lib.ub200_pack_ids_host(P(*[x.ctypes.data for x in d]), P(*[x.ctypes.data for x in y]), L, B, 500,
                                    ref.ctypes.data, ref.size) == 0
     for dd, yy in ((d, y), ([x.astype(np.float64) for x in d], [list(map(float, x)) for x in y])):
         out = np.full(8 * L * B, 7, np.uint8)
         dp, kd = column_ptrs(dd, B)
         lp, kl = column_ptrs(yy, B)
-        assert lib.ub200_pack_ids_host(dp, lp, L, B, out.ctypes.data, out.size) == 0
+        assert lib.ub200_pack_ids_host(dp, lp, L, B, 500, out.ctypes.data, out.size) == 0
         assert np.array_equal(out, ref)
+    # ids beyond the PAD row (or negative / NaN) are an error, like np.take's IndexError in the reference
+    # (base_algorithm.py:150): the kernels gather rows unchecked
+    bad = [x.copy() for x in d]
+    bad[3][5] = 501.0
+    dp, kd = column_ptrs(bad, B)
+    lp, kl = column_ptrs(y, B)
+    assert lib.ub200_pack_ids_host(dp, lp, L, B, 500, out.ctypes.data, out.size) == 5
+    assert b"outside" in lib.ub200_last_error()
+    bad[3][5] = -1.0
+    dp, kd = column_ptrs(bad, B)
+    assert lib.ub200_pack_ids_host(dp, lp, L, B, 500, out.ctypes.data, out.size) == 5
     with pytest.raises(Exception):
         column_ptrs([d[0], d[1][:5]], B)          # ragged arrays are not a valid feed
 

@@ -22,7 +22,7 @@ SIGNATURES = {
     "ub200_launch_count": (ctypes.c_ulonglong, []),
     "ub200_feed_bytes": (_sz, [_i, _i, _i, _i]),
     "ub200_pack_feed_host": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _sz, _i]),
-    "ub200_pack_ids_host": (_i, [_vp, _vp, _i, _i, _vp, _sz]),
+    "ub200_pack_ids_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _sz]),
     "ub200_convert_f64_f32_host": (_i, [_vp, _vp, _sz, _i]),
     "ub200_stage_feed": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _sz, _vp, _i, _i, _vp]),
     "ub200_set_tc_mode": (_i, [_i]),

@@ -235,17 +235,24 @@ Job make_job(const double* src, float* dst, long long n, int n_threads, int n_gr
     return j;
 }
 
-void pack_ids(const float* const* docid_cols, const float* const* label_cols, int L, int B, void* dst) {
+// returns the number of ids outside [0, max_id] (max_id = the PAD row): the kernels gather feats[id] unchecked, where
+// the reference's np.take raises IndexError (base_algorithm.py:150)
+long long pack_ids(const float* const* docid_cols, const float* const* label_cols, int L, int B, void* dst,
+                   long long max_id) {
     int32_t* docid = reinterpret_cast<int32_t*>(dst);                                              // [L, B]
     float* labels = reinterpret_cast<float*>(static_cast<char*>(dst) + (size_t)4 * L * B);         // [B, L]
+    long long bad = 0;
     for (int l = 0; l < L; ++l) {
         const float* d = docid_cols[l];
         const float* y = label_cols[l];
         for (int b = 0; b < B; ++b) {
-            docid[(size_t)l * B + b] = (int32_t)d[b];
+            const float v = d[b];
+            bad += !(v >= 0.f && v <= (float)max_id);
+            docid[(size_t)l * B + b] = (int32_t)v;
             labels[(size_t)b * L + l] = y[b];
         }
     }
+    return bad;
 }
 
 }  // namespace
@@ -263,10 +270,11 @@ extern "C" UB200_API int ub200_convert_f64_f32_host(const double* src, float* ds
 }
 
 extern "C" UB200_API int ub200_pack_ids_host(const float* const* docid_cols, const float* const* label_cols, int L,
-                                             int B, void* dst, size_t dst_bytes) {
+                                             int B, int max_id, void* dst, size_t dst_bytes) {
     HP_CHECK(dst && docid_cols && label_cols && L > 0 && B > 0, 2, "pack_ids_host: bad arguments");
     HP_CHECK(dst_bytes >= (size_t)8 * L * B, 3, "pack_ids_host: destination too small");
-    pack_ids(docid_cols, label_cols, L, B, dst);
+    const long long bad = pack_ids(docid_cols, label_cols, L, B, dst, max_id);
+    HP_CHECK(bad == 0, 5, "pack_ids_host: %lld document ids outside [0, %d] (the feed indexes rows the feature matrix does not have)", bad, max_id);
     return 0;
 }
 
@@ -279,7 +287,8 @@ extern "C" UB200_API int ub200_pack_feed_host(const double* feats, int n_docs, i
     HP_CHECK(dst_bytes >= need, 3, "pack_feed_host: destination too small (%zu < %zu)", dst_bytes, need);
     char* base = static_cast<char*>(dst);
     float* f32 = reinterpret_cast<float*>(base + align_up((size_t)8 * L * B, 256));   // [n_docs + 1, F]
-    pack_ids(docid_cols, label_cols, L, B, dst);
+    const long long bad = pack_ids(docid_cols, label_cols, L, B, dst, n_docs);
+    HP_CHECK(bad == 0, 5, "pack_feed_host: %lld document ids outside [0, %d]", bad, n_docs);
     const long long nf = (long long)n_docs * F;
     memset(f32 + nf, 0, sizeof(float) * (size_t)F);      // the PAD row (base_algorithm.py:148-149)
     if (nf) pool()->run(make_job(feats, f32, nf, n_threads, 1), [](Slot&) {});
@@ -308,7 +317,8 @@ extern "C" UB200_API int ub200_stage_feed(const double* feats, int n_docs, int F
     auto copy = [&](size_t b0, size_t b1) {
         if (err == cudaSuccess && b1 > b0) err = cudaMemcpyAsync(db + b0, hb + b0, b1 - b0, cudaMemcpyHostToDevice, st);
     };
-    pack_ids(docid_cols, label_cols, L, B, pinned);
+    const long long bad = pack_ids(docid_cols, label_cols, L, B, pinned, n_docs);
+    HP_CHECK(bad == 0, 5, "stage_feed: %lld document ids outside [0, %d]", bad, n_docs);
     memset(f32 + nf, 0, sizeof(float) * (size_t)F);      // the PAD row
     copy(0, (size_t)8 * L * B);
     if (nf == 0) {

@@ -1285,14 +1285,33 @@ extern "C" UB200_API int ub200_f16_timeline(long long* out192) {
 namespace ub200 {
 namespace f16 {
 
+// cuTensorMapEncodeTiled is looked up through the runtime (cudaGetDriverEntryPoint) instead of linked: the library must
+// load on machines without a driver (the CPU test suite checks its exports there)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
 int make_tmap_f32(CUtensorMap* m, const float* base, size_t rows, size_t cols) {
     const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)cols * sizeof(float)};
     const cuuint32_t box[2] = {32, 128};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = cuTensorMapEncodeTiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride,
-                                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    EncodeTiledFn fn = encode_tiled_fn();
+    UB_CHECK(fn != nullptr, 101, "cuTensorMapEncodeTiled is not available from this driver");
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     UB_CHECK(r == CUDA_SUCCESS, 101, "cuTensorMapEncodeTiled failed (%d) for [%zu, %zu] at %p", (int)r, rows, cols,
              (const void*)base);
     return 0;

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) clip_update_kernel(float* __restrict__ p,
     }
 }
 
-// norm + clip + update in one launch.  `bar` = {arrive, depart, timeout flag}: all zero on entry and on exit.
+// norm + clip + update in one launch.  `bar` = {arrive, depart}: zero on entry and on exit.
 __global__ void __launch_bounds__(256) clip_update_fused_kernel(float* __restrict__ p, float* __restrict__ g,
                                                                  float* __restrict__ state, size_t n,
                                                                  const float* __restrict__ den, float scale_const,
@@ -125,9 +125,11 @@ __global__ void __launch_bounds__(256) clip_update_fused_kernel(float* __restric
         unsigned int seen;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
-            if (seen < gridDim.x && clock64() - t0 > (1ll << 31)) {      // ~1 s: never hang the device
-                bar[2] = 1u;
-                break;
+            if (seen < gridDim.x && clock64() - t0 > (1ll << 31)) {      // ~1 s: never hang the device ...
+                // ... and never update the parameters with a clip coefficient from incomplete partial sums: abort the
+                // kernel (the error surfaces at the next synchronisation), as the exchange kernel does (peer.cu)
+                printf("ub200 optimizer: grid barrier timed out (block %d saw %u of %u)\n", blockIdx.x, seen, gridDim.x);
+                __trap();
             }
         } while (seen < gridDim.x);
     }

@@ -117,6 +117,21 @@ class RankerEngine(object):
         self._pack_chunks = int(os.environ.get("UB200_PACK_CHUNKS", "6"))
         self._scores = {}
         self._dscores = {}
+        # CUDA graphs captured by the learning algorithms have the raw pointers of the workspaces / score buffers baked
+        # in.  Whenever one of those buffers is released the generation moves on, and every graph captured under an
+        # older generation is discarded instead of replayed (base_algorithm.py: _run_step).
+        self.generation = 0
+
+    MAX_SHAPES = 64      # (L, B) shapes whose workspaces stay cached (DirectLabelFeed batches vary in size)
+
+    @staticmethod
+    def _evict_lru(cache, limit):
+        """dicts keep insertion order and hits re-insert their key: the first key is the least recently used one"""
+        evicted = False
+        while len(cache) >= limit:
+            cache.pop(next(iter(cache)))
+            evicted = True
+        return evicted
 
     # ---- data-parallel exchange buffer ----------------------------------------------------------------
     def _alloc_gradbuf(self, f32):
@@ -207,31 +222,34 @@ class RankerEngine(object):
     # ---- workspaces ------------------------------------------------------------------------------
     def _mlp_ws(self, L, B, training):
         key = (L, B, int(bool(training)))
-        ws = self._ws.get(key)
+        ws = self._ws.pop(key, None)
         if ws is None:
             n = int(lib.ub200_mlp_workspace_bytes(L, B, self.F, self._hidden_c, self.n_hidden, key[2]))
+            if self._evict_lru(self._ws, self.MAX_SHAPES):
+                self.generation += 1
             ws = torch.zeros(max(n, 256), dtype=torch.uint8, device=self.device)
-            if len(self._ws) > 8:
-                self._ws.clear()
-            self._ws[key] = ws
+        self._ws[key] = ws                        # (re-)inserted last = most recently used
         return ws
 
     def loss_ws(self, B, L):
         n = max(int(lib.ub200_loss_workspace_bytes(B, L)), int(lib.ub200_pair_workspace_bytes(B, L)))
         if self._loss_ws is None or self._loss_ws.numel() < n:
+            if self._loss_ws is not None:
+                self.generation += 1
             self._loss_ws = torch.zeros(n, dtype=torch.uint8, device=self.device)
         return self._loss_ws
 
     def scores_buf(self, B, L):
         key = (B, L)
-        t = self._scores.get(key)
+        t = self._scores.pop(key, None)
         if t is None:
-            if len(self._scores) > 8:
-                self._scores.clear()
-                self._dscores.clear()
+            if self._evict_lru(self._scores, self.MAX_SHAPES):
+                self.generation += 1
+                for k in [k for k in self._dscores if k not in self._scores]:
+                    del self._dscores[k]
             t = torch.empty(B, L, dtype=torch.float32, device=self.device)
-            self._scores[key] = t
             self._dscores[key] = torch.empty(B, L, dtype=torch.float32, device=self.device)
+        self._scores[key] = t
         return t
 
     def dscores_buf(self, B, L):
@@ -312,7 +330,7 @@ class RankerEngine(object):
             self._staged_cache.entries.clear()       # views of the previous staging buffer
         dptr, keep_d = column_ptrs(docid_arrays, B)
         lptr, keep_l = column_ptrs(label_arrays, B)
-        check(lib.ub200_pack_ids_host(dptr, lptr, L, B, self._pin.data_ptr(), self._pin.numel()),
+        check(lib.ub200_pack_ids_host(dptr, lptr, L, B, n_rows, self._pin.data_ptr(), self._pin.numel()),
               "ub200_pack_ids_host")
         self._dev[:nbytes].copy_(self._pin[:nbytes], non_blocking=True)
         st = Staged()
@@ -340,15 +358,27 @@ class RankerEngine(object):
                                     int(check_validation), int(max_rounds), B, int(pad_id), int(seed), int(offset),
                                     _ptr(docid), _ptr(labels), _ptr(query_idx), _stream()), "ub200_click_batch")
 
+    # bytes of resident feature matrices kept in HBM at once (train / valid / test sets of one run stay resident side by
+    # side; the least recently used one goes when the cap would be exceeded)
+    RESIDENT_CAP_BYTES = int(float(os.environ.get("UB200_RESIDENT_CAP_GB", "96")) * (1 << 30))
+
     def ensure_resident(self, feats):
-        """Uploads the data set's whole feature matrix (fp32 + zero PAD row) unless it is the one already resident."""
+        """Makes the data set's whole feature matrix (fp32 + zero PAD row) resident and current.  Matrices are cached by
+        `resident_key()`: main.py alternates train / validation / test feeds on one model, and re-converting GBs of
+        f64 at every switch (and orphaning the CUDA graphs keyed on the old pointer) would defeat "uploaded once"."""
         n_rows, F = feats.shape
         if F != self.F:
             raise _capi.UltraB200Error("resident feature matrix has %d columns, the ranker expects %d" % (F, self.F))
         if n_rows >= (1 << 24):
             raise _capi.UltraB200Error("doc ids travel as float32 in the feed format: at most 2^24 rows per data set")
         key = feats.resident_key()
-        if getattr(self, "_resident_key", None) != key:
+        cache = self.__dict__.setdefault("_resident_cache", {})
+        ent = cache.pop(key, None)
+        if ent is None:
+            need = 4 * (n_rows + 1) * F
+            while cache and sum(e[0].numel() * 4 for e in cache.values()) + need > self.RESIDENT_CAP_BYTES:
+                cache.pop(next(iter(cache)))                         # least recently used
+                self.generation += 1                                 # graphs keyed on its pointer must not be replayed
             dev = torch.empty((n_rows + 1) * F, dtype=torch.float32, device=self.device)
             chunk_rows = max(1, (32 << 20) // (4 * F))
             pin = torch.empty(chunk_rows * F, dtype=torch.float32, pin_memory=True)
@@ -361,9 +391,10 @@ class RankerEngine(object):
                 dev[r0 * F:r1 * F].copy_(pin[:n], non_blocking=True)
                 torch.cuda.current_stream().synchronize()           # the pinned chunk is reused
             dev[n_rows * F:].zero_()                                 # PAD row (base_algorithm.py:148-149)
-            self._resident = dev.view(n_rows + 1, F)
-            self._resident_key = key
-            self._resident_host = feats                              # keeps the address alive while it is the key
+            ent = (dev.view(n_rows + 1, F), feats)                   # the host array keeps its address alive while it is the key
+        cache[key] = ent                                             # most recently used last
+        self._resident = ent[0]
+        self._resident_key = key
 
     def staged_views(self, dev, L, B, n_docs):
         return self._staged_cache.get(dev, L, B, n_docs, self.F)

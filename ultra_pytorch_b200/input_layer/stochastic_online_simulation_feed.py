@@ -89,12 +89,14 @@ class StochasticOnlineSimulationFeed(ClickSimulationFeed):
         perm = self.model.engine.pl_sample(scores, st.docid, st.n_docs, self.hparams.tau, self._seed, self._draws)
         return perm.cpu().numpy().astype(np.int64)
 
-    def _simulate_prefix(self, labels, check_validation):
+    def _simulate_prefix(self, labels, check_validation, valid):
         """Clicks on the first rank_list_size positions of the re-ranked lists (:150-161): PBM sample, re-drawn (up to
-        MAX_SAMPLE_ROUND_NUM times) for lists without any click when check_validation is set."""
+        MAX_SAMPLE_ROUND_NUM times) for lists without any click when check_validation is set.  `valid` masks the real
+        positions: the reference samples only the list_len real documents (:150 truncates to the list), so a click drawn
+        on a PAD slot (label 0 still has the noise-click probability) must neither survive nor stop the re-draw."""
         if self.hparams.oracle_mode:
-            return labels.copy()
-        p = self.click_model.click_probability(labels)
+            return labels * valid
+        p = self.click_model.click_probability(labels) * valid
         clicks = (self.rng.random(labels.shape) < p).astype(np.float64)
         if check_validation:
             for _ in range(self.MAX_SAMPLE_ROUND_NUM):
@@ -117,8 +119,10 @@ class StochasticOnlineSimulationFeed(ClickSimulationFeed):
         list_len = np.where((docid < n_docs).any(axis=1), list_len, 0)
         k = min(K, L)
         clicks = np.zeros_like(new_label)
-        clicks[:, :k] = self._simulate_prefix(new_label[:, :k].astype(np.float64), check_validation)
-        clicks[np.arange(L)[None, :] >= list_len[:, None]] = 0.0        # only real positions receive labels (:171-176)
+        valid = (np.arange(L)[None, :] < list_len[:, None])
+        clicks[:, :k] = self._simulate_prefix(new_label[:, :k].astype(np.float64), check_validation,
+                                              valid[:, :k].astype(np.float64))
+        clicks[~valid] = 0.0                                            # only real positions receive labels (:171-176)
         for l in range(L):
             input_feed[self.model.docid_inputs_name[l]] = np.ascontiguousarray(new_docid[:, l], dtype=np.float32)
             input_feed[self.model.labels_name[l]] = np.ascontiguousarray(clicks[:, l], dtype=np.float32)

@@ -97,10 +97,14 @@ class B200Algorithm(_reference_base()):
             return self.device_step(st)
         key = (st.B, st.L, st.feats.data_ptr(), st.docid.data_ptr())
         ent = self._graphs.get(key)
+        if ent is not None and ent[4] != self.engine.generation:
+            # a buffer this graph has baked in (workspace, scores, loss scratch) was released since the capture
+            del self._graphs[key]
+            ent = None
         if ent is None:
             if len(self._graphs) > 512:
                 self._graphs.clear()
-            ent = self._graphs[key] = [0, None, None, None]
+            ent = self._graphs[key] = [0, None, None, None, self.engine.generation]
         if ent[1] is not None:
             ent[1].replay()
             if ent[3] is not None:
@@ -109,7 +113,9 @@ class B200Algorithm(_reference_base()):
             return ent[2]
         ent[0] += 1
         if ent[0] <= 2:                      # warm-up: workspaces get allocated outside the capture
-            return self.device_step(st)
+            out = self.device_step(st)
+            ent[4] = self.engine.generation   # allocations of the warm-up itself are not releases of captured buffers
+            return out
         torch.cuda.synchronize()
         if not dp:
             graph = torch.cuda.CUDAGraph()
