@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="skip the informational feed + train leg")
     ap.add_argument("--cpu-steps", type=int, default=0, help="timed steps of the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-all-configs", action="store_true", help="skip the per-config / list-length table")
+    ap.add_argument("--min-seconds", type=float, default=0.5,
+                    help="the K timed steps are repeated (>= 5 times) until this much device time has been measured")
     return ap.parse_args()
 
 
@@ -192,51 +195,71 @@ def main_b200(args):
     model = getattr(la, w["algo"])(types.SimpleNamespace(feature_size=F), settings)
     eng = model.engine
 
-    # ---- synthetic batches (rank-specific seeds: every rank trains on its own shard of queries) ----
-    n_host = 8
-    feeds = [synth.make_feed(1000 * rank + i, F, L, B, w["labels"]) for i in range(n_host)]
-    step_bytes = eng.stage(feeds[0]["letor_features"], [feeds[0]["docid_input%d" % l] for l in range(L)],
-                           [feeds[0]["label%d" % l] for l in range(L)]).h2d_bytes
-    ring_n = max(4, int(1.25 * L2_BYTES / step_bytes) + 1)
-    ring = []
-    for i in range(ring_n):
-        f = feeds[i % n_host]
-        st = eng.stage(f["letor_features"], [f["docid_input%d" % l] for l in range(L)],
-                       [f["label%d" % l] for l in range(L)])
-        torch.cuda.synchronize()
-        own = eng._dev[:st.h2d_bytes].clone()
-        ring.append(eng.staged_views(own, L, B, st.n_docs))
-    use_graph = la.B200Algorithm.USE_GRAPH and (world == 1 or la.B200Algorithm.USE_GRAPH_DP)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def build_ring(mdl, wl, n_host=8):
+        """host feeds + a ring of distinct device-resident batches larger than the L2 (rank-specific seeds: every rank
+        trains on its own shard of queries)"""
+        e = mdl.engine
+        Fq, Lq, Bq = wl["F"], wl["L"], wl["B"]
+        fds = [synth.make_feed(1000 * rank + i, Fq, Lq, Bq, wl["labels"]) for i in range(n_host)]
+        sb = e.stage(fds[0]["letor_features"], [fds[0]["docid_input%d" % l] for l in range(Lq)],
+                     [fds[0]["label%d" % l] for l in range(Lq)]).h2d_bytes
+        n = max(4, int(1.25 * L2_BYTES / sb) + 1)
+        rg = []
+        for i in range(n):
+            f = fds[i % n_host]
+            st = e.stage(f["letor_features"], [f["docid_input%d" % l] for l in range(Lq)],
+                         [f["label%d" % l] for l in range(Lq)])
+            torch.cuda.synchronize()
+            own = e._dev[:st.h2d_bytes].clone()
+            rg.append(e.staged_views(own, Lq, Bq, st.n_docs))
+        return fds, rg, sb
+
+    def time_steps(mdl, rg, steps, warmup, min_seconds, graphs):
+        """K steps per repeat, timed on the device (CUDA events on the launching stream, barrier + synchronize on both
+        sides, max over ranks); repeated >= 5 times and until min_seconds of device time have been measured; the MEDIAN
+        repeat is reported.  Every ring slot has its CUDA graph before the first timed step."""
+        n = len(rg)
+        for i in range(max(warmup, 3)):
+            mdl.run_step(rg[i % n])
+        if graphs:
+            for i in range(3 * n):
+                mdl.run_step(rg[i % n])
+        times, total, k0 = [], 0.0, 0
+        while len(times) < 5 or total < min_seconds * 1e3:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            for k in range(steps):
+                mdl.run_step(rg[(k0 + k) % n])
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times.append(float(t.item()))
+            total += times[-1]
+            k0 += steps
+            if len(times) >= 200:
+                break
+        times.sort()
+        return times[len(times) // 2], times, total
+
+    feeds, ring, step_bytes = build_ring(model, w)
+    ring_n, n_host = len(ring), len(feeds)
+    use_graph = la.B200Algorithm.USE_GRAPH and (world == 1 or la.B200Algorithm.USE_GRAPH_DP)
+
     # ---- value leg: device-resident batches ----
-    for i in range(max(args.warmup, 3)):
-        model.run_step(ring[i % ring_n])
-    if use_graph:                       # make sure every ring slot has its graph before timing
-        for i in range(3 * ring_n):
-            model.run_step(ring[i % ring_n])
-    barrier()
     launches0 = _capi.lib.ub200_launch_count()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for k in range(args.steps):
-        model.run_step(ring[k % ring_n])
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms, rep_times, timed_total_ms = time_steps(model, ring, args.steps, args.warmup, args.min_seconds, use_graph)
     eager_launches = _capi.lib.ub200_launch_count() - launches0
-    t = torch.tensor([ms], device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
     value = world * B * args.steps / (ms / 1e3)
 
     # kernels per step (graph replays launch the captured kernels without passing through the library counter)
@@ -246,7 +269,7 @@ def main_b200(args):
     model.run_step(ring[0])
     per_step = _capi.lib.ub200_launch_count() - c0
     la.B200Algorithm.USE_GRAPH = model.USE_GRAPH_saved
-    gpu_launches = per_step * args.steps if use_graph else eager_launches
+    gpu_launches = per_step * args.steps * len(rep_times) if use_graph else eager_launches
 
     # ---- roofline leg: K1 (DNN forward + backward kernels) timed alone, graph-replayed ----
     st0 = ring[0]
@@ -276,40 +299,72 @@ def main_b200(args):
     except Exception:  # noqa: BLE001
         pass
     peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+
+    def dense_peak(dtype, tf32):
+        """torch.matmul 8192^3, best of 10 (the way MEASURED_PEAKS.json measures its bf16 number)"""
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        a_ = torch.randn(8192, 8192, device="cuda", dtype=dtype)
+        b_ = torch.randn(8192, 8192, device="cuda", dtype=dtype)
+        best = 1e9
+        for _ in range(12):
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            torch.matmul(a_, b_)
+            q1.record()
+            torch.cuda.synchronize()
+            best = min(best, q0.elapsed_time(q1))
+        torch.backends.cuda.matmul.allow_tf32 = False
+        return 2.0 * 8192 ** 3 / (best / 1e3) / 1e12
+    tf32_peak = dense_peak(torch.float32, True) if rank == 0 else None
+    f16_peak = dense_peak(torch.float16, False) if rank == 0 else None
     traffic, traffic_src = None, None
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum of the K1 kernels of ONE step, from the committed ncu --set full
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    try:   # warm-cache dram__bytes_read.sum + dram__bytes_write.sum of the K1 kernels of ONE replayed step (ncu)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         ent = tr.get("%s_B%d" % (args.workload, B))
         if ent:
             traffic, traffic_src = ent["k1_dram_bytes_per_step"], tr.get("source")
     except Exception:  # noqa: BLE001
         pass
     achieved_tf = flops / (k1_ms / 1e3) / 1e12
+    alg_bytes = int(4 * L * B * F)
     roofline = {"bound": "tensor", "achieved": round(achieved_tf, 3), "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": round(achieved_tf / peak_tf, 5), "traffic": traffic, "traffic_source": traffic_src,
-                "algorithmic_hbm_bytes": int(4 * L * B * F),
+                "algorithmic_hbm_bytes": alg_bytes,
+                "traffic_over_algorithmic": round(traffic / alg_bytes, 2) if traffic else None,
                 "kernel": "K1 DNN forward+backward (all launches of ub200_mlp_forward + ub200_mlp_backward)",
                 "ms_per_launch_group": round(k1_ms, 4), "fwd_ms": round(fwd_ms, 4),
                 "algorithmic_flops": flops, "peak_source": "MEASURED_PEAKS.json bf16 burst" if peaks else "fallback",
+                # the arithmetic is fp32-accurate through THREE fp16 products per multiply (x = hi + lo), so the ceiling
+                # of this formulation is a third of the 16-bit dense rate; 3xTF32 (round 1) had a sixth
+                "f16_dense_peak_measured": round(f16_peak, 1) if f16_peak else None,
+                "tf32_dense_peak_measured": round(tf32_peak, 1) if tf32_peak else None,
+                "frac_of_split_ceiling": round(achieved_tf / (peak_tf / 3.0), 5),
+                "frac_of_tf32_peak_over_3": round(achieved_tf / (tf32_peak / 3.0), 5) if tf32_peak else None,
                 "fp32_ffma_peak_tflops": 72.0, "frac_of_fp32_ffma_peak": round(achieved_tf / 72.0, 4)}
 
-    # ---- e2e leg: public train(input_feed) with host feeds ----
+    # ---- e2e leg: public train(input_feed) with host feeds (wall clock around K train() calls + a final synchronize;
+    # >= 5 repeats, median) ----
     for i in range(6):
         model.train(feeds[i % n_host])
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        model.train(feeds[k % n_host])
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_times = []
+    while len(e2e_times) < 5 or sum(e2e_times) < args.min_seconds:
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            model.train(feeds[k % n_host])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_times.append(float(t.item()))
+        if len(e2e_times) >= 100:
+            break
     clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions (value leg .. e2e leg)
-    t = torch.tensor([e2e_s], device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    e2e_s = sorted(e2e_times)[len(e2e_times) // 2]
     e2e = {"value": round(world * B * args.steps / e2e_s, 1), "unit": "queries/s",
            "h2d_bytes_per_step": int(model.last_h2d_bytes), "d2h_bytes_per_step": int(model.last_d2h_bytes),
-           "ms_per_step": round(1e3 * e2e_s / args.steps, 4)}
+           "ms_per_step": round(1e3 * e2e_s / args.steps, 4), "repeats": len(e2e_times)}
 
     # ---- pipeline leg (informational): what main.py's loop does per step - feed.get_batch() + model.train() - with
     # the drop-in ClickSimulationFeed on a synthetic data set, (a) in the reference's feed format (feature rows copied
@@ -323,10 +378,10 @@ def main_b200(args):
         ds = synth.synthetic_dataset(2048, L, F, seed=7 + rank)
         pipeline = {"what": "ClickSimulationFeed.get_batch + train() per step, synthetic data set of 2048 queries",
                     "unit": "queries/s"}
-        n_pipe = max(20, min(args.steps, 200))
+        n_pipe = max(200, min(args.steps, 1000))
         for name, hp in (("host_rows", ""), ("resident", "resident_features=True"), ("device", "device_batches=True")):
             feeder = ClickSimulationFeed(model, B, "click_model_json=%s,%s" % (synth.PBM_JSON, hp))
-            for _ in range(6):
+            for _ in range(24):          # the device feed rotates 4 output buffers and a graph needs 3 visits of each
                 model.train(feeder.get_batch(ds, check_validation=True)[0])
             barrier()
             t0 = time.perf_counter()
@@ -336,6 +391,106 @@ def main_b200(args):
             dt = time.perf_counter() - t0
             pipeline[name] = {"value": round(world * B * n_pipe / dt, 1), "ms_per_step": round(1e3 * dt / n_pipe, 4),
                               "h2d_bytes_per_step": int(model.last_h2d_bytes)}
+
+    # ---- the north_star table: every BASELINE.json config + the list-length sweep of the headline net, same method
+    # (resident ring > L2, CUDA-graph replay, device-timed, median of >= 5 repeats, max over ranks), shorter runs ----
+    all_configs = None
+    if not args.no_all_configs:
+        all_configs = []
+        table = [(n, dict(synth.WORKLOADS[n])) for n in ("c1_na_toy", "c3_dla_yahoo", "c4_lambdarank_mslr30k",
+                                                         "c4_pairdebias_mslr30k", "c5_dla_istella")]
+        for Lq in (10, 20, 100, 200):
+            table.append(("c2net_ipw_L%d" % Lq, dict(algo="IPWrank", F=136, L=Lq, B=256, hidden=[256, 128, 64],
+                                                      labels="click")))
+        for name, wq in table:
+            if name == args.workload:
+                continue
+            torch.manual_seed(0)
+            mq = getattr(la, wq["algo"])(types.SimpleNamespace(feature_size=wq["F"]), synth.exp_settings(wq))
+            fq, rq, sbq = build_ring(mq, wq, n_host=4)
+            steps_q = 50
+            ms_q, reps_q, _ = time_steps(mq, rq, steps_q, 3, 0.1, use_graph)
+            # K1 alone (forward + backward launches), L2 flushed between iterations
+            e_q = mq.engine
+            st_q = rq[0]
+            dq = e_q.dscores_buf(wq["B"], wq["L"])
+            gf_q, gb_q = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(gf_q):
+                e_q.forward(st_q.feats, st_q.docid.view(-1), wq["L"], wq["B"], training=True)
+            with torch.cuda.graph(gb_q):
+                e_q.backward(st_q.feats, st_q.docid.view(-1), wq["L"], wq["B"], dq)
+            k1 = []
+            for it in range(8):
+                flush.zero_()
+                q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                q0.record(); gf_q.replay(); gb_q.replay(); q1.record()
+                torch.cuda.synchronize()
+                if it >= 3:
+                    k1.append(q0.elapsed_time(q1))
+            k1_q = sum(k1) / len(k1)
+            fl_q = synth.train_flops_per_query(wq["F"], wq["L"], wq["hidden"]) * wq["B"]
+            tf_q = fl_q / (k1_q / 1e3) / 1e12
+            all_configs.append({"workload": name, "algo": wq["algo"], "features": wq["F"], "list_len": wq["L"],
+                                "hidden": wq["hidden"], "batch_queries": wq["B"],
+                                "value": round(world * wq["B"] * steps_q / (ms_q / 1e3), 1), "unit": "queries/s",
+                                "ms_per_step": round(ms_q / steps_q, 5), "repeats": len(reps_q),
+                                "k1_ms": round(k1_q, 4), "k1_tflops": round(tf_q, 2),
+                                "k1_frac_of_bf16_peak": round(tf_q / peak_tf, 5),
+                                "k1_frac_of_split_ceiling": round(tf_q / (peak_tf / 3.0), 5)})
+            del mq, fq, rq, gf_q, gb_q
+            torch.cuda.empty_cache()
+
+    # ---- data-parallel self-check (N > 1): replicas must stay bitwise equal, and the sharded step must equal a
+    # single-GPU step on the merged batch (rank 0 re-runs the merged batches on one GPU) ----
+    dp_check = None
+    if world > 1:
+        import numpy as np
+        torch.manual_seed(0)
+        mdp = getattr(la, w["algo"])(types.SimpleNamespace(feature_size=F), settings)
+        init = {k: v.clone() for k, v in mdp.model.state_dict().items()}
+        Bc = 64
+        for step in range(3):
+            mdp.train(synth.make_feed(7000 + 100 * step + rank, F, L, Bc, w["labels"]))
+        flat = mdp.engine.params.clone()
+        gathered = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        same = all(torch.equal(gathered[0], g_) for g_ in gathered)
+        err = None
+        if rank == 0:
+            ws_fn = la.B200Algorithm.world_size
+            la.B200Algorithm.world_size = staticmethod(lambda: 1)      # a plain single-GPU model (no rendezvous)
+            try:
+                torch.manual_seed(0)
+                ref = getattr(la, w["algo"])(types.SimpleNamespace(feature_size=F), settings)
+                ref.model.load_state_dict(init)
+                for step in range(3):
+                    fs = [synth.make_feed(7000 + 100 * step + r, F, L, Bc, w["labels"]) for r in range(world)]
+                    feats_m = np.concatenate([f["letor_features"] for f in fs], axis=0)
+                    merged = {"letor_features": feats_m}
+                    for l in range(L):
+                        d_, y_, base = [], [], 0
+                        for f in fs:
+                            n_ = f["letor_features"].shape[0]
+                            di = f["docid_input%d" % l].astype(np.int64)
+                            d_.append(np.where(di == n_, feats_m.shape[0], di + base))
+                            y_.append(f["label%d" % l])
+                            base += n_
+                        merged["docid_input%d" % l] = np.concatenate(d_).astype(np.float32)
+                        merged["label%d" % l] = np.concatenate(y_).astype(np.float32)
+                    ref.train(merged)
+                a_, b_ = flat, ref.engine.params
+                keep = torch.ones_like(a_, dtype=torch.bool)       # mathematically-zero gradients random-walk
+                for nm, off, shape in mdp.engine.layer_slices():
+                    if nm in ("layer_norm%d.bias" % len(hidden), "linear%d.bias" % len(hidden)):
+                        keep[off:off + int(np.prod(shape))] = False
+                err = float((a_ - b_)[keep].abs().max() / b_[keep].abs().mean())
+            finally:
+                la.B200Algorithm.world_size = ws_fn
+        dist.barrier()
+        dp_check = {"replicas_bitwise_equal": bool(same), "vs_single_gpu": err,
+                    "what": "3 train() steps of %d queries per rank; vs_single_gpu = max|param_dp - param_single| / "
+                            "mean|param| against one GPU training on the merged batches" % Bc}
 
     if rank == 0:
         line = {
@@ -349,7 +504,14 @@ def main_b200(args):
                              (ring_n, ring_n * step_bytes / 1e6)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "kernels_per_step": int(per_step),
             "roofline": roofline,
+            "repeats": len(rep_times), "timed_region_s": round(timed_total_ms / 1e3, 4),
+            "timing": "value = K steps / the MEDIAN of `repeats` device-timed repetitions of the K-step loop "
+                      "(min %.3f ms, max %.3f ms per repetition)" % (min(rep_times), max(rep_times)),
         }
+        if all_configs is not None:
+            line["all_configs"] = all_configs
+        if dp_check is not None:
+            line["dp_check"] = dp_check
         if pipeline is not None:
             line["pipeline"] = pipeline
         if world == 1 and not args.no_cpu_baseline:

@@ -51,6 +51,13 @@ CASES = [
     ("lambdarank_linear", "lambdarank", 14, 7, 7, 6, [], "graded", 2),
     ("prsrank_small", "prsrank", 10, 6, 8, 8, [16, 8], "graded", 3),
     ("prsrank_click", "prsrank", 10, 7, 7, 6, [16, 8], "click", 2),
+    # BASELINE.json shapes (configs 3, 5, 4 and the config-2 net under the pairwise loss): every hidden layer runs on the
+    # tensor cores, so reference-generated numbers go THROUGH the tcgen05 kernels for DLA / LambdaRank / PairDebias too.
+    # Stored compactly (trailing True): features as float32 (they are float32-exact), no post-step parameters.
+    ("dla_c3like", "dla", 700, 20, 20, 16, [512, 256, 128], "click", 1, True),
+    ("dla_c5like", "dla", 220, 100, 100, 8, [512, 256, 128], "click", 1, True),
+    ("lambdarank_c4like", "lambdarank", 136, 200, 200, 8, [512, 256, 128], "graded", 1, True),
+    ("pairdebias_c2net", "pairdebias", 136, 40, 40, 16, [256, 128, 64], "click", 1, True),
 ]
 
 
@@ -92,7 +99,7 @@ def state_to_np(sd, prefix):
     return {prefix + k: v.detach().cpu().numpy().copy() for k, v in sd.items()}
 
 
-def run_case(ultra, name, algo, F, L_train, L_max, B, hidden, kind, n_steps):
+def run_case(ultra, name, algo, F, L_train, L_max, B, hidden, kind, n_steps, compact=False):
     random.seed(0)
     np.random.seed(0)
     torch.manual_seed(0)
@@ -135,7 +142,8 @@ def run_case(ultra, name, algo, F, L_train, L_max, B, hidden, kind, n_steps):
 
     # validation on the initial parameters (forward only, L = max_candidate_num)
     vfeed, vdoc, vlab = make_feed(rs, model, B, L_max, F, "graded")
-    out["valid/features"] = vfeed[model.letor_features_name]
+    feat_dtype = np.float32 if compact else np.float64          # tests/helpers.py: load_golden casts back to float64
+    out["valid/features"] = vfeed[model.letor_features_name].astype(feat_dtype)
     out["valid/docids"] = vdoc
     out["valid/labels"] = vlab
     _, scores, summary = model.validation(dict(vfeed))
@@ -156,7 +164,7 @@ def run_case(ultra, name, algo, F, L_train, L_max, B, hidden, kind, n_steps):
         for step in range(n_steps):
             feed, doc, lab = make_feed(rs, model, B, L_max, F, kind)
             pre = "step%d/" % step
-            out[pre + "features"] = feed[model.letor_features_name]
+            out[pre + "features"] = feed[model.letor_features_name].astype(feat_dtype)
             out[pre + "docids"] = doc
             out[pre + "labels"] = lab
             grads_seen.clear()
@@ -170,11 +178,13 @@ def run_case(ultra, name, algo, F, L_train, L_max, B, hidden, kind, n_steps):
                     out[pre + "grad_prop/" + n] = g.numpy().copy()
                 for n, g in zip(names, grads_seen[1]):
                     out[pre + "grad/" + n] = g.numpy().copy()
-                out.update(state_to_np(model.propensity_model.state_dict(), pre + "param_prop/"))
+                if not compact:
+                    out.update(state_to_np(model.propensity_model.state_dict(), pre + "param_prop/"))
             else:
                 for n, g in zip(names, grads_seen[0]):
                     out[pre + "grad/" + n] = g.numpy().copy()
-            out.update(state_to_np(model.model.state_dict(), pre + "param/"))
+            if not compact:
+                out.update(state_to_np(model.model.state_dict(), pre + "param/"))
             if algo in ("pairdebias", "lambdarank"):
                 out[pre + "t_plus"] = model.t_plus.detach().numpy().copy()
                 out[pre + "t_minus"] = model.t_minus.detach().numpy().copy()

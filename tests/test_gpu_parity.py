@@ -1,9 +1,10 @@
 """GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI / the plugin classes, against
 (a) the committed golden vectors produced by the unmodified reference and (b) the CPU oracle on seeded inputs.
 
-Tolerance (tests/helpers.py): |a - ref| <= 1e-5 * max(|ref|, mean|ref|) for scores and losses' gradients w.r.t.
-the scores; parameter gradients accumulate over M = L*B rows and are held to 5e-5 on the same scale (the fp32
-reference itself differs from an fp64 evaluation by ~3e-6 on scores).
+Tolerance (tests/helpers.py, BASELINE.json north_star "within 1e-5 rel fp32"): |a - ref| <= 1e-5 * max(|ref|, mean|ref|)
+for scores, the losses' gradients w.r.t. the scores, the losses themselves, the parameter gradients (which accumulate
+over M = L*B rows) and the parameters after the optimizer step (the fp32 reference itself differs from an fp64
+evaluation by ~3e-6 on scores).
 """
 import json
 import os
@@ -86,18 +87,18 @@ def test_train_steps_match_reference(name, tmp_path):
         feed = make_feed(model, g[pre + "features"], g[pre + "docids"], g[pre + "labels"])
         loss, _, _ = model.train(feed)
         ref_loss = float(g[pre + "loss"])
-        assert abs(loss - ref_loss) <= 2e-5 * abs(ref_loss), (name, step, loss, ref_loss)
+        assert abs(loss - ref_loss) <= 1e-5 * abs(ref_loss), (name, step, loss, ref_loss)
         gref = sub(g, pre + "grad/")
         floor = grad_floor(gref)
         total = np.sqrt(sum(float((v.astype(np.float64) ** 2).sum()) for v in gref.values()))
         coef = min(1.0, 5.0 / (total + 1e-6))          # the plugin leaves the CLIPPED gradient in .grad
         for n, ref in gref.items():
             got = named[n].grad.detach().cpu().numpy()
-            assert_close(got, ref * coef, 5e-5, "%s step %d grad %s" % (name, step, n), floor * coef)
+            assert_close(got, ref * coef, 1e-5, "%s step %d grad %s" % (name, step, n), floor * coef)
         for n, ref in sub(g, pre + "param/").items():
             ok = np.abs(gref[n]) > 1e-3 * floor         # see tests/test_oracle_vs_golden.py on zero gradients
             got = named[n].detach().cpu().numpy()
-            assert_close(got[ok], ref[ok], 1e-4, "%s step %d param %s" % (name, step, n))
+            assert_close(got[ok], ref[ok], 1e-5, "%s step %d param %s" % (name, step, n))
         if algo in ("pairdebias", "lambdarank"):
             assert_close(model.t_plus.cpu().numpy(), g[pre + "t_plus"], 2e-5, "t_plus")
             assert_close(model.t_minus.cpu().numpy(), g[pre + "t_minus"], 2e-5, "t_minus")
@@ -107,10 +108,14 @@ def test_train_steps_match_reference(name, tmp_path):
             pcoef = min(1.0, 5.0 / (ptotal + 1e-6))
             pfloor = 0.1 * float(np.abs(pg["linear_layer.weight"]).max())
             lw = model.propensity_model.linear_layer
-            assert_close(lw.weight.grad.cpu().numpy(), pg["linear_layer.weight"] * pcoef, 5e-5, "dprop_w")
-            assert_close(lw.bias.grad.cpu().numpy(), pg["linear_layer.bias"] * pcoef, 5e-5, "dprop_b", pfloor * pcoef)
+            assert_close(lw.weight.grad.cpu().numpy(), pg["linear_layer.weight"] * pcoef, 1e-5, "dprop_w")
+            # the DenoisingNet bias gradient is sum_l ELU'(.) g_l with sum_l g_l == 0 (softmax shift invariance): a
+            # cancelling sum whose fp32 value in the REFERENCE already carries ~1e-5 of rounding noise on this scale
+            assert_close(lw.bias.grad.cpu().numpy(), pg["linear_layer.bias"] * pcoef, 3e-5, "dprop_b", pfloor * pcoef)
         # restart every step from the reference's parameters: Adagrad's sign-like first steps amplify rounding
         # noise on mathematically-zero gradients (identically in the reference)
+        if not sub(g, pre + "param/"):
+            continue                                    # compact golden (single step, no post-step parameters stored)
         model.model.load_state_dict({k: torch.from_numpy(v) for k, v in sub(g, pre + "param/").items()})
         if algo == "dla":
             model.propensity_model.load_state_dict(
@@ -176,7 +181,7 @@ def test_mlp_forward_backward_vs_oracle(F, hidden, L, B):
         ref = g64[n]
         got = grads[off:off + ref.size].reshape(ref.shape)
         off += ref.size
-        assert_close(got, ref, 5e-5, "grad " + n, floor)
+        assert_close(got, ref, 1e-5, "grad " + n, floor)
     # run-to-run determinism (fixed-order reductions)
     eng.forward(feats_dev, docid_dev, L, B, training=True)
     grads2 = eng.backward(feats_dev, docid_dev, L, B, _dev(dsc)).cpu().numpy()

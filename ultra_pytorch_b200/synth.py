@@ -58,7 +58,7 @@ def make_feed(seed, F, L, B, labels="click", pad_tail=0):
 
 
 def exp_settings(workload):
-    w = WORKLOADS[workload]
+    w = WORKLOADS[workload] if isinstance(workload, str) else workload
     hp = "propensity_estimator_json=%s" % IPW_JSON if w["algo"] == "IPWrank" else ""
     return {
         "learning_algorithm": "ultra_pytorch_b200.learning_algorithm.%s" % w["algo"],
