@@ -188,6 +188,17 @@ UB200_API int ub200_clip_update(float* params, float* grads, float* state_sum, s
 UB200_API int ub200_pl_sample(const float* scores, const int32_t* docid, int n_docs, int B, int L, float tau,
                     unsigned long long seed, unsigned long long offset, int32_t* perm, void* stream);
 
+/* ---- N2: validation metrics on the device -----------------------------------------------------------------
+ * Replaces remove_padding_for_metric_eval (base_algorithm.py:88-116) and the per-list part of the reference's metric
+ * code (ultra/utils/metrics.py:191-336, 456-495): scores of PAD documents (docid == n_docs; docid may be NULL) are
+ * masked to -100000, every list is ranked (stable, descending) and  out[b] = { ndcg@topn[0..n) | err@topn[0..n) | mrr }
+ * is written ([B, 2 n_topn + 1] floats; n_topn <= 8).  discount[r] = 1 / log2(r + 2) is supplied by the caller.
+ * *flag is set to 1 when a label is not an integer in [0, 30] (gains are formed as exact powers of two).  The batch
+ * means are left to the caller (B x n values instead of B x L scores cross the bus). */
+UB200_API int ub200_rank_metrics(const float* scores, const float* labels, const int32_t* docid, int n_docs, int B, int L,
+                       const float* discount, const int* topn, int n_topn, float max_label, float* out, int* flag,
+                       void* stream);
+
 /* ---- N1: click simulation + batch assembly on the device ----------------------------------------------------------
  * Replaces ClickSimulationFeed.get_batch (click_simulation_feed.py:101-174) + PositionBiasedModel.sampleClicksForOneList
  * (click_models.py:80-110) for a data set resident in HBM.  init_list [nq, L] i32 (row ids, < 0 = PAD), rel [nq, L] f32

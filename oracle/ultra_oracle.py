@@ -312,6 +312,61 @@ def prsrank(scores, labels, ipw_table, sigma=1.0, dt=np.float32):
 # ----------------------------------------------------------------------------------------------
 # A7: clip_grad_norm_ + Adagrad / SGD  (base_algorithm.py:208-226, dla.py:141-166)
 # ----------------------------------------------------------------------------------------------
+def rank_metrics_per_list(scores_bl, labels_bl, docids_bl, n_docs, topn, max_label):
+    """Per-list NDCG@n / ERR@n / MRR exactly as the reference's torch-CPU code evaluates them for one list
+    (ultra/learning_algorithm/base_algorithm.py:88-116 PAD masking; ultra/utils/metrics.py:224-265 label validation,
+    :191-221 DCG, :456-495 NDCG, :300-336 ERR, :268-298 MRR), in float32 with torch's CPU rules: cumsum / cumprod
+    accumulate in double and round every prefix to float, everything else is float32 op by op; the sort is the stable
+    descending one.  Returns [B, 2 n + 1] float32: ndcg | err | mrr (the batch means are left to the caller)."""
+    f32 = np.float32
+    s = np.asarray(scores_bl, dtype=f32).copy()
+    y = np.asarray(labels_bl, dtype=f32).copy()
+    B, L = s.shape
+    if docids_bl is not None:
+        s[np.asarray(docids_bl) == n_docs] = f32(-100000.0)
+    topn = [min(int(n), L) for n in topn]
+    n = len(topn)
+    # the discount table comes from torch itself (metrics.py:212): torch's vectorised log2 and numpy's differ in the
+    # last bit for some ranks, and the point of this function is bit-fidelity to the reference's CPU arithmetic
+    import torch
+    disc = (torch.tensor(1) / torch.log2(torch.arange(L, dtype=torch.float) + 2.0)).numpy()
+    out = np.zeros((B, 2 * n + 1), dtype=f32)
+    for b in range(B):
+        p, v = s[b].copy(), y[b].copy()
+        bad = ~(v >= 0)
+        mn = p.min()
+        v[bad] = 0
+        p[bad] = f32(f32(-1e-6) + mn)
+        order = np.argsort(-p.astype(np.float64), kind="stable")
+        ideal = np.argsort(-v.astype(np.float64), kind="stable")
+        ys, yi = v[order], v[ideal]
+        cd = ci = 0.0
+        dcg, idcg = {}, {}
+        for r in range(max(topn)):
+            cd += float(f32(f32(f32(2.0) ** ys[r] - f32(1.0)) * disc[r]))
+            ci += float(f32(f32(f32(2.0) ** yi[r] - f32(1.0)) * disc[r]))
+            dcg[r], idcg[r] = f32(cd), f32(ci)
+        for q, t in enumerate(topn):
+            out[b, q] = f32(0) if idcg[t - 1] == 0 else f32(dcg[t - 1] / idcg[t - 1])
+        cp = 1.0
+        err = [f32(0)] * n
+        mrr = f32(0)
+        for r in range(L):
+            rel = f32(f32(f32(2.0) ** ys[r] - f32(1.0)) / f32(2.0 ** max_label))
+            om = f32(f32(1.0) - rel)
+            cp *= float(om)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                nonrel = f32(f32(cp) / om)
+            rr = f32(f32(1.0) / f32(r + 1))
+            for q, t in enumerate(topn):
+                rrq = rr if r < t else f32(rr * f32(0))
+                err[q] = f32(err[q] + f32(f32(f32(rel * nonrel) * rrq) * f32(1.0)))
+            mrr = max(mrr, f32((f32(1.0) if ys[r] >= 1.0 else f32(0.0)) * rr))
+        out[b, n:2 * n] = err
+        out[b, 2 * n] = mrr
+    return out
+
+
 def clip_grad_norm(grads, names, max_norm, dt=np.float32):
     """Returns (total_norm, clipped grads).  torch: coef = max_norm/(norm+1e-6) clamped to 1, always applied."""
     total = np.sqrt(sum((np.linalg.norm(grads[n].astype(dt).reshape(-1)) ** 2 for n in names))).astype(dt)

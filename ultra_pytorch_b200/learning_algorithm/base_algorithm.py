@@ -231,18 +231,34 @@ class B200Algorithm(_reference_base()):
             scores = eng.forward(st.feats, st.docid.view(-1), L, st.B, training=False)
             self.output = scores.clone()
         if not is_online_simulation:
-            out_host = self.output.cpu()
-            self.last_d2h_bytes = out_host.numel() * 4
-            docid_bl = np.stack([np.asarray(input_feed[self.docid_inputs_name[i]]) for i in range(L)], axis=1)
-            # same memory layout as the reference (a TRANSPOSED view of the [L, B] stack, base_algorithm.py:181-182):
-            # torch reduces strided tensors in a layout-dependent order, and the metrics must be bit-identical
-            self.labels = torch.from_numpy(np.transpose(
-                np.asarray([np.asarray(input_feed[self.labels_name[i]], dtype=np.float32) for i in range(L)])))
-            pad_removed = self.remove_padding_for_metric_eval(torch.from_numpy(docid_bl), out_host)
-            for metric in self.exp_settings['metrics']:
-                topn = self.exp_settings['metrics_topn']
-                metric_values = b200_metrics.make_ranking_metric_fn(metric, topn)(self.labels, pad_removed, None)
-                for n, metric_value in zip(topn, metric_values):
+            wanted = list(self.exp_settings['metrics'])
+            topn = [int(n) for n in self.exp_settings['metrics_topn']]
+            on_device = [m for m in wanted if m in b200_metrics.DEVICE_METRICS]
+            host_vals = {}
+            if on_device:
+                # N2: PAD masking (base_algorithm.py:88-116), ranking and the per-list DCG / ERR / MRR chains run on the
+                # device; B x (2 n + 1) floats come back instead of the B x L scores
+                per_list, flag = b200_metrics.per_list_metrics(self.output, st.labels, st.docid, st.n_docs,
+                                                               [min(n, L) for n in topn])
+                host = torch.cat([per_list.view(-1), flag.to(torch.float32)]).cpu()
+                self.last_d2h_bytes = host.numel() * 4
+                if host[-1].item() != 0:
+                    on_device = []                 # labels that are not small integers: the reference's module takes over
+                else:
+                    host_vals = b200_metrics.batch_means(host[:-1].view(st.B, -1), L, topn)
+            rest = [m for m in wanted if m not in on_device]
+            if rest:
+                out_host = self.output.cpu()
+                self.last_d2h_bytes = out_host.numel() * 4
+                docid_bl = np.stack([np.asarray(input_feed[self.docid_inputs_name[i]]) for i in range(L)], axis=1)
+                # same memory layout as the reference (a TRANSPOSED view of the [L, B] stack, base_algorithm.py:181-182)
+                self.labels = torch.from_numpy(np.transpose(
+                    np.asarray([np.asarray(input_feed[self.labels_name[i]], dtype=np.float32) for i in range(L)])))
+                pad_removed = self.remove_padding_for_metric_eval(torch.from_numpy(docid_bl), out_host)
+                for metric in rest:
+                    host_vals[metric] = b200_metrics.reference_metric_fn(metric, topn)(self.labels, pad_removed, None)
+            for metric in wanted:
+                for n, metric_value in zip(topn, host_vals[metric]):
                     self.create_summary('%s_%d' % (metric, n), '%s_%d' % (metric, n), metric_value.item(), False)
         return None, self.output, self.eval_summary
 
