@@ -41,6 +41,20 @@ for B, L in ((256, 40), (65536, 40), (1 << 20, 40), (1 << 18, 200)):
     out.append({"kernel": "K2 softmax_ce<IPW>", "B": B, "L": L, "ms": round(ms, 4), "algorithmic_GBs": round(byts / ms / 1e6, 1),
                 "hbm_peak_GBs": hbm, "frac": round(byts / ms / 1e6 / hbm, 4)})
     del s, y, d
+for B, L in ((256, 20), (1 << 20, 20), (1 << 18, 100)):
+    # DLA (both losses + DenoisingNet): bytes/list = 12 L + 8 as for K2 (the propensity logits are L shared floats)
+    s = torch.randn(B, L, device="cuda")
+    y = (torch.rand(B, L, device="cuda") < 0.2).float()
+    pw = torch.randn(L, device="cuda") * 0.1
+    pb = torch.zeros(1, device="cuda")
+    d = torch.empty(B, L, device="cuda")
+    dp = torch.zeros(L + 1, device="cuda")
+    sums = torch.zeros(4, device="cuda")
+    ms = timeit(lambda: eng.dla_loss(s, y, pw, pb, d, dp, sums))
+    byts = B * (12 * L + 8)
+    out.append({"kernel": "K2 dla_loss", "B": B, "L": L, "ms": round(ms, 4), "algorithmic_GBs": round(byts / ms / 1e6, 1),
+                "hbm_peak_GBs": hbm, "frac": round(byts / ms / 1e6 / hbm, 4)})
+    del s, y, d
 for B, L, kind in ((256, 200, "lambdarank"), (4096, 200, "lambdarank"), (4096, 40, "lambdarank"), (4096, 200, "pairdebias")):
     s = torch.randn(B, L, device="cuda")
     y = torch.randint(0, 5, (B, L), device="cuda").float() if kind == "lambdarank" else (torch.rand(B, L, device="cuda") < 0.2).float()

@@ -56,7 +56,51 @@ class B200Algorithm(_reference_base()):
     USE_GRAPH_DP = os.environ.get("UB200_GRAPH_DP", "1") != "0"
 
     # ---- construction helpers ---------------------------------------------------------------------
+    @staticmethod
+    def _bootstrap_data_parallel():
+        """Data parallel through the reference's UNMODIFIED main.py: under `torchrun --nproc-per-node N
+        main.py ...` every process is one replica on one GPU.  The first B200 algorithm constructed in such a process
+        (WORLD_SIZE > 1, no process group yet) binds the process to cuda:LOCAL_RANK and joins the NCCL group; every
+        rank samples its own batches (global batch = N x batch_size) and the replicas stay bitwise equal, so the
+        checkpoint main.py writes without any rank guard (main.py:199-214) is rank 0's: on the other ranks
+        `torch.save` of a parameter dictionary is skipped (nothing else in main.py is saved with torch.save)."""
+        import torch.distributed as dist
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world <= 1 or not dist.is_available() or dist.is_initialized():
+            return
+        if os.environ.get("UB200_DP_BOOTSTRAP", "1") == "0":
+            return
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if dist.get_rank() != 0:
+            plain_save = torch.save
+
+            def save_on_rank0_only(obj, f, *a, **kw):
+                if isinstance(obj, dict) and obj and all(isinstance(v, torch.Tensor) for v in obj.values()):
+                    return None
+                return plain_save(obj, f, *a, **kw)
+            torch.save = save_on_rank0_only
+
+    def _register_param_dump(self, engine):
+        """UB200_DP_DUMP=path_with_%d: every rank writes its flat parameter vector there at interpreter exit (used by
+        the 2-rank main.py test to show that the replicas stayed bitwise equal)."""
+        pattern = os.environ.get("UB200_DP_DUMP")
+        if not pattern or getattr(B200Algorithm, "_dump_registered", False):
+            return
+        B200Algorithm._dump_registered = True
+        import atexit
+        import torch.distributed as dist
+
+        def dump():
+            rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+            torch.cuda.synchronize()
+            # the unpatched torch.save: on ranks > 0 the bootstrap skips parameter dictionaries only, a tensor passes
+            torch.save(engine.params.detach().cpu(), pattern % rank)
+        atexit.register(dump)
+
     def _init_common(self, data_set, exp_settings, extra_floats):
+        self._bootstrap_data_parallel()
         self.is_cuda_avail = True                # online feeds call .cpu() on the scores when this is set
         self.cuda = torch.device('cuda')
         self.train_summary = {}
@@ -147,7 +191,17 @@ class B200Algorithm(_reference_base()):
         if not hasattr(model, "engine"):
             raise TypeError("%s is not a B200 ranking model (no .engine): the B200 learning algorithms drive the "
                             "fused kernels directly and have no fallback path" % cls_path)
+        self._register_param_dump(model.engine)
+        self.broadcast_initial_state(model.engine.params)
         return model
+
+    def broadcast_initial_state(self, *tensors):
+        """Data parallel: every replica starts from rank 0's initial values (the reference's main.py seeds nothing, so
+        each process draws its own initial weights; torch's DDP broadcasts at construction for the same reason)."""
+        import torch.distributed as dist
+        if self.world_size() > 1:
+            for t in tensors:
+                dist.broadcast(t, src=0)
 
     @property
     def engine(self):

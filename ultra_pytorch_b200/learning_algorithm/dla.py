@@ -61,6 +61,7 @@ class DLA(B200Algorithm):
         # for the same torch seed
         self.propensity_model = DenoisingNet(self.rank_list_size, torch.device('cuda', torch.cuda.current_device()))
         self.model = self.create_model(self.feature_size)
+        self.broadcast_initial_state(self.propensity_model.flat)
         if self.hparams.propensity_learning_rate < 0:
             self.propensity_learning_rate = float(self.hparams.learning_rate)
         else:
