@@ -199,6 +199,18 @@ UB200_API int ub200_rank_metrics(const float* scores, const float* labels, const
                        const float* discount, const int* topn, int n_topn, float max_label, float* out, int* flag,
                        void* stream);
 
+/* ---- RegressionEM (N4) ----------------------------------------------------------------------------------------
+ * Replaces RegressionEM.train's E-step / sampling / loss / M-step statistics (ultra/learning_algorithm/
+ * regression_EM.py:122-183) for the scores [B, L] the ranker produced (the constant sigmoid_prob_b of the reference is 0):
+ * posteriors from the current propensities prop[L], pseudo-labels ceil(p_r1 - u) with u from Philox (seed, offset) or
+ * from `uniforms` [B, L] (parity tests), dscores = sigmoid(s) - label (UN-normalised: the mean over B*L is applied by the
+ * optimizer scale), out = [sum of the BCE-with-logits terms, B*L, S_0..S_{L-1}] with S_l the M-step sums.  Workspace:
+ * ub200_pair_workspace_bytes(B, L).  ub200_regem_update applies prop_l <- (1 - em_step) prop_l + em_step S_l / B. */
+UB200_API int ub200_regression_em(const float* scores, const float* clicks, int B, int L, const float* prop,
+                        const float* uniforms, unsigned long long seed, unsigned long long offset, float* dscores,
+                        float* out, void* workspace, size_t workspace_bytes, void* stream);
+UB200_API int ub200_regem_update(float* prop, const float* out, int L, float em_step, void* stream);
+
 /* ---- N1: click simulation + batch assembly on the device ----------------------------------------------------------
  * Replaces ClickSimulationFeed.get_batch (click_simulation_feed.py:101-174) + PositionBiasedModel.sampleClicksForOneList
  * (click_models.py:80-110) for a data set resident in HBM.  init_list [nq, L] i32 (row ids, < 0 = PAD), rel [nq, L] f32

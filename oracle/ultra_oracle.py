@@ -312,6 +312,25 @@ def prsrank(scores, labels, ipw_table, sigma=1.0, dt=np.float32):
 # ----------------------------------------------------------------------------------------------
 # A7: clip_grad_norm_ + Adagrad / SGD  (base_algorithm.py:208-226, dla.py:141-166)
 # ----------------------------------------------------------------------------------------------
+def regression_em(scores, clicks, propensity, uniforms, em_step=0.05, dt=np.float32):
+    """One RegressionEM step on given scores (ultra/learning_algorithm/regression_EM.py:122-183; `sigmoid_prob_b` is the
+    constant 0): E-step posteriors, pseudo-labels ceil(p_r1 - u) (:20-34), mean BCE-with-logits and its gradient, M-step."""
+    s = np.asarray(scores, dtype=dt)
+    c = np.asarray(clicks, dtype=dt)
+    e = np.asarray(propensity, dtype=dt).reshape(1, -1)
+    gamma = sigmoid(s).astype(dt)
+    den = 1 - e * gamma
+    p_e1_r0 = e * (1 - gamma) / den
+    p_e0_r1 = (1 - e) * gamma / den
+    p_r1 = c + (1 - c) * p_e0_r1
+    labels = np.ceil(p_r1 - np.asarray(uniforms, dtype=dt)).astype(dt)
+    bce = np.maximum(s, 0) - s * labels + np.log1p(np.exp(-np.abs(s)))
+    n = s.size
+    new_prop = (1 - em_step) * e + em_step * np.mean(c + (1 - c) * p_e1_r0, axis=0, keepdims=True)
+    return {"loss": float(bce.astype(np.float64).sum() / n), "dscores": ((gamma - labels) / n).astype(dt),
+            "labels": labels, "propensity": new_prop.astype(dt)}
+
+
 def rank_metrics_per_list(scores_bl, labels_bl, docids_bl, n_docs, topn, max_label):
     """Per-list NDCG@n / ERR@n / MRR exactly as the reference's torch-CPU code evaluates them for one list
     (ultra/learning_algorithm/base_algorithm.py:88-116 PAD masking; ultra/utils/metrics.py:224-265 label validation,
@@ -391,7 +410,7 @@ def sgd_step(params, grads, names, lr, dt=np.float32):
 # whole train steps (what BaseAlgorithm.train does, per algorithm)
 # ----------------------------------------------------------------------------------------------
 class OracleTrainer:
-    """Replays `train(input_feed)` of NA / IPW / DLA / PairDebias / LambdaRank on the CPU.
+    """Replays `train(input_feed)` of NA / IPW / DLA / PairDebias / LambdaRank / PRSrank / RegressionEM on the CPU.
 
     State mirrors the reference objects: params (ranker state_dict), Adagrad accumulators (persistent for
     NA/IPW/PairDebias/LambdaRank, re-created every step for DLA, dla.py:153-154), t_plus/t_minus, the
@@ -408,7 +427,8 @@ class OracleTrainer:
         self.state_sum = {n: np.zeros_like(self.params[n]) for n in self.names}
         self.F = feature_size
         self.L = L_train
-        defaults = {"na": 0.05, "ipw": 0.05, "dla": 0.05, "pairdebias": 0.005, "lambdarank": 0.05, "prsrank": 0.05}
+        defaults = {"na": 0.05, "ipw": 0.05, "dla": 0.05, "pairdebias": 0.005, "lambdarank": 0.05, "prsrank": 0.05,
+                    "regem": 0.05}
         self.lr = defaults[algo] if learning_rate is None else learning_rate
         self.max_norm = max_gradient_norm
         self.sigma, self.em_step, self.reg_p = sigma, em_step, reg_p
@@ -419,6 +439,9 @@ class OracleTrainer:
         if algo in ("pairdebias", "lambdarank"):
             self.t_plus = np.ones(L_train, dtype=dt)
             self.t_minus = np.ones(L_train, dtype=dt)
+        if algo == "regem":
+            self.propensity = (np.ones(L_train, dtype=dt) * dt(0.9)).reshape(1, -1)     # regression_EM.py:94-97
+            self.uniforms = None            # the caller provides the step's uniform draws [B, L_train]
         self.last = {}
 
     def scores(self, features, docids_bl):
@@ -453,6 +476,10 @@ class OracleTrainer:
         elif self.algo == "prsrank":
             r = prsrank(s, y, self.ipw_table, self.sigma, dt)
             loss, ds = r["loss"], r["dscores"]
+        elif self.algo == "regem":
+            r = regression_em(s, y, self.propensity, self.uniforms, self.em_step, dt)
+            loss, ds = r["loss"], r["dscores"]
+            self.propensity = r["propensity"]
         else:
             raise ValueError(self.algo)
         grads = dnn_backward(scores_grad_to_rows(ds), cache, self.params, self.n_layers, dt)

@@ -33,6 +33,7 @@ ALGOS = {
     "pairdebias": "ultra.learning_algorithm.PairDebias",
     "lambdarank": "ultra.learning_algorithm.LambdaRank",
     "prsrank": "ultra.learning_algorithm.PRSrank",
+    "regem": "ultra.learning_algorithm.RegressionEM",
 }
 
 # name, algo, F, L_train (selection_bias_cutoff), L_max (max_candidate_num), B, hidden, label kind, n_steps
@@ -54,6 +55,9 @@ CASES = [
     # BASELINE.json shapes (configs 3, 5, 4 and the config-2 net under the pairwise loss): every hidden layer runs on the
     # tensor cores, so reference-generated numbers go THROUGH the tcgen05 kernels for DLA / LambdaRank / PairDebias too.
     # Stored compactly (trailing True): features as float32 (they are float32-exact), no post-step parameters.
+    # RegressionEM samples pseudo-labels: the uniform draws of get_bernoulli_sample are recorded with the golden
+    ("regem_small", "regem", 10, 6, 8, 8, [16, 8], "click", 3),
+    ("regem_c2net", "regem", 136, 40, 40, 16, [256, 128, 64], "click", 1, True),
     ("dla_c3like", "dla", 700, 20, 20, 16, [512, 256, 128], "click", 1, True),
     ("dla_c5like", "dla", 220, 100, 100, 8, [512, 256, 128], "click", 1, True),
     ("lambdarank_c4like", "lambdarank", 136, 200, 200, 8, [512, 256, 128], "graded", 1, True),
@@ -121,6 +125,16 @@ def run_case(ultra, name, algo, F, L_train, L_max, B, hidden, kind, n_steps, com
     }
     cls = ultra.utils.find_class(ALGOS[algo])
     model = cls(ds, exp_settings)
+    drawn = []
+    if algo == "regem":
+        # record the uniform draws of the pseudo-label sampler (regression_EM.py:20-34; same expression, CPU branch)
+        mod = sys.modules["ultra.learning_algorithm.regression_EM"]
+
+        def recording_sampler(probs):
+            u = torch.rand(probs.shape)
+            drawn.append(u)
+            return torch.ceil(probs - u)
+        mod.get_bernoulli_sample = recording_sampler
     # give LayerNorm affine params non-trivial values so that their gradients are exercised
     with torch.no_grad():
         for n, p in model.model.named_parameters():
@@ -168,8 +182,12 @@ def run_case(ultra, name, algo, F, L_train, L_max, B, hidden, kind, n_steps, com
             out[pre + "docids"] = doc
             out[pre + "labels"] = lab
             grads_seen.clear()
+            drawn.clear()
             loss, _, _ = model.train(dict(feed))
             out[pre + "loss"] = np.float64(loss)
+            if algo == "regem":
+                out[pre + "uniform"] = drawn[0].numpy().copy()
+                out[pre + "propensity"] = model.propensity.detach().numpy().copy()
             names = [n for n, _ in model.model.named_parameters()]
             if algo == "dla":
                 # separate_gradient_update clips the propensity net first, then the ranker (dla.py:161-163)

@@ -30,6 +30,8 @@ SETTINGS = {
     # every feed replaced by its drop-in, data sets resident in HBM (train: batches assembled on the device)
     "ipw_all_b200feeds": ("ultra_pytorch_b200.learning_algorithm.IPWrank",
                           "ultra_pytorch_b200.input_layer.ClickSimulationFeed"),
+    # RegressionEM
+    "regem": ("ultra_pytorch_b200.learning_algorithm.RegressionEM", "ultra.input_layer.ClickSimulationFeed"),
     # the Linear ranker
     "ipw_linear": ("ultra_pytorch_b200.learning_algorithm.IPWrank", "ultra.input_layer.ClickSimulationFeed"),
 }

@@ -20,7 +20,7 @@ from tests.helpers import assert_close, golden_names, grad_floor, load_golden, s
 pytestmark = pytest.mark.gpu
 
 ALGO_CLASS = {"na": "NavieAlgorithm", "ipw": "IPWrank", "dla": "DLA", "pairdebias": "PairDebias",
-              "lambdarank": "LambdaRank", "prsrank": "PRSrank"}
+              "lambdarank": "LambdaRank", "prsrank": "PRSrank", "regem": "RegressionEM"}
 
 
 def _dev(x, dtype=torch.float32):
@@ -126,6 +126,8 @@ def test_train_steps_match_reference(name, tmp_path):
     for step in range(int(g["meta_n_steps"])):
         pre = "step%d/" % step
         feed = make_feed(model, g[pre + "features"], g[pre + "docids"], g[pre + "labels"])
+        if algo == "regem":
+            model.replay_uniforms = _dev(g[pre + "uniform"])      # the reference's own pseudo-label draws
         loss, _, _ = model.train(feed)
         ref_loss = float(g[pre + "loss"])
         assert abs(loss - ref_loss) <= 1e-5 * abs(ref_loss), (name, step, loss, ref_loss)
@@ -140,6 +142,8 @@ def test_train_steps_match_reference(name, tmp_path):
             ok = np.abs(gref[n]) > 1e-3 * floor         # see tests/test_oracle_vs_golden.py on zero gradients
             got = named[n].detach().cpu().numpy()
             assert_close(got[ok], ref[ok], 1e-5, "%s step %d param %s" % (name, step, n))
+        if algo == "regem":
+            assert_close(model.propensity.cpu().numpy(), g[pre + "propensity"], 1e-5, "propensity")
         if algo in ("pairdebias", "lambdarank"):
             assert_close(model.t_plus.cpu().numpy(), g[pre + "t_plus"], 2e-5, "t_plus")
             assert_close(model.t_minus.cpu().numpy(), g[pre + "t_minus"], 2e-5, "t_minus")
@@ -461,3 +465,28 @@ def test_ranker_build_and_checkpoint_interchange(tmp_path):
     assert len(outs) == doc.shape[1] and tuple(outs[0].shape) == (doc.shape[0], 1)
     got = torch.cat(outs, dim=1).cpu().numpy()
     assert_close(got, g["valid/scores"], 1e-5, "build() scores")
+
+
+def test_regression_em_sampler_distribution():
+    """Without replayed draws the pseudo-labels come from Philox: their frequencies must match p_r1 (5 sigma), and two
+    consecutive steps must not repeat the same draws."""
+    from ultra_pytorch_b200.engine import RankerEngine
+    eng = RankerEngine(4, [])
+    B, L = 65536, 10
+    rs = np.random.RandomState(3)
+    s = _dev(np.tile(rs.randn(1, L).astype(np.float32), (B, 1)))
+    c = torch.zeros(B, L, device="cuda")
+    prop = _dev(np.linspace(0.9, 0.2, L).astype(np.float32))
+    d1, d2 = torch.empty(B, L, device="cuda"), torch.empty(B, L, device="cuda")
+    out = torch.zeros(2 + L, device="cuda")
+    eng.regression_em(s, c, prop, None, 1234, 1, d1, out)
+    eng.regression_em(s, c, prop, None, 1234, 2, d2, out)
+    gamma = torch.sigmoid(s[0])
+    lab1 = (gamma[None, :] - d1)                      # dscores = sigmoid(s) - label
+    lab2 = (gamma[None, :] - d2)
+    assert set(torch.unique(lab1.round()).tolist()) <= {0.0, 1.0}
+    p = ((1 - prop) * gamma / (1 - prop * gamma)).cpu().numpy().astype(np.float64)
+    freq = lab1.round().mean(dim=0).cpu().numpy()
+    sigma = np.sqrt(p * (1 - p) / B)
+    assert np.all(np.abs(freq - p) <= 5 * sigma + 1e-6), (freq, p)
+    assert not torch.equal(lab1.round(), lab2.round())

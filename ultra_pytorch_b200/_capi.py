@@ -26,6 +26,8 @@ SIGNATURES = {
     "ub200_convert_f64_f32_host": (_i, [_vp, _vp, _sz, _i]),
     "ub200_stage_feed": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _sz, _vp, _i, _i, _vp]),
     "ub200_rank_metrics": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _ip, _i, ctypes.c_float, _vp, _vp, _vp]),
+    "ub200_regression_em": (_i, [_vp, _vp, _i, _i, _vp, _vp, ctypes.c_ulonglong, ctypes.c_ulonglong, _vp, _vp, _vp, _sz, _vp]),
+    "ub200_regem_update": (_i, [_vp, _vp, _i, ctypes.c_float, _vp]),
     "ub200_set_tc_mode": (_i, [_i]),
     "ub200_mlp_param_count": (_sz, [_i, _ip, _i]),
     "ub200_mlp_workspace_bytes": (_sz, [_i, _i, _i, _ip, _i, _i]),

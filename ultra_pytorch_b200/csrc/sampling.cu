@@ -159,6 +159,91 @@ __global__ void __launch_bounds__(256) click_batch_kernel(const int32_t* __restr
 
 using namespace ub200;
 
+// ---------------------------------------------------------------------------------------------------------------
+// RegressionEM (ultra/learning_algorithm/regression_EM.py:108-190): E-step posteriors, Bernoulli pseudo-labels, the
+// pointwise sigmoid cross-entropy and its gradient, and the M-step statistics of the examination propensities, one pass
+// ---------------------------------------------------------------------------------------------------------------
+// Per element (list b, position l), with gamma = sigmoid(s) and e = propensity[l]:
+//   P(E=1,R=0 | C=0) = e (1 - gamma) / (1 - e gamma)        P(E=0,R=1 | C=0) = (1 - e) gamma / (1 - e gamma)
+//   p_r1 = c + (1 - c) P(E=0,R=1|C=0)        label = ceil(p_r1 - u), u ~ U[0,1)   (get_bernoulli_sample, :20-34)
+//   loss += BCEWithLogits(s, label)           ds = sigmoid(s) - label              (mean over B*L: the caller divides)
+//   S_l  += c + (1 - c) P(E=1,R=0|C=0)       (M-step: e_l <- (1 - eta) e_l + eta S_l / B)
+// One warp per list, lanes over the positions; per-warp position accumulators in shared memory, block partials and a
+// last-block reduction in fixed order (deterministic).  out = [sum loss, B*L, S_0 .. S_{L-1}]: sums over the lists,
+// so data-parallel ranks add their buffers before dividing.  u comes from Philox keyed by (seed, offset, b, l), or from
+// `uniforms` [B, L] when given (parity tests replay the reference's draws).
+__global__ void __launch_bounds__(256) regression_em_kernel(const float* __restrict__ scores,
+                                                             const float* __restrict__ clicks, int B, int L,
+                                                             const float* __restrict__ prop,
+                                                             const float* __restrict__ uniforms,
+                                                             unsigned long long seed, unsigned long long offset,
+                                                             float* __restrict__ dscores, float* __restrict__ out,
+                                                             unsigned int* counter, float* __restrict__ partials) {
+    griddep_launch();
+    griddep_wait();
+    extern __shared__ float sm[];                  // [nw][L] position accumulators
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    float* acc = sm + (size_t)wid * L;
+    for (int l = lane; l < L; l += kWarp) acc[l] = 0.f;
+    __syncwarp();
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    float loss = 0.f;
+    for (int b = blockIdx.x * nw + wid; b < B; b += gridDim.x * nw) {
+        for (int l = lane; l < L; l += kWarp) {
+            const size_t i = (size_t)b * L + l;
+            const float s = scores[i], c = clicks[i], e = prop[l];
+            const float gamma = 1.0f / (1.0f + expf(-s));
+            const float den = 1.0f - e * gamma;
+            const float p_e1_r0 = e * (1.0f - gamma) / den;
+            const float p_e0_r1 = (1.0f - e) * gamma / den;
+            const float p_r1 = c + (1.0f - c) * p_e0_r1;
+            float u;
+            if (uniforms) {
+                u = uniforms[i];
+            } else {
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)l, (uint32_t)b, (uint32_t)offset, (uint32_t)(offset >> 32)), key);
+                u = (float)(r.x >> 8) * (1.0f / 16777216.0f);          // [0, 1) like torch.rand
+            }
+            const float label = ceilf(p_r1 - u);
+            loss += fmaxf(s, 0.f) - s * label + log1pf(expf(-fabsf(s)));
+            dscores[i] = gamma - label;
+            acc[l] += c + (1.0f - c) * p_e1_r0;
+        }
+    }
+    loss = warp_sum(loss);
+    __shared__ float red[8];
+    if (lane == 0) red[wid] = loss;
+    __syncthreads();
+    const int width = 2 + L;
+    float* mine = partials + (size_t)blockIdx.x * width;
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int q = 0; q < nw; ++q) t += red[q];
+        mine[0] = t;
+        mine[1] = 0.f;
+    }
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+        float t = 0.f;
+        for (int q = 0; q < nw; ++q) t += sm[(size_t)q * L + l];
+        mine[2 + l] = t;
+    }
+    if (last_block_ticket(counter, gridDim.x)) {
+        for (int k = threadIdx.x; k < width; k += blockDim.x) {
+            float t = 0.f;
+            for (int q = 0; q < (int)gridDim.x; ++q) t += partials[(size_t)q * width + k];
+            out[k] = (k == 1) ? (float)B * (float)L : t;
+        }
+    }
+}
+
+// M-step (regression_EM.py:181-183): e_l <- (1 - eta) e_l + eta * S_l / B with B = out[1] / L (summed over the ranks)
+__global__ void regem_update_kernel(float* __restrict__ prop, const float* __restrict__ out, int L, float em_step) {
+    griddep_launch();
+    griddep_wait();
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < L) prop[l] = (1.0f - em_step) * prop[l] + em_step * (out[2 + l] / (out[1] / (float)L));
+}
+
 extern "C" UB200_API int ub200_click_batch(const int32_t* init_list, const float* rel, int nq, int L,
                                            const float* exam_prob, int n_exam, const float* click_prob, int n_cp,
                                            int oracle_mode, int check_validation, int max_rounds, int B, int pad_id,
@@ -189,5 +274,33 @@ extern "C" UB200_API int ub200_pl_sample(const float* scores, const int32_t* doc
     launch_k(pl_sample_kernel, grid, threads, smem, static_cast<cudaStream_t>(stream), scores, docid, n_docs, B, L, tau,
              seed, offset, perm);
     UB_LAUNCH_CHECK("pl_sample_kernel");
+    return 0;
+}
+
+extern "C" UB200_API int ub200_regression_em(const float* scores, const float* clicks, int B, int L, const float* prop,
+                                             const float* uniforms, unsigned long long seed, unsigned long long offset,
+                                             float* dscores, float* out, void* workspace, size_t workspace_bytes,
+                                             void* stream) {
+    UB_CHECK(B > 0 && L > 0, 1, "regression_em: bad B=%d L=%d", B, L);
+    UB_CHECK(scores && clicks && prop && dscores && out && workspace, 2, "regression_em: null pointer");
+    const int grid = (B + 7) / 8 < 2 * kNumSMs ? (B + 7) / 8 : 2 * kNumSMs;
+    const size_t need = 256 + sizeof(float) * (size_t)(2 * kNumSMs) * (2 + L);
+    UB_CHECK(workspace_bytes >= need, 3, "regression_em: workspace too small (%zu < %zu)", workspace_bytes, need);
+    unsigned int* counter = static_cast<unsigned int*>(workspace);
+    float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
+    const size_t smem = sizeof(float) * 8 * (size_t)L;
+    UB_CHECK(smem <= 200 * 1024, 4, "regression_em: list length %d too large", L);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(regression_em_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    launch_k(regression_em_kernel, grid, 256, smem, static_cast<cudaStream_t>(stream), scores, clicks, B, L, prop, uniforms,
+             seed, offset, dscores, out, counter, partials);
+    UB_LAUNCH_CHECK("regression_em_kernel");
+    return 0;
+}
+
+extern "C" UB200_API int ub200_regem_update(float* prop, const float* out, int L, float em_step, void* stream) {
+    UB_CHECK(prop && out && L > 0, 2, "regem_update: bad arguments");
+    launch_k(regem_update_kernel, (L + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), prop, out, L, em_step);
+    UB_LAUNCH_CHECK("regem_update_kernel");
     return 0;
 }

@@ -449,6 +449,16 @@ class RankerEngine(object):
         check(lib.ub200_pairdebias(_ptr(scores), _ptr(clicks), B, L, _ptr(t_plus), _ptr(t_minus), _ptr(dscores),
                                    _ptr(out), _ptr(ws), ws.numel(), _stream()), "ub200_pairdebias")
 
+    def regression_em(self, scores, clicks, prop, uniforms, seed, offset, dscores, out):
+        B, L = scores.shape
+        ws = self.loss_ws(B, L)
+        check(lib.ub200_regression_em(_ptr(scores), _ptr(clicks), B, L, _ptr(prop), _ptr(uniforms), int(seed), int(offset),
+                                      _ptr(dscores), _ptr(out), _ptr(ws), ws.numel(), _stream()), "ub200_regression_em")
+
+    def regem_update(self, prop, out, em_step):
+        check(lib.ub200_regem_update(_ptr(prop), _ptr(out), prop.numel(), float(em_step), _stream()),
+              "ub200_regem_update")
+
     def em_update(self, t_plus, t_minus, out, em_step, reg_p, safe_div):
         check(lib.ub200_em_update(_ptr(t_plus), _ptr(t_minus), _ptr(out), t_plus.numel(), float(em_step),
                                   float(reg_p), int(bool(safe_div)), _stream()), "ub200_em_update")
