@@ -61,6 +61,25 @@ for c in range(12):
     if t[1, 16 + 2 * c] > 0:
         ev.append((us(t[1, 16 + 2 * c]), "mma:   chunk L%d.%d operands ready" % (c // 4, c % 4)))
         ev.append((us(t[1, 17 + 2 * c]), "mma:   chunk L%d.%d issued" % (c // 4, c % 4)))
+if "--bwd" in sys.argv:
+    dsc = torch.randn(B, L, device="cuda")
+    for rep in range(3):
+        eng.forward(feats, docid, L, B, training=True)
+        eng.backward(feats, docid, L, B, dsc)
+        torch.cuda.synchronize()
+    lib.ub200_f16_timeline(buf)
+    t = np.array(list(buf), dtype=np.int64).reshape(3, 64)
+    t0 = t[0, 20]
+    nl = len(hidden)
+    ev = [(us(t[0, 20]), "bwd worker: begin (after setup)"), (us(t[0, 36]), "bwd worker: final-layer sums exchanged"),
+          (us(t[0, 21]), "bwd worker: final step done (dZ stored, A operand written)"), (us(t[0, 39]), "bwd worker: end")]
+    for q in range(nl - 1, -1, -1):
+        if t[0, 25 + 4 * q] > t0:
+            ev.append((us(t[0, 25 + 4 * q]), "bwd worker: dZ_%d stores drained" % q))
+    for q in range(nl - 1, 0, -1):
+        ev.append((us(t[0, 22 + 4 * q]), "bwd worker: dgrad_%d accumulator ready" % q))
+        ev.append((us(t[0, 24 + 4 * q]), "bwd worker: dgrad_%d LN-backward sums exchanged" % q))
+        ev.append((us(t[0, 23 + 4 * q]), "bwd worker: dgrad_%d epilogue done" % q))
 if "--wgrad" in sys.argv:
     dsc = torch.randn(B, L, device="cuda")
     for rep in range(3):

@@ -628,6 +628,7 @@ __device__ __forceinline__ float emit_dz(const BwdArgs& a, int q, float* dz, int
         }
     }
     if (threadIdx.x == 0) bulk_wait_read0();
+    if (threadIdx.x == 0) TL(0, 25 + 4 * q);
     {   // tensor-wide max for the weight-gradient operand scale: max is order independent, so the atomic is deterministic
         const float wm = warp_max(mx);
         if (lane == 0 && wm > 0.f) atomicMax(a.dzmax[q], __float_as_uint(wm));
@@ -696,6 +697,7 @@ __device__ __forceinline__ float bwd_final(const BwdArgs& a, YPipe& yp, int trow
         s2 = ((p0.y + p1.y) + (p2.y + p3.y)) / (float)N;
     }
     worker_bar();
+    if (threadIdx.x == 0) TL(0, 36);
     const float f = ds * rs;
 #pragma unroll
     for (int it = 0; it < NQ; ++it) {
@@ -756,6 +758,7 @@ __device__ __forceinline__ float bwd_epilogue(const BwdArgs& a, int q, float inv
         s2 = ((p0.y + p1.y) + (p2.y + p3.y)) / (float)N;
     }
     worker_bar();
+    if (threadIdx.x == 0) TL(0, 24 + 4 * q);
     if (!HOLD) {
         const int i0 = grow - trow;
         float mx = 0.f;
@@ -898,21 +901,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd16_kernel(const __grid_constan
         YPipe yp{bars->y_full, bars->y_empty, 0u};
         float inv;
         const int nqf = a.N[a.nl - 1] >> 6;
+        if (tid == 0) TL(0, 20);
         if (nqf == 1) inv = bwd_final<1>(a, yp, trow, cg, grow, lane, a_ring, bars);
         else if (nqf == 2) inv = bwd_final<2>(a, yp, trow, cg, grow, lane, a_ring, bars);
         else if (nqf == 3) inv = bwd_final<3>(a, yp, trow, cg, grow, lane, a_ring, bars);
         else inv = bwd_final<4>(a, yp, trow, cg, grow, lane, a_ring, bars);
+        if (tid == 0) TL(0, 21);
         for (int q = a.nl - 1; q >= 1; --q) {
             mbar_wait(&bars->accum[q], 0);
             __syncwarp();
             tc_fence_after();
+            if (tid == 0) TL(0, 22 + 4 * q);
             const int nq = a.N[q - 1] >> 6;
             if (nq == 1) inv = bwd_epilogue<1>(a, q, inv, yp, tlane, trow, cg, grow, lane, a_ring, b_ring, bars);
             else if (nq == 2) inv = bwd_epilogue<2>(a, q, inv, yp, tlane, trow, cg, grow, lane, a_ring, b_ring, bars);
             else if (nq == 3) inv = bwd_epilogue<3>(a, q, inv, yp, tlane, trow, cg, grow, lane, a_ring, b_ring, bars);
             else if (nq == 4) inv = bwd_epilogue<4>(a, q, inv, yp, tlane, trow, cg, grow, lane, a_ring, b_ring, bars);
             else inv = bwd_epilogue<8>(a, q, inv, yp, tlane, trow, cg, grow, lane, a_ring, b_ring, bars);
+            if (tid == 0) TL(0, 23 + 4 * q);
         }
+        if (tid == 0) TL(0, 39);
     }
     __syncwarp();
     tc_fence_before();
