@@ -22,7 +22,7 @@ if "--build" in sys.argv:
                           ["--cudart", "static", "-lcuda", "-Xcompiler", "-pthread"])
     print(OUT)
     sys.exit(0)
-os.environ["UB200_LIB"] = OUT
+os.environ["UB200_LIB"] = os.environ.get("UB200_TL_LIB", OUT)
 import numpy as np, torch
 from ultra_pytorch_b200 import _capi
 from ultra_pytorch_b200.engine import RankerEngine

@@ -237,14 +237,13 @@ __device__ __forceinline__ void tma_layer(const uint16_t* img, int rows_total, i
 }
 
 // issues the MMAs of one layer: D[h] (+)= A[it] * B[it][h]^T over the contraction chunks; kc = contraction length.
-// ONE thread runs this; the other lanes of its warp wait at the final block barrier.  (Running the loop warp-converged
-// with an elected lane issuing - the usual CUTLASS shape - dead-locked on hardware in two different formulations, and
-// the compiler's uniform-operand "waterfall" code around the unrolled form below produced out-of-range descriptors in
-// the backward kernel (compute-sanitizer), so the backward pass keeps the plain loop.)  FAST = the K = 16 steps
-// unrolled with descriptors advanced by adds and no memory clobber on the MMA asm: every instruction's latency is
-// exposed in a single-threaded loop, and the plain form pays ~160 cycles per tcgen05.mma (in-kernel timeline) against
-// ~80 for the unrolled one; the tensor core itself needs 32 - 128.
-template <bool DUAL, bool FAST>
+// The whole MMA warp runs the loop CONVERGED and one elected lane issues (the CUTLASS shape): loop state and descriptor
+// arithmetic are warp-uniform, so the three tcgen05.mma of a K = 16 step leave back to back.  Two earlier forms cost
+// real time: a single-lane (divergent) loop exposes every register-to-uniform move (80 - 160 cycles per MMA against
+// 32 - 128 to execute one, in-kernel timeline), and converged loops that passed the 64-bit descriptors as values hung
+// or produced out-of-range descriptors (the compiler's uniform-operand waterfall code) - hence the 32-bit halves
+// assembled inside the asm (mma_f16_lohi) and every commit inside the elected branch.
+template <bool DUAL>
 __device__ __forceinline__ void mma_layer_impl(uint32_t tmem_base, int kc, int bn, int nh, uint8_t* a_ring,
                                                uint8_t* b_ring, uint64_t* a_full, uint64_t* a_empty, uint64_t* b_full,
                                                uint64_t* b_empty, uint64_t* accum, int tl_base) {
@@ -252,11 +251,13 @@ __device__ __forceinline__ void mma_layer_impl(uint32_t tmem_base, int kc, int b
     const int sb = b_stage_bytes(bn), nst = b_stages(bn);
     const uint32_t idesc = make_idesc_f16(bn, 0, 0);
     const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_ring);
+    const uint64_t d0 = make_smem_desc(0, 16, 1024);             // K-major, 128B swizzle: LBO 16, SBO 1024
+    const uint32_t dhi = (uint32_t)(d0 >> 32), dlo0 = (uint32_t)d0;
     int g = 0;
     for (int it = 0; it < nch; ++it) {
         const int sa = it % A_STAGES;
         mbar_wait(&a_full[sa], (uint32_t)(it / A_STAGES) & 1u);
-        const uint32_t a_hi = a_base + sa * A_STAGE, a_lo = a_hi + A_HALF;
+        const uint32_t a_hi = dlo0 | (((a_base + sa * A_STAGE) >> 4) & 0x3FFFu), a_lo = a_hi + (A_HALF >> 4);
         const int rem = kc - it * 64;
         const int nk = rem >= 64 ? 4 : (rem + 15) >> 4;
         for (int h = 0; h < nh; ++h, ++g) {
@@ -264,58 +265,40 @@ __device__ __forceinline__ void mma_layer_impl(uint32_t tmem_base, int kc, int b
             mbar_wait(&b_full[s], (uint32_t)(g / nst) & 1u);
             tc_fence_after();
             TL(1, 16 + 2 * (tl_base + it));
-            const uint32_t b_hi = b_base + s * sb, b_lo = b_hi + (uint32_t)bn * 128u;
+            const uint32_t b_hi = dlo0 | (((b_base + s * sb) >> 4) & 0x3FFFu), b_lo = b_hi + (uint32_t)((bn * 128) >> 4);
             const uint32_t d_main = tmem_base + (uint32_t)h * 256u;
             const uint32_t d_corr = DUAL ? tmem_base + 256u : d_main;
-            if (FAST) {
-                const uint64_t dah0 = make_smem_desc(a_hi, 16, 1024), dal0 = make_smem_desc(a_lo, 16, 1024);
-                const uint64_t dbh0 = make_smem_desc(b_hi, 16, 1024), dbl0 = make_smem_desc(b_lo, 16, 1024);
+            if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     if (k < nk) {
-                        const uint64_t dah = desc_advance(dah0, k * 32), dal = desc_advance(dal0, k * 32);
-                        const uint64_t dbh = desc_advance(dbh0, k * 32), dbl = desc_advance(dbl0, k * 32);
-                        const uint32_t acc = (it | k) != 0 ? 1u : 0u;
+                        const uint32_t acc = (it | k) != 0 ? 1u : 0u;      // one K = 16 step = 32 bytes along the row
                         if (DUAL) {
-                            mma_f16(d_corr, dal, dbh, idesc, acc);
-                            mma_f16(d_corr, dah, dbl, idesc, 1u);
-                            mma_f16(d_main, dah, dbh, idesc, acc);
+                            mma_f16_lohi(d_corr, a_lo + 2 * k, dhi, b_hi + 2 * k, dhi, idesc, acc);
+                            mma_f16_lohi(d_corr, a_hi + 2 * k, dhi, b_lo + 2 * k, dhi, idesc, 1u);
+                            mma_f16_lohi(d_main, a_hi + 2 * k, dhi, b_hi + 2 * k, dhi, idesc, acc);
                         } else {
-                            mma_f16(d_main, dah, dbh, idesc, acc);
-                            mma_f16(d_main, dal, dbh, idesc, 1u);
-                            mma_f16(d_main, dah, dbl, idesc, 1u);
+                            mma_f16_lohi(d_main, a_hi + 2 * k, dhi, b_hi + 2 * k, dhi, idesc, acc);
+                            mma_f16_lohi(d_main, a_lo + 2 * k, dhi, b_hi + 2 * k, dhi, idesc, 1u);
+                            mma_f16_lohi(d_main, a_hi + 2 * k, dhi, b_lo + 2 * k, dhi, idesc, 1u);
                         }
                     }
                 }
-            } else {
-                for (int k = 0; k < nk; ++k) {
-                    const uint64_t dah = make_smem_desc(a_hi + k * 32, 16, 1024), dal = make_smem_desc(a_lo + k * 32, 16, 1024);
-                    const uint64_t dbh = make_smem_desc(b_hi + k * 32, 16, 1024), dbl = make_smem_desc(b_lo + k * 32, 16, 1024);
-                    const uint32_t acc = (it | k) != 0 ? 1u : 0u;
-                    if (DUAL) {
-                        mma_f16_sync(d_corr, dal, dbh, idesc, acc);
-                        mma_f16_sync(d_corr, dah, dbl, idesc, 1u);
-                        mma_f16_sync(d_main, dah, dbh, idesc, acc);
-                    } else {
-                        mma_f16_sync(d_main, dah, dbh, idesc, acc);
-                        mma_f16_sync(d_main, dal, dbh, idesc, 1u);
-                        mma_f16_sync(d_main, dah, dbl, idesc, 1u);
-                    }
-                }
+                mma_commit(&b_empty[s]);
+                if (h == nh - 1) mma_commit(&a_empty[sa]);
+                if (h == nh - 1 && it == nch - 1) mma_commit(accum);
             }
-            mma_commit(&b_empty[s]);
+            __syncwarp();
             TL(1, 17 + 2 * (tl_base + it));
         }
-        mma_commit(&a_empty[sa]);
     }
-    mma_commit(accum);
 }
-template <bool FAST>
+// called by ALL lanes of the MMA warp
 __device__ __forceinline__ void mma_layer(uint32_t tmem_base, int kc, int bn, int nh, int dual, uint8_t* a_ring,
                                           uint8_t* b_ring, uint64_t* a_full, uint64_t* a_empty, uint64_t* b_full,
                                           uint64_t* b_empty, uint64_t* accum, int tl_base = 0) {
-    if (dual) mma_layer_impl<true, FAST>(tmem_base, kc, bn, nh, a_ring, b_ring, a_full, a_empty, b_full, b_empty, accum, tl_base);
-    else mma_layer_impl<false, FAST>(tmem_base, kc, bn, nh, a_ring, b_ring, a_full, a_empty, b_full, b_empty, accum, tl_base);
+    if (dual) mma_layer_impl<true>(tmem_base, kc, bn, nh, a_ring, b_ring, a_full, a_empty, b_full, b_empty, accum, tl_base);
+    else mma_layer_impl<false>(tmem_base, kc, bn, nh, a_ring, b_ring, a_full, a_empty, b_full, b_empty, accum, tl_base);
 }
 
 // combine the 4 column groups' (mean, M2) partials of a row (each over `cnt` values) in fixed order -> (mean, rstd)
@@ -385,13 +368,16 @@ __device__ __forceinline__ void fwd_epilogue(const FwdArgs& a, int q, int n0, ui
             // tensor stores: full 128-byte lines leave the SM instead of 32 scattered 16-byte pieces per instruction
             // (a thread-per-row global store cost 3.3 us of the layer-0 epilogue, in-kernel timeline).  Rows >= M are
             // clipped by the tensor map.  Buffers alternate (it & 1) inside the idle A ring.
+            if (it >= 2) {                                // this buffer's previous store (chunk it - 2) has drained;
+                if (threadIdx.x == 0) bulk_wait_read1();  // the store of chunk it - 1 may still be in flight
+                worker_bar();
+            }
             uint8_t* stg = a_ring + (it & 1) * A_STAGE + (cg >> 1) * 16384 + trow * 128;
 #pragma unroll
             for (int p = 0; p < 4; ++p)
                 *reinterpret_cast<float4*>(stg + ((((cg & 1) * 4 + p) ^ (trow & 7)) << 4)) =
                     make_float4(y[it * 16 + 4 * p], y[it * 16 + 4 * p + 1], y[it * 16 + 4 * p + 2], y[it * 16 + 4 * p + 3]);
             fence_proxy_async();
-            if (threadIdx.x == 0) bulk_wait_read0();      // the store issued from the buffer written next has drained
             worker_bar();
             if (threadIdx.x == 0) {
                 const uint8_t* src = a_ring + (it & 1) * A_STAGE;
@@ -503,15 +489,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd16_kernel(const __grid_constan
                 TL(2, 2 * q + 1);
             }
     } else if (warp == MMA_WARP) {
-        if (lane == 0)
-            for (int q = 0; q < a.nl; ++q) {
-                const int K = q == 0 ? a.K0 : a.N[q - 1];
-                const int bn = q == 0 ? a.bn0 : a.N[q];
-                TL(1, 2 * q);
-                mma_layer<true>(tmem_base, K, bn, 1, a.dual[q], a_ring, b_ring, bars->a_full[q], bars->a_empty[q],
-                                bars->b_full[q], bars->b_empty[q], &bars->accum[q], 4 * q);
-                TL(1, 2 * q + 1);
-            }
+        for (int q = 0; q < a.nl; ++q) {
+            const int K = q == 0 ? a.K0 : a.N[q - 1];
+            const int bn = q == 0 ? a.bn0 : a.N[q];
+            TL(1, 2 * q);
+            mma_layer(tmem_base, K, bn, 1, a.dual[q], a_ring, b_ring, bars->a_full[q], bars->a_empty[q], bars->b_full[q],
+                      bars->b_empty[q], &bars->accum[q], 4 * q);
+            TL(1, 2 * q + 1);
+        }
       }
     } else {
         regs_worker();
@@ -616,9 +601,12 @@ __device__ __forceinline__ float emit_dz(const BwdArgs& a, int q, float* dz, int
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) mx = fmaxf(mx, fabsf(dz[it * 16 + i]));
+        if (it >= 2) {                                    // this buffer's previous store (chunk it - 2) has drained
+            if (threadIdx.x == 0) bulk_wait_read1();
+            worker_bar();
+        }
         sts_chunk16(a_ring + (it & 1) * A_STAGE, trow, cg, dz + it * 16);
         fence_proxy_async();
-        if (threadIdx.x == 0) bulk_wait_read0();          // the store issued from the buffer written next has drained
         worker_bar();
         if (threadIdx.x == 0) {
             const uint8_t* src = a_ring + (it & 1) * A_STAGE;
@@ -777,9 +765,12 @@ __device__ __forceinline__ float bwd_epilogue(const BwdArgs& a, int q, float inv
                 o[i] = row_ok ? rs * (d - s1 - xh * s2) * elu_grad_from_out(yv[i]) : 0.f;
                 mx = fmaxf(mx, fabsf(o[i]));
             }
+            if (it >= 2) {
+                if (threadIdx.x == 0) bulk_wait_read1();
+                worker_bar();
+            }
             sts_chunk16(a_ring + (it & 1) * A_STAGE, trow, cg, o);
             fence_proxy_async();
-            if (threadIdx.x == 0) bulk_wait_read0();
             worker_bar();
             if (threadIdx.x == 0) {
                 const uint8_t* src = a_ring + (it & 1) * A_STAGE;
@@ -859,13 +850,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd16_kernel(const __grid_constan
                 tma_layer(a.wd[q], kq, 0, bn, nh, a.N[q] >> 6, b_ring, bars->b_full[q], bars->b_empty[q]);
             }
       } else if (warp == MMA_WARP) {
-        if (lane == 0)
-            for (int q = a.nl - 1; q >= 1; --q) {
-                const int kq = a.N[q - 1];
-                const int nh = kq > 256 ? 2 : 1, bn = kq / nh;
-                mma_layer<false>(tmem_base, a.N[q], bn, nh, 0, a_ring, b_ring, bars->a_full[q], bars->a_empty[q],
-                                 bars->b_full[q], bars->b_empty[q], &bars->accum[q]);
-            }
+        for (int q = a.nl - 1; q >= 1; --q) {
+            const int kq = a.N[q - 1];
+            const int nh = kq > 256 ? 2 : 1, bn = kq / nh;
+            mma_layer(tmem_base, a.N[q], bn, nh, 0, a_ring, b_ring, bars->a_full[q], bars->a_empty[q], bars->b_full[q],
+                      bars->b_empty[q], &bars->accum[q]);
+        }
       } else if (warp == Y_WARP) {
         // activation loader: the chunk sequence the workers consume - Y_{nl-1} for the final-layer step, then for every
         // data gradient q the input activations Y_{q-1} of its LayerNorm-backward (twice when they are streamed)
@@ -1077,33 +1067,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad16_kernel(WgArgs a) {
 
     if (warp >= NW) {
         regs_control();
-        if (warp == MMA_WARP && lane == 0) {
+        if (warp == MMA_WARP) {
+            // converged warp, elected lane issues (see mma_layer_impl).  MN-major tiles: LBO = next 64 MN elements
+            // (1024 B), SBO = next 8 contraction rows (atoms x 1024 B); one K = 16 step = two 8-row groups.
             const int stage = 2 * WG_A_HALF + 2 * L.bn * 128;
             const uint32_t sbo_b = (uint32_t)(L.bn / 64) * 1024u;
             const uint32_t idesc = make_idesc_f16(n_mma, 1, 1);
             const uint32_t ring_base = smem_u32(ring);
+            const uint64_t da0 = make_smem_desc(0, 1024, 2048), db0 = make_smem_desc(0, 1024, sbo_b);
+            const uint32_t a_dhi = (uint32_t)(da0 >> 32), a_dlo = (uint32_t)da0;
+            const uint32_t b_dhi = (uint32_t)(db0 >> 32), b_dlo = (uint32_t)db0;
             for (int it = 0; it < n_chunks; ++it) {
                 const int s = it % WG_STAGES;
                 mbar_wait(&bars->full[s], (uint32_t)(it / WG_STAGES) & 1u);
                 tc_fence_after();
-                // MN-major tiles: LBO = next 64 MN elements (1024 B), SBO = next 8 contraction rows
-                const uint32_t a_hi = ring_base + s * stage, a_lo = a_hi + WG_A_HALF;
-                const uint32_t b_hi = a_hi + 2 * WG_A_HALF, b_lo = b_hi + (uint32_t)L.bn * 128u;
+                if (it < 6) TL(1, 40 + 2 * it);
+                const uint32_t a_hi = a_dlo | (((ring_base + s * stage) >> 4) & 0x3FFFu), a_lo = a_hi + (WG_A_HALF >> 4);
+                const uint32_t b_hi = b_dlo | (((ring_base + s * stage + 2 * WG_A_HALF) >> 4) & 0x3FFFu);
+                const uint32_t b_lo = b_hi + (uint32_t)((L.bn * 128) >> 4);
                 const int rem = r_end - (r_begin + it * 64);
                 const int nk = rem >= 64 ? 4 : (rem + 15) >> 4;
-                for (int k = 0; k < nk; ++k) {
-                    // one K = 16 step = two 8-row groups
-                    const uint64_t dah = make_smem_desc(a_hi + k * 4096, 1024, 2048), dal = make_smem_desc(a_lo + k * 4096, 1024, 2048);
-                    const uint64_t dbh = make_smem_desc(b_hi + k * 2 * sbo_b, 1024, sbo_b), dbl = make_smem_desc(b_lo + k * 2 * sbo_b, 1024, sbo_b);
-                    const uint32_t acc = (it | k) != 0 ? 1u : 0u;
-                    mma_f16_sync(tmem_base + 256, dal, dbh, idesc, acc);
-                    mma_f16_sync(tmem_base + 256, dah, dbl, idesc, 1u);
-                    mma_f16_sync(tmem_base, dah, dbh, idesc, acc);
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (k < nk) {
+                            const uint32_t ka = (uint32_t)(k * 4096) >> 4, kb = (uint32_t)(k * 2 * sbo_b) >> 4;
+                            const uint32_t acc = (it | k) != 0 ? 1u : 0u;
+                            mma_f16_lohi(tmem_base + 256, a_lo + ka, a_dhi, b_hi + kb, b_dhi, idesc, acc);
+                            mma_f16_lohi(tmem_base + 256, a_hi + ka, a_dhi, b_lo + kb, b_dhi, idesc, 1u);
+                            mma_f16_lohi(tmem_base, a_hi + ka, a_dhi, b_hi + kb, b_dhi, idesc, acc);
+                        }
+                    }
+                    mma_commit(&bars->empty[s]);
+                    if (it == n_chunks - 1) mma_commit(&bars->accum);
+                    if (it < 6) TL(1, 41 + 2 * it);
                 }
-                mma_commit(&bars->empty[s]);
-                if (it < 6) TL(1, 41 + 2 * it);
+                __syncwarp();
             }
-            mma_commit(&bars->accum);
+            if (n_chunks == 0 && elect_one()) mma_commit(&bars->accum);      // (wgrad_plan never produces an empty slice)
+            __syncwarp();
         }
     } else {
         regs_worker();

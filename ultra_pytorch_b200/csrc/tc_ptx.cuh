@@ -230,6 +230,21 @@ __device__ __forceinline__ void mma_f16_sync(uint32_t tmem_d, uint64_t desc_a, u
         : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// tcgen05.mma with the two shared-memory descriptors given as 32-bit halves (the high half - SBO, version, swizzle - is
+// the same for every MMA of a layer; the low half carries the start address and LBO): the 64-bit values are assembled
+// inside the asm, so the compiler never has to move a 64-bit per-thread value into a uniform register pair (its
+// "waterfall" code for that miscompiled the unrolled issue loops: out-of-range descriptors, compute-sanitizer)
+__device__ __forceinline__ void mma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        :
+        : "r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate));
+}
 // one lane of a fully converged warp (warp-uniform issue loops keep their operands in uniform registers)
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -286,6 +301,8 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, in
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all bulk stores committed by this thread have finished READING shared memory (the buffers may be reused)
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... all but the most recently committed one
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // byte offset of 16-byte chunk `c` (0..7) of row `r` inside a [rows x 128 B] tile with the 128B swizzle
 __device__ __forceinline__ uint32_t swz128(uint32_t r, uint32_t c) {
