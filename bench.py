@@ -352,7 +352,7 @@ def main_b200(args):
 
     # ---- e2e leg: public train(input_feed) with host feeds (wall clock around K train() calls + a final synchronize;
     # >= 5 repeats, median) ----
-    for i in range(6):
+    for i in range(12):              # two staging buffer pairs, each seen three times before its CUDA graph exists
         model.train(feeds[i % n_host])
     e2e_times = []
     while len(e2e_times) < 5 or sum(e2e_times) < args.min_seconds:

@@ -82,6 +82,25 @@ UB200_API int ub200_stage_feed(const double* feats_host, int n_docs, int F, cons
                      const float* const* label_cols_host, int L, int B, void* pinned_host, size_t pinned_bytes,
                      void* device_dst, int n_threads, int n_groups, void* stream);
 
+/* Double-buffered staging (the host side of train(), base_algorithm.py:169-186 + DNN.py:72-75, overlapped with the
+ * device work of the previous step): same packing as ub200_stage_feed, but the copies run on `copy_stream`.  The caller
+ * alternates between two (pinned, device) buffer pairs; `slot_free` (cudaEvent_t, may be NULL) was recorded on
+ * `compute_stream` behind the last kernel that reads this device buffer and is waited for before the first copy;
+ * `ready` (cudaEvent_t) is recorded behind the last copy and `compute_stream` is made to wait for it.
+ * ub200_stage_ids_pipelined is the variant for a data set resident in HBM (ids / labels block only).
+ * ub200_event_record = cudaEventRecord(event, stream). */
+UB200_API int ub200_stage_feed_pipelined(const double* feats_host, int n_docs, int F, const float* const* docid_cols_host,
+                     const float* const* label_cols_host, int L, int B, void* pinned_host, size_t pinned_bytes,
+                     void* device_dst, int n_threads, int n_groups, void* copy_stream, void* compute_stream,
+                     void* slot_free, void* ready);
+UB200_API int ub200_stage_ids_pipelined(const float* const* docid_cols_host, const float* const* label_cols_host, int L,
+                     int B, int max_id, void* pinned_host, size_t pinned_bytes, void* device_dst, void* copy_stream,
+                     void* compute_stream, void* slot_free, void* ready);
+UB200_API int ub200_event_record(void* event, void* stream);
+/* diagnostics: wall-clock stamps (ns since entry) of the last ub200_stage_feed* call - [0] ids packed, [2 + k] copy of
+ * group k issued, [31] return */
+UB200_API int ub200_stage_timeline(long long* out32);
+
 /* ---- K1: DNN ranker forward / backward ----------------------------------------------------------------
  * Replaces: host gather base_algorithm.py:148-152, cat + f64->f32 cast DNN.py:72-73, the nn.Sequential of
  * [LayerNorm -> Linear -> ELU] x n_hidden + LayerNorm -> Linear(1) DNN.py:43-55,77, split/cat DNN.py:87-88 +
@@ -167,8 +186,9 @@ UB200_API int ub200_em_update(float* t_plus, float* t_minus, const float* out, i
  * norm_out[0] receives the pre-clip norm.
  */
 /* Early read-back of a step's scalars (the reference's loss.item(), e.g. ipw_rank.py:181-182): copies n <= 32 floats
- * from src (device) to host_dst and then stores the launch count (dev_counter, device, zero-initialised) into
- * host_seq; host_dst / host_seq are MAPPED PINNED host memory (UVA: the host pointer is valid on the device).  The
+ * from src (device) to host_dst[(c & 1) * 32 ...] and then stores the launch count c (dev_counter, device,
+ * zero-initialised, incremented by every launch) into host_seq; host_dst (2 x 32 floats) / host_seq are MAPPED PINNED
+ * host memory (UVA: the host pointer is valid on the device).  The
  * host polls host_seq instead of synchronising the stream, so train() returns while the backward pass and the optimizer
  * step of the batch are still running; everything later on the stream stays ordered behind them. */
 UB200_API int ub200_publish(const float* src, int n, float* host_dst, unsigned int* host_seq, unsigned int* dev_counter,

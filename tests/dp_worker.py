@@ -49,9 +49,10 @@ def main():
         torch.manual_seed(0)
         model = getattr(la, algo)(ds, settings)
         init = {k: v.clone() for k, v in model.model.state_dict().items()}
-        for step in range(4):                      # step 2+ runs through the two-graph DP path
+        dp_losses = []
+        for step in range(4):                      # step 2+ runs through the CUDA-graph DP path
             feed = synth.make_feed(100 * step + rank, F, L, B, "click")
-            model.train(feed)
+            dp_losses.append(model.train(feed)[0])
         flat = model.engine.params.clone()
         gathered = [torch.empty_like(flat) for _ in range(world)]
         dist.all_gather(gathered, flat)
@@ -65,9 +66,19 @@ def main():
             la.B200Algorithm.world_size = staticmethod(lambda: 1)
             ref = getattr(la, algo)(ds, settings)
             ref.model.load_state_dict(init)
+            ref_losses = []
             for step in range(4):
                 feeds = [synth.make_feed(100 * step + r, F, L, B, "click") for r in range(world)]
-                ref.train(merged_feed(feeds, L))
+                ref_losses.append(ref.train(merged_feed(feeds, L))[0])
+            # data-parallel train() returns the exact global loss one step late (base_algorithm.py: LAG_LOSS_DP); the
+            # first call returns its own
+            lag = 1 if la.B200Algorithm.LAG_LOSS_DP else 0
+            want = [ref_losses[max(0, k - lag)] for k in range(4)]
+            loss_err = max(abs(a - b) / max(abs(b), 1e-12) for a, b in zip(dp_losses, want))
+            print("DP %s: losses %s vs single-GPU (lag %d) %s -> rel err %.2e" % (algo, dp_losses, lag, want, loss_err),
+                  flush=True)
+            if loss_err > 1e-4:
+                err = max(err, 1.0)
             a, b = flat, ref.engine.params
             # exclude the entries whose gradient is mathematically zero under shift-invariant losses (last LayerNorm
             # bias, last linear bias): Adagrad turns their rounding noise into +-lr moves (tests/test_oracle_vs_golden.py)
@@ -76,7 +87,7 @@ def main():
             for name, off, shape in model.engine.layer_slices():
                 if name in ("layer_norm%d.bias" % nl, "linear%d.bias" % nl):
                     keep[off:off + int(np.prod(shape))] = False
-            err = float((a - b)[keep].abs().max() / b[keep].abs().mean())
+            err = max(err, float((a - b)[keep].abs().max() / b[keep].abs().mean()))
         la.B200Algorithm.world_size = staticmethod(
             lambda: dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1)
         t = torch.tensor([1.0 if same else 0.0, err], device="cuda")

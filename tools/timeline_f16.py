@@ -61,6 +61,11 @@ for c in range(12):
     if t[1, 16 + 2 * c] > 0:
         ev.append((us(t[1, 16 + 2 * c]), "mma:   chunk L%d.%d operands ready" % (c // 4, c % 4)))
         ev.append((us(t[1, 17 + 2 * c]), "mma:   chunk L%d.%d issued" % (c // 4, c % 4)))
+def show(ev):
+    for tt, n in sorted(ev):
+        print("%8.2f us  %s" % (tt, n))
+    print()
+show(ev)
 if "--bwd" in sys.argv:
     dsc = torch.randn(B, L, device="cuda")
     for rep in range(3):
@@ -80,6 +85,7 @@ if "--bwd" in sys.argv:
         ev.append((us(t[0, 22 + 4 * q]), "bwd worker: dgrad_%d accumulator ready" % q))
         ev.append((us(t[0, 24 + 4 * q]), "bwd worker: dgrad_%d LN-backward sums exchanged" % q))
         ev.append((us(t[0, 23 + 4 * q]), "bwd worker: dgrad_%d epilogue done" % q))
+    show(ev)
 if "--wgrad" in sys.argv:
     dsc = torch.randn(B, L, device="cuda")
     for rep in range(3):
@@ -99,5 +105,4 @@ if "--wgrad" in sys.argv:
         if t[1, 40 + 2 * c] > t0:
             ev.append((us(t[1, 40 + 2 * c]), "wgrad mma: chunk %d operands ready" % c))
             ev.append((us(t[1, 41 + 2 * c]), "wgrad mma: chunk %d issued" % c))
-for tt, n in sorted(ev):
-    print("%8.2f us  %s" % (tt, n))
+    show(ev)

@@ -25,6 +25,10 @@ SIGNATURES = {
     "ub200_pack_ids_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _sz]),
     "ub200_convert_f64_f32_host": (_i, [_vp, _vp, _sz, _i]),
     "ub200_stage_feed": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _sz, _vp, _i, _i, _vp]),
+    "ub200_stage_feed_pipelined": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _sz, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "ub200_stage_ids_pipelined": (_i, [_vp, _vp, _i, _i, _i, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "ub200_event_record": (_i, [_vp, _vp]),
+    "ub200_stage_timeline": (_i, [_vp]),
     "ub200_rank_metrics": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _ip, _i, ctypes.c_float, _vp, _vp, _vp]),
     "ub200_regression_em": (_i, [_vp, _vp, _i, _i, _vp, _vp, ctypes.c_ulonglong, ctypes.c_ulonglong, _vp, _vp, _vp, _sz, _vp]),
     "ub200_regem_update": (_i, [_vp, _vp, _i, ctypes.c_float, _vp]),

@@ -13,6 +13,7 @@
 #include <immintrin.h>
 #include <sched.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
 
@@ -41,7 +42,8 @@ namespace {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-constexpr long long kBlock = 16384;      // elements per conversion block (128 KB in, 64 KB out)
+constexpr long long kBlock = 4096;       // elements per conversion block (32 KB in, 16 KB out): a block is ~2 us of one
+                                         // core, so the short first group of a staged feed is done a few us after the start
 constexpr int kMaxGroups = 16;
 
 // ---- f64 -> f32 ---------------------------------------------------------------------------------------------
@@ -68,10 +70,29 @@ __attribute__((target("avx2"))) void cvt_avx2(const double* s, float* d, long lo
     _mm_sfence();
 }
 
+// the same with ordinary stores: the staging buffers are reused every other step and small enough (5.6 MB at config 2)
+// to stay in the last-level cache, where the PCIe read of the H2D copy finds them - no DRAM round trip for the fp32 copy
+__attribute__((target("avx2"))) void cvt_avx2_cached(const double* s, float* d, long long n) {
+    long long i = 0;
+    for (; i + 16 <= n; i += 16) {
+        const __m128 a = _mm256_cvtpd_ps(_mm256_loadu_pd(s + i));
+        const __m128 b = _mm256_cvtpd_ps(_mm256_loadu_pd(s + i + 4));
+        const __m128 c = _mm256_cvtpd_ps(_mm256_loadu_pd(s + i + 8));
+        const __m128 e = _mm256_cvtpd_ps(_mm256_loadu_pd(s + i + 12));
+        _mm256_storeu_ps(d + i, _mm256_set_m128(b, a));
+        _mm256_storeu_ps(d + i + 8, _mm256_set_m128(e, c));
+    }
+    for (; i < n; ++i) d[i] = (float)s[i];
+}
+
 typedef void (*cvt_fn)(const double*, float*, long long);
 cvt_fn pick_cvt() {
     __builtin_cpu_init();
-    return __builtin_cpu_supports("avx2") ? cvt_avx2 : cvt_scalar;
+    if (!__builtin_cpu_supports("avx2")) return cvt_scalar;
+    // streaming stores by default: measured on the B200 hosts, H2D copies out of a staging buffer that the CPUs left in
+    // their caches (UB200_PACK_NT=0) run ~40 % slower than out of DRAM
+    const char* nt = getenv("UB200_PACK_NT");
+    return (nt && nt[0] == '0') ? cvt_avx2_cached : cvt_avx2;
 }
 const cvt_fn g_cvt = pick_cvt();
 
@@ -85,7 +106,13 @@ struct Job {
     long long n = 0, nblocks = 0;
     int n_workers = 0;                      // workers (besides the caller) that should join
     int n_groups = 1;
-    long long blocks_per_group = 1;
+    long long group_first[kMaxGroups + 1] = {0};   // group k = blocks [group_first[k], group_first[k + 1])
+    bool caller_polls_only = false;
+    int group_of(long long b) const {
+        int k = 0;
+        while (k + 1 < n_groups && b >= group_first[k + 1]) ++k;
+        return k;
+    }
 };
 struct Slot {
     Job job;
@@ -116,6 +143,11 @@ public:
     // block it converts and while it waits (used to issue the H2D copies of finished groups)
     template <typename F>
     void run(Job job, F&& on_poll) {
+        run(job, [](Slot&) {}, on_poll);
+    }
+    // `pre` runs on the caller right after the job has been published (the workers are already converting)
+    template <typename P, typename F>
+    void run(Job job, P&& pre, F&& on_poll) {
         std::lock_guard<std::mutex> call_lock(call_mu_);        // one job at a time
         const uint64_t g = gen_.load() + 1;
         Slot& s = slots_[g & 1];
@@ -128,7 +160,10 @@ public:
             std::lock_guard<std::mutex> lk(mu_);
             cv_.notify_all();
         }
-        work(s, job, [&] { on_poll(s); });
+        pre(s);
+        // with enough workers the caller only issues the copies (a cudaMemcpyAsync call costs ~4 us, during which a
+        // converting caller would sit on a block the copy of its group waits for)
+        if (!(job.caller_polls_only && job.n_workers > 0)) work(s, job, [&] { on_poll(s); });
         for (;;) {
             bool all = true;
             for (int k = 0; k < job.n_groups; ++k) all = all && group_complete(s, job, k);
@@ -139,10 +174,7 @@ public:
         }
     }
     static bool group_complete(const Slot& s, const Job& j, int k) {
-        const long long b0 = k * j.blocks_per_group;
-        long long b1 = b0 + j.blocks_per_group;
-        if (b1 > j.nblocks) b1 = j.nblocks;
-        return s.group_done[k].load(std::memory_order_acquire) >= b1 - b0;
+        return s.group_done[k].load(std::memory_order_acquire) >= j.group_first[k + 1] - j.group_first[k];
     }
 
 private:
@@ -153,7 +185,7 @@ private:
             if (b >= j.nblocks) break;
             const long long lo = b * kBlock, hi = lo + kBlock < j.n ? lo + kBlock : j.n;
             g_cvt(j.src + lo, j.dst + lo, hi - lo);
-            s.group_done[b / j.blocks_per_group].fetch_add(1, std::memory_order_release);
+            s.group_done[j.group_of(b)].fetch_add(1, std::memory_order_release);
             after_block();
         }
     }
@@ -222,37 +254,69 @@ Job make_job(const double* src, float* dst, long long n, int n_threads, int n_gr
     j.nblocks = (n + kBlock - 1) / kBlock;
     int w = (n_threads < 1 ? 1 : n_threads) - 1;
     if (w > pool()->max_workers()) w = pool()->max_workers();
-    if (j.nblocks < 4) w = 0;                                  // tiny inputs: not worth waking anybody
+    if (j.nblocks < 16) w = 0;                                 // tiny inputs: not worth waking anybody
     if (w > 0) pool()->ensure(w);
     j.n_workers = w;
     if (n_groups > kMaxGroups) n_groups = kMaxGroups;
     if (n_groups > j.nblocks) n_groups = (int)j.nblocks;
     if (n_groups < 1) n_groups = 1;
-    j.n_groups = n_groups;
-    j.blocks_per_group = (j.nblocks + n_groups - 1) / n_groups;
-    if (j.blocks_per_group < 1) j.blocks_per_group = 1;
-    j.n_groups = j.nblocks ? (int)((j.nblocks + j.blocks_per_group - 1) / j.blocks_per_group) : 0;
+    // Groups that double in size: the copy of the (small) first group starts almost at once and, because converting a
+    // group is faster than copying the one before it (PCIe 5: ~107 us for 5.6 MB, conversion ~60 us on 15 threads), the
+    // copy engine never waits again; every copy costs ~4 us of set-up, so few groups - 1/16, 2/16, 4/16, 9/16 by default.
+    if (j.nblocks == 0) {
+        j.n_groups = 0;
+        return j;
+    }
+    long long unit = j.nblocks >> n_groups;
+    if (unit < 1) unit = 1;
+    int k = 0;
+    long long b = 0;
+    j.group_first[0] = 0;
+    while (k < n_groups - 1 && b + (unit << k) < j.nblocks) {
+        b += unit << k;
+        j.group_first[++k] = b;
+    }
+    j.group_first[++k] = j.nblocks;
+    j.n_groups = k;
     return j;
 }
 
 // returns the number of ids outside [0, max_id] (max_id = the PAD row): the kernels gather feats[id] unchecked, where
 // the reference's np.take raises IndexError (base_algorithm.py:150)
-long long pack_ids(const float* const* docid_cols, const float* const* label_cols, int L, int B, void* dst,
-                   long long max_id) {
+// slice `part` of `parts` of the ids / labels packing (positions [l0, l1) of the ids, queries [b0, b1) of the labels)
+long long pack_ids_part(const float* const* docid_cols, const float* const* label_cols, int L, int B, void* dst,
+                        long long max_id, int part, int parts) {
     int32_t* docid = reinterpret_cast<int32_t*>(dst);                                              // [L, B]
     float* labels = reinterpret_cast<float*>(static_cast<char*>(dst) + (size_t)4 * L * B);         // [B, L]
     long long bad = 0;
-    for (int l = 0; l < L; ++l) {
+    const float hi = (float)max_id;
+    const int l_begin = (int)((long long)L * part / parts), l_end = (int)((long long)L * (part + 1) / parts);
+    const int q_begin = (int)((long long)B * part / parts), q_end = (int)((long long)B * (part + 1) / parts);
+    for (int l = l_begin; l < l_end; ++l) {              // contiguous on both sides: vectorises
         const float* d = docid_cols[l];
-        const float* y = label_cols[l];
+        int32_t* o = docid + (size_t)l * B;
+        long long bad_l = 0;
         for (int b = 0; b < B; ++b) {
             const float v = d[b];
-            bad += !(v >= 0.f && v <= (float)max_id);
-            docid[(size_t)l * B + b] = (int32_t)v;
-            labels[(size_t)b * L + l] = y[b];
+            bad_l += !(v >= 0.f && v <= hi);
+            o[b] = (int32_t)v;
+        }
+        bad += bad_l;
+    }
+    // the transpose [L][B] -> [B][L] in tiles of 32 queries: L read streams of 128 bytes each, contiguous writes
+    for (int b0 = q_begin; b0 < q_end; b0 += 32) {
+        const int b1 = b0 + 32 < q_end ? b0 + 32 : q_end;
+        for (int b = b0; b < b1; ++b) {
+            float* o = labels + (size_t)b * L;
+            for (int l = 0; l < L; ++l) o[l] = label_cols[l][b];
         }
     }
     return bad;
+}
+
+long long pack_ids(const float* const* docid_cols, const float* const* label_cols, int L, int B, void* dst,
+                   long long max_id) {
+    return pack_ids_part(docid_cols, label_cols, L, B, dst, max_id, 0, 1);
 }
 
 }  // namespace
@@ -299,15 +363,24 @@ extern "C" UB200_API int ub200_pack_feed_host(const double* feats, int n_docs, i
 // H2D copy of each finished group of blocks is issued while the rest is still being converted.  Returns after the
 // last copy has been ENQUEUED (stream order makes the data visible to the kernels launched after it); `pinned` may
 // be rewritten once the stream has passed the last copy (the caller syncs once per step for the loss anyway).
-extern "C" UB200_API int ub200_stage_feed(const double* feats, int n_docs, int F, const float* const* docid_cols,
-                                          const float* const* label_cols, int L, int B, void* pinned,
-                                          size_t pinned_bytes, void* device, int n_threads, int n_groups,
-                                          void* stream) {
+// wall-clock stamps of the last stage_feed call (ns since its entry): [0] ids packed, [1] conversion job published,
+// [2 + k] copy of group k issued, [30] job complete, [31] return; read with ub200_stage_timeline (diagnostics)
+static long long g_stage_tl[32];
+static inline long long now_ns() {
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+extern "C" UB200_API int ub200_stage_timeline(long long* out32) {
+    for (int i = 0; i < 32; ++i) out32[i] = g_stage_tl[i];
+    return 0;
+}
+
+static int stage_feed_impl(const double* feats, int n_docs, int F, const float* const* docid_cols,
+                           const float* const* label_cols, int L, int B, void* pinned, size_t pinned_bytes, void* device,
+                           int n_threads, int n_groups, cudaStream_t st) {
     HP_CHECK(pinned && device && docid_cols && label_cols && (feats || n_docs == 0), 2, "stage_feed: null pointer");
     HP_CHECK(L > 0 && B > 0 && F > 0 && n_docs >= 0, 1, "stage_feed: bad sizes");
     const size_t need = ub200_feed_bytes(n_docs, F, L, B);
     HP_CHECK(pinned_bytes >= need, 3, "stage_feed: staging buffer too small (%zu < %zu)", pinned_bytes, need);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     char* hb = static_cast<char*>(pinned);
     char* db = static_cast<char*>(device);
     const size_t off_f = align_up((size_t)8 * L * B, 256);
@@ -317,26 +390,116 @@ extern "C" UB200_API int ub200_stage_feed(const double* feats, int n_docs, int F
     auto copy = [&](size_t b0, size_t b1) {
         if (err == cudaSuccess && b1 > b0) err = cudaMemcpyAsync(db + b0, hb + b0, b1 - b0, cudaMemcpyHostToDevice, st);
     };
-    const long long bad = pack_ids(docid_cols, label_cols, L, B, pinned, n_docs);
-    HP_CHECK(bad == 0, 5, "stage_feed: %lld document ids outside [0, %d]", bad, n_docs);
-    memset(f32 + nf, 0, sizeof(float) * (size_t)F);      // the PAD row
-    copy(0, (size_t)8 * L * B);
+    const long long t_in = now_ns();
+    for (int i = 0; i < 32; ++i) g_stage_tl[i] = 0;
+    long long bad = 0;
     if (nf == 0) {
-        copy(off_f, need);
+        bad = pack_ids(docid_cols, label_cols, L, B, pinned, n_docs);
+        memset(f32, 0, sizeof(float) * (size_t)F);           // the PAD row
+        copy(0, need);
     } else {
-        const Job job = make_job(feats, f32, nf, n_threads, n_groups);
+        // The workers start converting at once.  The caller packs the ids / labels block in four slices, polling for
+        // finished groups in between (the first group of feature rows is usually on its way before the ids are
+        // packed), copies it, and then converts / polls with the others.
+        Job job = make_job(feats, f32, nf, n_threads, n_groups);
+        // with a full set of workers the caller only packs the ids and issues the copies (measured: the first copy
+        // leaves ~12 us earlier than when the caller converts blocks between polls); UB200_PACK_ISSUER=0 / 1 forces it
+        static const int issuer = [] { const char* v = getenv("UB200_PACK_ISSUER"); return v ? (v[0] == '1' ? 1 : 0) : -1; }();
+        job.caller_polls_only = issuer == 1 || (issuer == -1 && job.n_workers >= 7);
         int issued = 0;
-        pool()->run(job, [&](Slot& s) {
+        auto poll = [&](Slot& s) {
             while (issued < job.n_groups && Pool::group_complete(s, job, issued)) {
-                const long long e0 = (long long)issued * job.blocks_per_group * kBlock;
-                long long e1 = e0 + job.blocks_per_group * kBlock;
+                const long long e0 = job.group_first[issued] * kBlock;
+                long long e1 = job.group_first[issued + 1] * kBlock;
                 const bool last = issued == job.n_groups - 1;
                 if (e1 > nf) e1 = nf;
                 copy(off_f + 4 * (size_t)e0, last ? need : off_f + 4 * (size_t)e1);
+                if (issued < 28) g_stage_tl[2 + issued] = now_ns() - t_in;
                 ++issued;
             }
-        });
+        };
+        auto pack_head = [&](Slot& s) {
+            memset(f32 + nf, 0, sizeof(float) * (size_t)F);      // the PAD row (travels with the last group)
+            for (int part = 0; part < 4; ++part) {
+                bad += pack_ids_part(docid_cols, label_cols, L, B, pinned, n_docs, part, 4);
+                poll(s);
+            }
+            copy(0, (size_t)8 * L * B);
+            g_stage_tl[0] = now_ns() - t_in;
+        };
+        pool()->run(job, pack_head, poll);
     }
+    g_stage_tl[31] = now_ns() - t_in;
+    HP_CHECK(bad == 0, 5, "stage_feed: %lld document ids outside [0, %d]", bad, n_docs);
     HP_CHECK(err == cudaSuccess, 100, "stage_feed: cudaMemcpyAsync failed: %s", cudaGetErrorString(err));
+    return 0;
+}
+
+extern "C" UB200_API int ub200_stage_feed(const double* feats, int n_docs, int F, const float* const* docid_cols,
+                                          const float* const* label_cols, int L, int B, void* pinned,
+                                          size_t pinned_bytes, void* device, int n_threads, int n_groups,
+                                          void* stream) {
+    return stage_feed_impl(feats, n_docs, F, docid_cols, label_cols, L, B, pinned, pinned_bytes, device, n_threads,
+                           n_groups, static_cast<cudaStream_t>(stream));
+}
+
+// ---- double-buffered staging: the copies of step i run on their own stream beside the kernels of step i - 1 ----------
+// The caller alternates between two (pinned, device) buffer pairs.  `slot_free` (may be null) is an event recorded on the
+// compute stream behind the last kernel that reads this device buffer: the copy stream waits for it before overwriting.
+// After the last copy `ready` is recorded on the copy stream and the compute stream is made to wait for it, so kernels
+// launched on the compute stream afterwards see the complete feed - without the copies queueing behind the backward
+// pass and optimizer step of the previous batch that are still running there.
+static int pipeline_begin(cudaStream_t copy, void* slot_free) {
+    if (slot_free) {
+        cudaError_t e = cudaStreamWaitEvent(copy, static_cast<cudaEvent_t>(slot_free), 0);
+        HP_CHECK(e == cudaSuccess, 100, "staging: cudaStreamWaitEvent(copy, slot_free) failed: %s", cudaGetErrorString(e));
+    }
+    return 0;
+}
+static int pipeline_end(cudaStream_t copy, cudaStream_t compute, void* ready) {
+    HP_CHECK(ready != nullptr, 2, "staging: null `ready` event");
+    cudaError_t e = cudaEventRecord(static_cast<cudaEvent_t>(ready), copy);
+    HP_CHECK(e == cudaSuccess, 100, "staging: cudaEventRecord failed: %s", cudaGetErrorString(e));
+    e = cudaStreamWaitEvent(compute, static_cast<cudaEvent_t>(ready), 0);
+    HP_CHECK(e == cudaSuccess, 100, "staging: cudaStreamWaitEvent(compute, ready) failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" UB200_API int ub200_stage_feed_pipelined(const double* feats, int n_docs, int F,
+                                                    const float* const* docid_cols, const float* const* label_cols,
+                                                    int L, int B, void* pinned, size_t pinned_bytes, void* device,
+                                                    int n_threads, int n_groups, void* copy_stream,
+                                                    void* compute_stream, void* slot_free, void* ready) {
+    cudaStream_t copy = static_cast<cudaStream_t>(copy_stream);
+    if (int rc = pipeline_begin(copy, slot_free)) return rc;
+    if (int rc = stage_feed_impl(feats, n_docs, F, docid_cols, label_cols, L, B, pinned, pinned_bytes, device,
+                                 n_threads, n_groups, copy))
+        return rc;
+    return pipeline_end(copy, static_cast<cudaStream_t>(compute_stream), ready);
+}
+
+// the same for a device-resident data set: only the ids / labels block (ub200_pack_ids_host layout) crosses PCIe
+extern "C" UB200_API int ub200_stage_ids_pipelined(const float* const* docid_cols, const float* const* label_cols,
+                                                   int L, int B, int max_id, void* pinned, size_t pinned_bytes,
+                                                   void* device, void* copy_stream, void* compute_stream,
+                                                   void* slot_free, void* ready) {
+    HP_CHECK(pinned && device && docid_cols && label_cols, 2, "stage_ids: null pointer");
+    HP_CHECK(L > 0 && B > 0, 1, "stage_ids: bad sizes");
+    const size_t need = (size_t)8 * L * B;
+    HP_CHECK(pinned_bytes >= need, 3, "stage_ids: staging buffer too small (%zu < %zu)", pinned_bytes, need);
+    const long long bad = pack_ids(docid_cols, label_cols, L, B, pinned, max_id);
+    HP_CHECK(bad == 0, 5, "stage_ids: %lld document ids outside [0, %d]", bad, max_id);
+    cudaStream_t copy = static_cast<cudaStream_t>(copy_stream);
+    if (int rc = pipeline_begin(copy, slot_free)) return rc;
+    cudaError_t e = cudaMemcpyAsync(device, pinned, need, cudaMemcpyHostToDevice, copy);
+    HP_CHECK(e == cudaSuccess, 100, "stage_ids: cudaMemcpyAsync failed: %s", cudaGetErrorString(e));
+    return pipeline_end(copy, static_cast<cudaStream_t>(compute_stream), ready);
+}
+
+// records `event` on `stream` (the engine marks "every kernel launched so far has been enqueued" with it)
+extern "C" UB200_API int ub200_event_record(void* event, void* stream) {
+    HP_CHECK(event != nullptr, 2, "event_record: null event");
+    cudaError_t e = cudaEventRecord(static_cast<cudaEvent_t>(event), static_cast<cudaStream_t>(stream));
+    HP_CHECK(e == cudaSuccess, 100, "event_record: %s", cudaGetErrorString(e));
     return 0;
 }

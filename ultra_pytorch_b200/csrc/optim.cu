@@ -182,10 +182,12 @@ __global__ void publish_kernel(const float* __restrict__ src, int n, float* host
                                unsigned int* dev_counter) {
     griddep_launch();
     griddep_wait();
-    if (threadIdx.x < n) host_dst[threadIdx.x] = src[threadIdx.x];
+    // launch c writes half (c & 1) of host_dst: a reader that is one launch behind (data-parallel steps return the
+    // previous step's loss) never races with the launch in flight
+    const unsigned int c = dev_counter[0] + 1u;
+    if (threadIdx.x < n) host_dst[(c & 1u) * 32u + threadIdx.x] = src[threadIdx.x];
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned int c = dev_counter[0] + 1u;
         dev_counter[0] = c;
         __threadfence_system();
         *reinterpret_cast<volatile unsigned int*>(host_seq) = c;

@@ -24,6 +24,16 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+_RESIDENT_CLS = []
+
+
+def _resident_features_cls():
+    if not _RESIDENT_CLS:
+        from .input_layer.resident import ResidentFeatures
+        _RESIDENT_CLS.append(ResidentFeatures)
+    return _RESIDENT_CLS[0]
+
+
 def column_ptrs(arrays, B):
     """ctypes array of the data pointers of L per-position feed arrays (f32 [B] each) + an object to keep alive.
 
@@ -39,8 +49,17 @@ def column_ptrs(arrays, B):
         if any(x.shape != (B,) for x in keep):
             raise ValueError("every docid_input / label array of a feed must have shape (%d,)" % B)
         return (ctypes.c_void_p * L)(*[x.ctypes.data for x in keep]), keep
-    addr = block.ctypes.data + np.arange(L, dtype=np.uint64) * np.uint64(4 * B)
+    key = (L, B)
+    offs = _ROW_OFFSETS.get(key)
+    if offs is None:
+        if len(_ROW_OFFSETS) > 256:
+            _ROW_OFFSETS.clear()
+        offs = _ROW_OFFSETS[key] = np.arange(L, dtype=np.uint64) * np.uint64(4 * B)
+    addr = offs + np.uint64(block.__array_interface__['data'][0])
     return (ctypes.c_void_p * L).from_buffer(addr), (block, addr)
+
+
+_ROW_OFFSETS = {}
 
 
 class Staged(object):
@@ -80,6 +99,38 @@ class StagedCache(object):
         return st
 
 
+class StagingSlot(object):
+    """One (pinned, device) buffer pair of the double-buffered input staging + its two events."""
+    __slots__ = ("pin", "dev", "pin_np", "free_ev", "ready_ev", "free_valid", "used", "resident_views", "pin_ptr",
+                 "pin_bytes", "dev_ptr", "free_h", "ready_h")
+
+    def __init__(self):
+        self.pin = self.dev = self.pin_np = None
+        # free_ev: recorded on the compute stream behind the last kernel that reads `dev`;
+        # ready_ev: recorded on the copy stream behind the last H2D copy into `dev`
+        self.free_ev = torch.cuda.Event()
+        self.ready_ev = torch.cuda.Event()
+        cur = torch.cuda.current_stream()
+        self.free_ev.record(cur)                 # torch creates the CUDA event lazily: materialise both handles now
+        self.ready_ev.record(cur)
+        self.free_h, self.ready_h = self.free_ev.cuda_event, self.ready_ev.cuda_event     # raw handles for the C calls
+        self.pin_ptr = self.pin_bytes = self.dev_ptr = 0
+        self.free_valid = False
+        self.used = False
+        self.resident_views = {}
+
+    def ensure(self, nbytes, device):
+        if self.pin is not None and self.pin.numel() >= nbytes:
+            return False
+        cap = int(nbytes * 1.5) + 1024
+        self.pin = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+        self.dev = torch.empty(cap, dtype=torch.uint8, device=device)
+        self.pin_np = self.pin.numpy()
+        self.pin_ptr, self.pin_bytes, self.dev_ptr = self.pin.data_ptr(), self.pin.numel(), self.dev.data_ptr()
+        self.resident_views.clear()
+        return True
+
+
 class RankerEngine(object):
     def __init__(self, feature_size, hidden, device=None, extra_floats=0):
         if not torch.cuda.is_available():
@@ -107,14 +158,19 @@ class RankerEngine(object):
         self._staged_cache = StagedCache()
         self._opt_ws = torch.zeros(int(lib.ub200_opt_workspace_bytes(self.P)), dtype=torch.uint8, device=self.device)
         self._loss_ws = None
-        self._pin = None
-        self._dev = None
+        # input staging: two (pinned, device) buffer pairs used alternately, copies on their own stream, so that the
+        # H2D transfer of step i overlaps the backward pass / optimizer step of step i - 1 (train() returns as soon as
+        # the loss is known).  UB200_STAGE_SLOTS=1: one pair, copies on the compute stream (the round-1 behaviour).
+        self._n_slots = max(1, int(os.environ.get("UB200_STAGE_SLOTS", "2")))
+        self._slots = None
+        self._slot_i = 0
+        self._copy_stream = None
         # host packer threads: the ranks of a node share its cores (torchrun exports LOCAL_WORLD_SIZE); spinning workers
         # of 8 ranks x 16 threads on 16 cores would starve each other
         local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
         self._pack_threads = int(os.environ.get("UB200_PACK_THREADS",
                                                 str(max(1, min(16, (os.cpu_count() or 1) // local_world)))))
-        self._pack_chunks = int(os.environ.get("UB200_PACK_CHUNKS", "6"))
+        self._pack_chunks = int(os.environ.get("UB200_PACK_CHUNKS", "4"))
         self._scores = {}
         self._dscores = {}
         # CUDA graphs captured by the learning algorithms have the raw pointers of the workspaces / score buffers baked
@@ -264,8 +320,7 @@ class RankerEngine(object):
         docid_arrays / label_arrays: L arrays of [B] (f32 in the feeds, base_algorithm.py:176-186).
         Device layout: docid i32 [L, B] (position-major) | labels f32 [B, L] |
                        feats f32 [n_docs+1, F] (last row = zero PAD, base_algorithm.py:148-149)."""
-        from .input_layer.resident import ResidentFeatures
-        if isinstance(letor_features, ResidentFeatures):
+        if isinstance(letor_features, _resident_features_cls()):
             return self._stage_resident(letor_features, docid_arrays, label_arrays)
         feats = np.asarray(letor_features)
         n_docs = feats.shape[0] if feats.ndim == 2 else 0
@@ -276,12 +331,8 @@ class RankerEngine(object):
         off_l = 4 * L * B
         off_f = (8 * L * B + 255) // 256 * 256
         total = off_f + 4 * nf
-        if self._pin is None or self._pin.numel() < total:
-            cap = int(total * 1.5) + 1024
-            self._pin = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
-            self._dev = torch.empty(cap, dtype=torch.uint8, device=self.device)
-            self._pin_np = self._pin.numpy()
-            self._staged_cache.entries.clear()       # views of the previous staging buffer
+        cs = _stream()                    # (torch.cuda.current_stream() costs ~5 us: asked once per call)
+        slot = self._acquire_slot(total, cs)
         def _f32_vec(x):
             return isinstance(x, np.ndarray) and x.dtype == np.float32 and x.flags.c_contiguous and x.shape == (B,)
         # feeds emit homogeneous per-position arrays (click_simulation_feed.py:141-150): checking the ends is enough
@@ -294,12 +345,19 @@ class RankerEngine(object):
             # stream while the rest is still being converted (csrc/hostpack.cpp).
             dptr, keep_d = column_ptrs(docid_arrays, B)
             lptr, keep_l = column_ptrs(label_arrays, B)
-            check(lib.ub200_stage_feed(feats.ctypes.data, n_docs, self.F, dptr, lptr, L, B, self._pin.data_ptr(),
-                                       self._pin.numel(), self._dev.data_ptr(), self._pack_threads, self._pack_chunks,
-                                       _stream()), "ub200_stage_feed")
-            return self.staged_views(self._dev, L, B, n_docs)
+            if self._n_slots > 1:
+                check(lib.ub200_stage_feed_pipelined(
+                    feats.__array_interface__['data'][0], n_docs, self.F, dptr, lptr, L, B, slot.pin_ptr, slot.pin_bytes, slot.dev_ptr,
+                    self._pack_threads, self._pack_chunks, self._copy_stream_h, cs,
+                    slot.free_h if slot.free_valid else None, slot.ready_h), "ub200_stage_feed_pipelined")
+            else:
+                check(lib.ub200_stage_feed(feats.__array_interface__['data'][0], n_docs, self.F, dptr, lptr, L, B, slot.pin_ptr,
+                                           slot.pin_bytes, slot.dev_ptr, self._pack_threads, self._pack_chunks, cs),
+                      "ub200_stage_feed")
+            slot.used = True
+            return self.staged_views(slot.dev, L, B, n_docs)
         else:
-            buf = self._pin_np
+            buf = slot.pin_np
             hd = buf[:off_l].view(np.int32).reshape(L, B)
             hl = buf[off_l:2 * off_l].view(np.float32).reshape(B, L)
             hf = buf[off_f:total].view(np.float32).reshape(n_docs + 1, self.F)
@@ -309,9 +367,50 @@ class RankerEngine(object):
             for l in range(L):
                 np.copyto(hd[l], docid_arrays[l], casting="unsafe")
                 hl[:, l] = label_arrays[l]
-        # the pinned buffer is reused next step: callers sync once per step (loss read-back) before re-staging
-        self._dev[:total].copy_(self._pin[:total], non_blocking=True)
-        return self.staged_views(self._dev, L, B, n_docs)
+        self._copy_slot(slot, total)
+        return self.staged_views(slot.dev, L, B, n_docs)
+
+    def _acquire_slot(self, nbytes, cs=None):
+        """The staging buffer pair of this call.  Marks, on the compute stream, the end of everything launched so far:
+        the pair used by the previous call may be overwritten (by the call after this one) once that point has passed.
+        The pinned half is reused two calls later; by then its copy has long finished (every train() / validation()
+        call reads a result of its own step back), which is checked rather than assumed."""
+        if self._slots is None:
+            self._slots = [StagingSlot() for _ in range(self._n_slots)]
+            self._copy_stream = torch.cuda.Stream(device=self.device) if self._n_slots > 1 else None
+            self._copy_stream_h = self._copy_stream.cuda_stream if self._n_slots > 1 else None
+        if self._n_slots > 1:
+            prev = self._slots[self._slot_i]
+            if prev.used:
+                check(lib.ub200_event_record(prev.free_h, _stream() if cs is None else cs), "ub200_event_record")
+                prev.free_valid = True
+            self._slot_i = (self._slot_i + 1) % self._n_slots
+        slot = self._slots[self._slot_i]
+        if slot.used and not slot.ready_ev.query():
+            slot.ready_ev.synchronize()
+        if slot.ensure(nbytes, self.device):
+            self._staged_cache.entries.clear()       # views of the previous staging buffer
+            slot.free_valid = False
+        return slot
+
+    @property
+    def _dev(self):
+        """device half of the staging pair used by the last stage() call"""
+        return None if self._slots is None else self._slots[self._slot_i].dev
+
+    def _copy_slot(self, slot, nbytes):
+        """pinned -> device for the paths that packed with numpy (same ordering as ub200_stage_feed_pipelined)"""
+        slot.used = True
+        if self._n_slots == 1:
+            slot.dev[:nbytes].copy_(slot.pin[:nbytes], non_blocking=True)
+            return
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(self._copy_stream):
+            if slot.free_valid:
+                self._copy_stream.wait_event(slot.free_ev)
+            slot.dev[:nbytes].copy_(slot.pin[:nbytes], non_blocking=True)
+            slot.ready_ev.record(self._copy_stream)
+        cur.wait_event(slot.ready_ev)
 
     def _stage_resident(self, feats, docid_arrays, label_arrays):
         """The feed's `letor_features` is the data set's whole feature matrix (input_layer/resident.py) and the doc ids
@@ -322,22 +421,28 @@ class RankerEngine(object):
         L = len(docid_arrays)
         B = len(docid_arrays[0])
         nbytes = 8 * L * B
-        if self._pin is None or self._pin.numel() < nbytes:
-            cap = int(nbytes * 1.5) + 1024
-            self._pin = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
-            self._dev = torch.empty(cap, dtype=torch.uint8, device=self.device)
-            self._pin_np = self._pin.numpy()
-            self._staged_cache.entries.clear()       # views of the previous staging buffer
+        cs = _stream()
+        slot = self._acquire_slot(nbytes, cs)
         dptr, keep_d = column_ptrs(docid_arrays, B)
         lptr, keep_l = column_ptrs(label_arrays, B)
-        check(lib.ub200_pack_ids_host(dptr, lptr, L, B, n_rows, self._pin.data_ptr(), self._pin.numel()),
-              "ub200_pack_ids_host")
-        self._dev[:nbytes].copy_(self._pin[:nbytes], non_blocking=True)
-        st = Staged()
-        st.docid = self._dev[:4 * L * B].view(torch.int32).view(L, B)
-        st.labels = self._dev[4 * L * B:nbytes].view(torch.float32).view(B, L)
-        st.feats = self._resident
-        st.B, st.L, st.n_docs, st.h2d_bytes = B, L, n_rows, nbytes
+        if self._n_slots > 1:
+            check(lib.ub200_stage_ids_pipelined(dptr, lptr, L, B, n_rows, slot.pin_ptr, slot.pin_bytes, slot.dev_ptr,
+                                                self._copy_stream_h, cs, slot.free_h if slot.free_valid else None,
+                                                slot.ready_h), "ub200_stage_ids_pipelined")
+            slot.used = True
+        else:
+            check(lib.ub200_pack_ids_host(dptr, lptr, L, B, n_rows, slot.pin_ptr, slot.pin_bytes), "ub200_pack_ids_host")
+            self._copy_slot(slot, nbytes)
+        key = (L, B, n_rows, self._resident.data_ptr())
+        st = slot.resident_views.get(key)
+        if st is None:
+            if len(slot.resident_views) >= 64:
+                slot.resident_views.clear()
+            st = slot.resident_views[key] = Staged()
+            st.docid = slot.dev[:4 * L * B].view(torch.int32).view(L, B)
+            st.labels = slot.dev[4 * L * B:nbytes].view(torch.float32).view(B, L)
+            st.feats = self._resident
+            st.B, st.L, st.n_docs, st.h2d_bytes = B, L, n_rows, nbytes
         return st
 
     def stage_device_feed(self, feed):
@@ -478,9 +583,9 @@ class RankerEngine(object):
         (csrc/optim.cu: publish_kernel) on a side stream forked from the current one; returns nothing - read with
         `read_published()` after the step has been launched."""
         if getattr(self, "_pub_host", None) is None:
-            self._pub_host = torch.zeros(64, dtype=torch.float32, pin_memory=True)          # [0, 32) values, [32] seq
+            self._pub_host = torch.zeros(128, dtype=torch.float32, pin_memory=True)   # 2 x 32 values, [64] seq
             self._pub_np = self._pub_host.numpy()
-            self._pub_seq_np = self._pub_np[32:33].view(np.uint32)
+            self._pub_seq_np = self._pub_np[64:65].view(np.uint32)
             self._pub_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
             self._pub_stream = torch.cuda.Stream(device=self.device)
             self._pub_launched = 0
@@ -488,7 +593,7 @@ class RankerEngine(object):
         self._pub_stream.wait_stream(cur)
         with torch.cuda.stream(self._pub_stream):
             check(lib.ub200_publish(_ptr(scalars), scalars.numel(), self._pub_host.data_ptr(),
-                                    self._pub_host.data_ptr() + 128, _ptr(self._pub_counter),
+                                    self._pub_host.data_ptr() + 256, _ptr(self._pub_counter),
                                     self._pub_stream.cuda_stream), "ub200_publish")
         self._pub_n = scalars.numel()
 
@@ -497,15 +602,16 @@ class RankerEngine(object):
         if getattr(self, "_pub_host", None) is not None:
             torch.cuda.current_stream().wait_stream(self._pub_stream)
 
-    def read_published(self, timeout_s=20.0):
-        """Waits (spinning on the host-visible sequence number) for the publish of the step launched last and returns
-        its scalars as a numpy array."""
+    def read_published(self, timeout_s=20.0, lag=0):
+        """Waits (spinning on the host-visible sequence number) for the publish of the step launched last (lag = 0) or
+        of the one before it (lag = 1) and returns its scalars as a numpy array."""
         import time
-        want = self._pub_launched & 0xFFFFFFFF          # the step launched last (B200Algorithm.run_step counts them)
+        want = (self._pub_launched - lag) & 0xFFFFFFFF  # B200Algorithm.run_step counts the launched steps
         seq = self._pub_seq_np
         spins = 0
         t0 = None
-        while int(seq[0]) != want:
+        # sequence numbers only grow: with lag = 1 the step in flight may already have published as well
+        while ((int(seq[0]) - want) & 0xFFFFFFFF) > lag:
             spins += 1
             if (spins & 0xFFF) == 0:
                 if t0 is None:
@@ -514,7 +620,8 @@ class RankerEngine(object):
                     torch.cuda.synchronize()          # surfaces a CUDA error if there is one
                     raise _capi.UltraB200Error("early loss read-back timed out (sequence %d, expected %d)"
                                                % (int(seq[0]), want))
-        return self._pub_np[:self._pub_n].copy()
+        half = 32 * (want & 1)
+        return self._pub_np[half:half + self._pub_n].copy()
 
     # ---- optimizer ------------------------------------------------------------------------------------
     def clip_update(self, params, grads, state_sum, den, scale_const, max_norm, lr, mode, norm_out=None):

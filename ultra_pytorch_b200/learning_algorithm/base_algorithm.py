@@ -46,6 +46,16 @@ _RANKER_ALIASES = {
 }
 
 
+_DEVICE_FEED_CLS = []
+
+
+def _device_feed_cls():
+    if not _DEVICE_FEED_CLS:
+        from ..input_layer.resident import DeviceFeed
+        _DEVICE_FEED_CLS.append(DeviceFeed)
+    return _DEVICE_FEED_CLS[0]
+
+
 class B200Algorithm(_reference_base()):
     PADDING_SCORE = -100000                      # base_algorithm.py:37
     VERBOSE = os.environ.get("UB200_QUIET", "0") != "1"
@@ -125,20 +135,37 @@ class B200Algorithm(_reference_base()):
         self.last_h2d_bytes = 0
         self.last_d2h_bytes = 0
         self._graphs = {}
+        self._feed_getters = {}
         self._phase = None       # None: whole step | 'pre': up to the all-reduce | 'post': after it
 
     def run_step(self, st):
         """device_step(st), replayed from CUDA graphs once the (B, L, buffer) combination has been seen twice."""
         out = self._run_step(st)
-        if getattr(self, "_early", False):
+        if getattr(self, "_early", False) or getattr(self, "_late", False):
             self.engine._pub_launched += 1          # one execution of the publish kernel per launched step
+        return out
+
+    # Data parallel: the loss of a step is only final after the exchange at its end, so an early read-back does not
+    # exist.  Instead the final scalars are published at the END of the step and train() of step i returns the loss of
+    # step i - 1 (the first call returns its own): the host never waits for the step it has just launched and packs /
+    # copies the next batch beside it.  The reference has no multi-process mode, so there is no contract to keep; the
+    # value is the exact global loss, one step late.  UB200_DP_LAG_LOSS=0 restores the blocking read of the own step.
+    LAG_LOSS_DP = os.environ.get("UB200_DP_LAG_LOSS", "1") != "0"
+
+    def _device_step_published(self, st):
+        out = self.device_step(st)
+        self._late = False
+        if out is not None and self.LAG_LOSS_DP and self.world_size() > 1 and out.numel() <= 32:
+            self.engine.publish(out)
+            self.engine.join_publish()
+            self._late = True
         return out
 
     def _run_step(self, st):
         # data parallel over peer memory: the exchange is one of OUR kernels, so the whole step is one graph again
         dp = self.world_size() > 1 and self.engine.peer is None
         if not self.USE_GRAPH or (dp and not self.USE_GRAPH_DP):
-            return self.device_step(st)
+            return self._device_step_published(st)
         key = (st.B, st.L, st.feats.data_ptr(), st.docid.data_ptr())
         ent = self._graphs.get(key)
         if ent is not None and ent[4] != self.engine.generation:
@@ -157,24 +184,24 @@ class B200Algorithm(_reference_base()):
             return ent[2]
         ent[0] += 1
         if ent[0] <= 2:                      # warm-up: workspaces get allocated outside the capture
-            out = self.device_step(st)
+            out = self._device_step_published(st)
             ent[4] = self.engine.generation   # allocations of the warm-up itself are not releases of captured buffers
             return out
         torch.cuda.synchronize()
         if not dp:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                out = self.device_step(st)
+                out = self._device_step_published(st)
             ent[1], ent[2] = graph, out
             graph.replay()
             return out
         g_pre, g_post = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         self._phase = "pre"
         with torch.cuda.graph(g_pre):
-            self.device_step(st)
+            self._device_step_published(st)
         self._phase = "post"
         with torch.cuda.graph(g_post):
-            out = self.device_step(st)
+            out = self._device_step_published(st)
         self._phase = None
         ent[1], ent[2], ent[3] = g_pre, out, g_post
         g_pre.replay()
@@ -234,15 +261,23 @@ class B200Algorithm(_reference_base()):
 
     # ---- input staging --------------------------------------------------------------------------------
     def _stage(self, input_feed, list_size):
-        from ..input_layer.resident import DeviceFeed
-        if isinstance(input_feed, DeviceFeed) and input_feed.L == list_size:
+        if isinstance(input_feed, _device_feed_cls()) and input_feed.L == list_size:
             # the batch was assembled on the device (N1): nothing to pack or copy
             self.letor_features = dict.__getitem__(input_feed, self.letor_features_name)
             st = self.engine.stage_device_feed(input_feed)
             self.last_h2d_bytes = 0
             return st
-        docids = [input_feed[self.docid_inputs_name[i]] for i in range(list_size)]
-        labels = [input_feed[self.labels_name[i]] for i in range(list_size)]
+        getters = self._feed_getters.get(list_size)
+        if getters is None:
+            import operator
+            one = list_size == 1                 # itemgetter with a single key returns the item, not a tuple
+            getters = self._feed_getters[list_size] = (
+                (lambda f, k=self.docid_inputs_name[0]: (f[k],)) if one else
+                operator.itemgetter(*self.docid_inputs_name[:list_size]),
+                (lambda f, k=self.labels_name[0]: (f[k],)) if one else
+                operator.itemgetter(*self.labels_name[:list_size]))
+        docids = getters[0](input_feed)
+        labels = getters[1](input_feed)
         self.letor_features = input_feed[self.letor_features_name]
         st = self.engine.stage(self.letor_features, docids, labels)
         self.last_h2d_bytes = st.h2d_bytes
@@ -268,6 +303,10 @@ class B200Algorithm(_reference_base()):
         """The one D2H read of a step (the reference's loss.item())."""
         if getattr(self, "_early", False):
             host = self.engine.read_published()
+            self.last_d2h_bytes = host.size * 4
+            return host
+        if getattr(self, "_late", False):
+            host = self.engine.read_published(lag=1 if self.engine._pub_launched > 1 else 0)
             self.last_d2h_bytes = host.size * 4
             return host
         host = t.detach().to("cpu", non_blocking=False)
