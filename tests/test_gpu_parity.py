@@ -227,10 +227,20 @@ def test_mlp_forward_backward_vs_oracle(F, hidden, L, B):
         got = grads[off:off + ref.size].reshape(ref.shape)
         off += ref.size
         assert_close(got, ref, 1e-5, "grad " + n, floor)
-    # run-to-run determinism (fixed-order reductions)
+    # Later steps: where the weight-gradient kernel takes its operands from the images the forward / backward kernels
+    # leave behind, the first backward pass of a workspace has no scale history yet and converts from fp32 instead, so
+    # step 1 and step 2 may differ in the last bits - both are held to the oracle.  From step 2 on the results are
+    # bit-identical run to run (fixed-order reductions).
     eng.forward(feats_dev, docid_dev, L, B, training=True)
     grads2 = eng.backward(feats_dev, docid_dev, L, B, _dev(dsc)).cpu().numpy()
-    assert np.array_equal(grads, grads2)
+    off = 0
+    for n in uo.param_names(n_layers):
+        ref = g64[n]
+        assert_close(grads2[off:off + ref.size].reshape(ref.shape), ref, 1e-5, "grad (step 2) " + n, floor)
+        off += ref.size
+    eng.forward(feats_dev, docid_dev, L, B, training=True)
+    grads3 = eng.backward(feats_dev, docid_dev, L, B, _dev(dsc)).cpu().numpy()
+    assert np.array_equal(grads2, grads3)
 
 
 @pytest.mark.parametrize("B,L", [(1, 1), (7, 5), (300, 40), (64, 200), (33, 45), (20, 100), (3, 300), (20000, 40)])

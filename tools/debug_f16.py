@@ -67,6 +67,8 @@ def main():
             torch.cuda.synchronize()
             tf += ev[0].elapsed_time(ev[1])
             tb += ev[1].elapsed_time(ev[2])
+        grads = eng.backward(feats, docid, L, B, dsc).clone()      # a later step: operand images (mask 128) are in use
+        torch.cuda.synchronize()
         res[mode] = (scores, ys, grads)
         print("mode %d done: fwd %.1f us  bwd %.1f us (eager launches, incl. prep)" % (mode, 1e3 * tf / reps, 1e3 * tb / reps),
               flush=True)

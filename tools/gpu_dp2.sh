@@ -1,7 +1,7 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_dp.py tests/test_gpu_dp_main.py -q -x > gpurun_out/pytest_dp2.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_dp2.log
 tail -15 gpurun_out/pytest_dp2.log | cut -c1-300
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus 2 --steps 200 --warmup 5 --no-pipeline > gpurun_out/bench_dp2.json 2> gpurun_out/bench_dp2.err; echo "bench rc=$?"
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus 2 --steps 200 --warmup 5 --no-pipeline --no-all-configs > gpurun_out/bench_dp2.json 2> gpurun_out/bench_dp2.err; echo "bench rc=$?"
 python - <<'PY'
 import json
 d=json.loads(open('gpurun_out/bench_dp2.json').read().strip().splitlines()[-1])

@@ -22,8 +22,10 @@ namespace ub200 {
 // 2 = data gradient, 4 = weight gradient; 0 = CUDA-core fp32 kernels everywhere.  Default 7 (env UB200_TC overrides).
 // 16 = forward as fused fp16-split launches (mlp_f16.cu), 32 = fused fp16-split data-gradient chain, 64 = fp16-split
 // weight gradients of all hidden layers in one launch (needs 32).
+// 128 = the fp16-split forward / backward kernels leave their (already split) A-operand tiles behind as operand images and
+// the weight-gradient kernel loads them with bulk copies instead of re-reading and re-converting fp32 (needs 16 | 32 | 64).
 enum { TC_FWD = 1, TC_DGRAD = 2, TC_WGRAD = 4, TC_FUSED_FWD = 8, TC_F16_FWD = 16, TC_F16_BWD = 32, TC_F16_WGRAD = 64,
-       TC_ALL = 127 };
+       TC_F16_IMG = 128, TC_ALL = 255 };
 static int g_tc_mode = -1;
 static int tc_mode() {
     if (g_tc_mode < 0) {
@@ -54,6 +56,22 @@ static void plan_wgrad16(const LayerDims& d, int M, f16::WgArgs* a) {
         a->l[j].ldp = (d.K[j] + 1 + 3) / 4 * 4;
     }
     f16::wgrad_plan(a, kNumSMs);
+}
+// Measured (B200, profiles/r02_images_ab.txt): writing the images costs the forward / backward kernels time on their
+// latency chain (the staging ring is shared with the copies), which the weight-gradient kernel only wins back when its
+// conversion work is large - nets with a wide layer (c3 / c4 / c5: +6 .. +19 % per step), not DNN[256,128,64] (-7 .. -13 %).
+// UB200_IMG=1 / 0 forces the images on / off for every shape the kernels support.
+static bool f16_images_on(const LayerDims& d) {
+    const int need = TC_F16_FWD | TC_F16_BWD | TC_F16_WGRAD | TC_F16_IMG;
+    if ((tc_mode() & need) != need || !f16_bwd_ok(d)) return false;
+    static const int forced = [] { const char* e = getenv("UB200_IMG"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+    if (forced >= 0) return forced == 1;
+    long long widest = 0;
+    for (int j = 0; j + 1 < d.n_layers; ++j) {
+        const long long kn = (long long)d.K[j] * d.N[j];
+        widest = kn > widest ? kn : widest;
+    }
+    return widest >= 100000;
 }
 static bool use_tc(int j, int K, int N, int what = 7) { return (tc_mode() & what) != 0 && tc_layer_ok(j, K, N); }
 
@@ -118,6 +136,12 @@ struct MlpWorkspace {
     float* wf2;                        // final layer: gamma_F w_F [K_F] followed by c_F + beta_F . w_F [1]
     float* dz16[UB200_MAX_LAYERS];     // dZ_j [M, N_j] of every hidden layer (the fused chain produces all of them)
     unsigned int* dzmax;               // [UB200_MAX_LAYERS] running max |dZ_j| (float bits)
+    // operand images for the weight-gradient kernel (mlp_f16.cuh: FwdArgs::ximg, BwdArgs::dzimg) + their bookkeeping.
+    // wscale / img_bad live across steps: the workspace must start zeroed (0 = no scale yet) and stay with its shape.
+    uint16_t* ximg[UB200_MAX_LAYERS];
+    uint16_t* dzimg[UB200_MAX_LAYERS];
+    float* wscale;                     // [UB200_MAX_LAYERS]
+    unsigned int* img_bad;             // [UB200_MAX_LAYERS]
     size_t total_bytes;
 };
 
@@ -210,6 +234,9 @@ static void carve(const LayerDims& d, int M, int training, char* base, MlpWorksp
     }
     w->wf2 = nullptr;
     w->dzmax = nullptr;
+    w->wscale = nullptr;
+    w->img_bad = nullptr;
+    for (int j = 0; j < UB200_MAX_LAYERS; ++j) w->ximg[j] = w->dzimg[j] = nullptr;
     if (f16_net_ok(d)) {
         const int nh = d.n_layers - 1;
         for (int j = 0; j < nh; ++j) {
@@ -230,6 +257,20 @@ static void carve(const LayerDims& d, int M, int training, char* base, MlpWorksp
         off = align_up(off + sizeof(float) * (d.K[nh] + 1), 256);
         w->dzmax = reinterpret_cast<unsigned int*>(base + off);
         off = align_up(off + sizeof(unsigned int) * UB200_MAX_LAYERS, 256);
+        if (training && f16_bwd_ok(d)) {
+            // (carved whenever the shapes allow it, whatever the mode mask says: the layout must not move with it)
+            w->wscale = reinterpret_cast<float*>(base + off);
+            off = align_up(off + sizeof(float) * UB200_MAX_LAYERS, 256);
+            w->img_bad = reinterpret_cast<unsigned int*>(base + off);
+            off = align_up(off + sizeof(unsigned int) * UB200_MAX_LAYERS, 256);
+            for (int j = 0; j < nh; ++j) {
+                off = align_up(off, 1024);
+                w->ximg[j] = reinterpret_cast<uint16_t*>(base + off);
+                off = align_up(off + f16::img_bytes(M, d.K[j]), 1024);
+                w->dzimg[j] = reinterpret_cast<uint16_t*>(base + off);
+                off = align_up(off + f16::img_bytes(M, d.N[j]), 1024);
+            }
+        }
     }
     w->total_bytes = off;
 }
@@ -259,6 +300,9 @@ static int prep_f16_weights(const LayerDims& d, const MlpWorkspace& w, const flo
     t.wf2 = w.wf2;
     t.cf2 = w.wf2 + d.K[nh];
     t.dzmax = training ? w.dzmax : nullptr;
+    const bool img = training && w.wscale && f16_images_on(d);
+    t.wscale = img ? w.wscale : nullptr;
+    t.img_bad = img ? w.img_bad : nullptr;
     return f16::prep(t, st);
 }
 
@@ -745,6 +789,7 @@ static int forward_f16(const LayerDims& d, const MlpWorkspace& w, const float* f
             a.wimg[q] = w.wf16[j + q];
             a.bias2[q] = w.bias2[j + q];
             a.Y[q] = w.Y[j + q];
+            a.ximg[q] = (training && w.wscale && f16_images_on(d)) ? w.ximg[j + q] : nullptr;
             if (training || (run == 1 && !a.has_final))
                 if (int rc = f16::make_tmap_f32(&a.ymap[q], w.Y[j + q], (size_t)M, (size_t)d.N[j + q])) return rc;
         }
@@ -969,10 +1014,13 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
             b.wd[q] = w.wd16[q];
             b.dZ[q] = w.dz16[q];
             b.dzmax[q] = w.dzmax + q;
+            b.dzimg[q] = (w.wscale && f16_images_on(d)) ? w.dzimg[q] : nullptr;
             if (int rc = f16::make_tmap_f32(&b.ymap[q], w.Y[q], (size_t)M, (size_t)d.N[q])) return rc;
             if (int rc = f16::make_tmap_f32(&b.dzmap[q], w.dz16[q], (size_t)M, (size_t)d.N[q])) return rc;
         }
         for (int q = 0; q <= nh; ++q) b.stats[q] = w.stats[q];
+        b.wscale = w.wscale;
+        b.img_bad = w.img_bad;
         if (int rc = f16::bwd(b, st)) return rc;
     }
     const bool wgrad16 = chain16 && (tc_mode() & TC_F16_WGRAD);
@@ -989,6 +1037,12 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
             l.stats = w.stats[j];
             l.dzmax = w.dzmax + j;
             l.out = w.partials[j];
+            if (w.wscale && f16_images_on(d)) {
+                l.ximg = w.ximg[j];
+                l.dzimg = w.dzimg[j];
+                l.wscale = w.wscale + j;
+                l.img_bad = w.img_bad + j;
+            }
         }
         if (int rc = f16::wgrad(wa, st)) return rc;
         for (int j = nl - 2; j >= 0; --j) {

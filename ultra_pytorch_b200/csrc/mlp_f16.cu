@@ -31,7 +31,7 @@ using namespace ub200::tc;
 
 constexpr int NW = 16;                        // worker warps
 constexpr int NWT = NW * 32;                  // 512 worker threads
-constexpr int MMA_WARP = 16, TMA_WARP = 17, Y_WARP = 18;
+constexpr int MMA_WARP = 16, TMA_WARP = 17, Y_WARP = 18, IMG_WARP = 19;
 constexpr int NTHREADS = 20 * 32;          // 4 worker warpgroups + 1 control warpgroup (warps 18, 19 idle)
 constexpr int A_STAGES = 3;
 constexpr int A_HALF = 128 * 128;             // one (hi | lo) A tile: 128 rows x 64 fp16
@@ -69,6 +69,7 @@ struct Bars {
     uint64_t accum[MAXF];
     uint64_t y_full[2];           // backward: activation chunks staged by the loader warp
     uint64_t y_empty[2];
+    uint64_t img_done[MAXF];      // the image warp has copied (and finished reading) every A stage of layer q
     uint32_t tmem_slot;
 };
 static_assert(sizeof(Bars) <= CTL_BYTES, "control block too large");
@@ -214,6 +215,35 @@ __device__ __forceinline__ void produce_first(const float* __restrict__ X, const
             for (int e = 0; e < 4; ++e) cur[e] = nxt[e];
         }
     }
+}
+
+// operand images (see FwdArgs::ximg): warp IMG_WARP copies every A-operand stage of a layer to global memory.  The stage
+// is released to the producers by TWO arrivals then: the MMA commit and this warp's (after the copy has read the stage).
+// fixed_stage >= 0: every chunk passes through that one stage (the streamed epilogue of the backward kernel).
+__device__ __forceinline__ void image_store_layer(uint16_t* img_tile, int n_chunks, uint8_t* a_ring, uint64_t* a_full,
+                                                  uint64_t* a_empty, uint64_t* done, int fixed_stage = -1) {
+    // two copies in flight: the stage of chunk it - 1 is released once its copy has been read while chunk it's runs
+    int prev = -1;
+    for (int it = 0; it < n_chunks; ++it) {
+        const int s = fixed_stage >= 0 ? fixed_stage : it % A_STAGES;
+        const uint32_t use = fixed_stage >= 0 ? (uint32_t)it : (uint32_t)(it / A_STAGES);
+        mbar_wait(&a_full[s], use & 1u);
+        bulk_s2g(img_tile + (size_t)it * (A_STAGE / 2), a_ring + s * A_STAGE, A_STAGE);
+        bulk_commit();
+        if (fixed_stage >= 0) {
+            bulk_wait_read0();
+            mbar_arrive(&a_empty[s]);
+        } else {
+            if (prev >= 0) {
+                bulk_wait_read1();
+                mbar_arrive(&a_empty[prev]);
+            }
+            prev = s;
+        }
+    }
+    bulk_wait_read0();
+    if (prev >= 0) mbar_arrive(&a_empty[prev]);
+    mbar_arrive(done);
 }
 
 // streams the B (weight image) tiles of one layer: chunk it, column half h -> ring stage (it * nh + h) % nst
@@ -453,17 +483,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd16_kernel(const __grid_constan
     if (tid == 0) TL(0, 0);
     const int i0 = blockIdx.x * 128;
     const int n0 = blockIdx.y * a.bn0;
+    // operand image of layer q's input: written by the CTAs of the first column tile only
+    const bool img_cta = blockIdx.y == 0;
     if (tid == 0) {
         for (int q = 0; q < MAXF; ++q) {
+            const uint32_t releases = (img_cta && q < a.nl && a.ximg[q]) ? 2u : 1u;
             for (int s = 0; s < A_STAGES; ++s) {
                 mbar_init(&bars->a_full[q][s], NW);
-                mbar_init(&bars->a_empty[q][s], 1);
+                mbar_init(&bars->a_empty[q][s], releases);
             }
             for (int s = 0; s < B_MAX_STAGES; ++s) {
                 mbar_init(&bars->b_full[q][s], 1);
                 mbar_init(&bars->b_empty[q][s], 1);
             }
             mbar_init(&bars->accum[q], 1);
+            mbar_init(&bars->img_done[q], 1);
         }
         fence_mbar_init();
     }
@@ -487,6 +521,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd16_kernel(const __grid_constan
                 tma_layer(a.wimg[q], a.N[q], q == 0 ? n0 : 0, bn, 1, (K + 63) >> 6, b_ring, bars->b_full[q],
                           bars->b_empty[q]);
                 TL(2, 2 * q + 1);
+            }
+      } else if (warp == IMG_WARP) {
+        if (lane == 0 && img_cta)
+            for (int q = 0; q < a.nl; ++q) {
+                if (!a.ximg[q]) continue;
+                const int nch = ((q == 0 ? a.K0 : a.N[q - 1]) + 63) >> 6;
+                image_store_layer(a.ximg[q] + (size_t)blockIdx.x * nch * (A_STAGE / 2), nch, a_ring, bars->a_full[q],
+                                  bars->a_empty[q], &bars->img_done[q]);
             }
     } else if (warp == MMA_WARP) {
         for (int q = 0; q < a.nl; ++q) {
@@ -515,6 +557,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd16_kernel(const __grid_constan
         for (int q = 0; q < a.nl; ++q) {
             const int bn = q == 0 ? a.bn0 : a.N[q];
             mbar_wait(&bars->accum[q], 0);
+            if (img_cta && a.ximg[q]) mbar_wait(&bars->img_done[q], 0);   // the epilogue reuses the A ring (staging)
             __syncwarp();
             tc_fence_after();
             if (tid == 0) TL(0, 8 + 4 * q);
@@ -538,6 +581,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd16_kernel(const __grid_constan
 // ---------------------------------------------------------------------------------------------------------------
 // backward (data-gradient chain)
 // ---------------------------------------------------------------------------------------------------------------
+constexpr float kImgMaxAbs = 32768.f;     // largest |value * image scale| an operand image accepts (fp16 max 65504)
 __device__ __forceinline__ float pow2_scale_from_max(float mx, float& inv) {
     // scale = 2^(10 - E), E = exponent of mx (so that mx * scale is in [2^10, 2^11)); exact powers of two
     int eb = (int)((__float_as_uint(mx) >> 23) & 255u);
@@ -587,9 +631,11 @@ __device__ __forceinline__ void take_y_chunk(YPipe& yp, const uint8_t* ybase, in
 // tail shared by the final-layer step and every data-gradient epilogue: dz[] (this thread's 16 * NQ columns of dZ_q) ->
 // global (for the weight-gradient kernel; staged, tensor stores), running max, and - when another data gradient
 // follows - the row-scaled fp16 A operand of that GEMM.  Returns the inverse row scale.  The A ring is idle here.
+// img_scale > 0: the operand tiles double as this step's weight-gradient image of dZ_q (BwdArgs::dzimg) and carry that
+// one scale for the whole layer instead of a row's own.
 template <int NQ>
 __device__ __forceinline__ float emit_dz(const BwdArgs& a, int q, float* dz, int trow, int cg, int grow, int lane,
-                                         uint8_t* a_ring, Bars* bars) {
+                                         uint8_t* a_ring, Bars* bars, float img_scale) {
     const bool row_ok = grow < a.M;
     const int i0 = grow - trow;
     float mx = 0.f;
@@ -621,14 +667,22 @@ __device__ __forceinline__ float emit_dz(const BwdArgs& a, int q, float* dz, int
         const float wm = warp_max(mx);
         if (lane == 0 && wm > 0.f) atomicMax(a.dzmax[q], __float_as_uint(wm));
     }
-    if (q == 0) return 1.f;
+    if (q == 0 && !(img_scale > 0.f)) return 1.f;
     float* part = reinterpret_cast<float*>(a_ring + 2 * A_STAGE);
     part[cg * 128 + trow] = mx;
     worker_bar();                                         // (also: the staging buffers have drained, see above)
     const float rmx = fmaxf(fmaxf(part[trow], part[128 + trow]), fmaxf(part[256 + trow], part[384 + trow]));
     worker_bar();
     float inv;
-    const float sc = pow2_scale_from_max(rmx, inv);
+    float sc = pow2_scale_from_max(rmx, inv);
+    if (img_scale > 0.f) {
+        if (rmx * img_scale <= kImgMaxAbs) {
+            sc = img_scale;
+            inv = 1.0f / img_scale;                       // exact: a power of two
+        } else if (cg == 0) {
+            a.img_bad[q] = 1u;                             // this row keeps its own scale: no image of dZ_q this step
+        }
+    }
     uint64_t* a_full = bars->a_full[q];
     uint64_t* a_empty = bars->a_empty[q];
 #pragma unroll
@@ -649,7 +703,7 @@ __device__ __forceinline__ float emit_dz(const BwdArgs& a, int q, float* dz, int
 // final layer backward for this thread's columns: dZ_last = LNbwd(ds * gamma_F w_F) . ELU'(y)
 template <int NQ>
 __device__ __forceinline__ float bwd_final(const BwdArgs& a, YPipe& yp, int trow, int cg, int grow, int lane,
-                                           uint8_t* a_ring, Bars* bars) {
+                                           uint8_t* a_ring, Bars* bars, float img_scale) {
     const int q = a.nl - 1, N = a.N[q];
     const bool row_ok = grow < a.M;
     float y[16 * NQ];
@@ -702,7 +756,7 @@ __device__ __forceinline__ float bwd_final(const BwdArgs& a, YPipe& yp, int trow
             }
         }
     }
-    return emit_dz<NQ>(a, q, y, trow, cg, grow, lane, a_ring, bars);
+    return emit_dz<NQ>(a, q, y, trow, cg, grow, lane, a_ring, bars, img_scale);
 }
 
 // epilogue of the data gradient of layer q: dXhat (tensor memory, NQ x 64 columns = width of layer q-1) ->
@@ -711,7 +765,7 @@ __device__ __forceinline__ float bwd_final(const BwdArgs& a, YPipe& yp, int trow
 template <int NQ>
 __device__ __forceinline__ float bwd_epilogue(const BwdArgs& a, int q, float inv_prev, YPipe& yp, uint32_t tlane,
                                               int trow, int cg, int grow, int lane, uint8_t* a_ring, uint8_t* b_ring,
-                                              Bars* bars) {
+                                              Bars* bars, float img_scale) {
     const int N = a.N[q - 1];
     const bool row_ok = grow < a.M;
     const float2 st = row_ok ? a.stats[q][grow] : make_float2(0.f, 1.f);
@@ -770,7 +824,19 @@ __device__ __forceinline__ float bwd_epilogue(const BwdArgs& a, int q, float inv
                 worker_bar();
             }
             sts_chunk16(a_ring + (it & 1) * A_STAGE, trow, cg, o);
+            if (img_scale > 0.f) {
+                // image chunk (scaled, split) through ring stage 2: released by the image warp chunk by chunk
+                mbar_wait(&bars->a_empty[q - 1][2], ((uint32_t)it & 1u) ^ 1u);
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = o[i] * img_scale;
+                store_split16(a_ring + 2 * A_STAGE, trow, cg, v);
+            }
             fence_proxy_async();
+            if (img_scale > 0.f) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->a_full[q - 1][2]);
+            }
             worker_bar();
             if (threadIdx.x == 0) {
                 const uint8_t* src = a_ring + (it & 1) * A_STAGE;
@@ -783,6 +849,7 @@ __device__ __forceinline__ float bwd_epilogue(const BwdArgs& a, int q, float inv
         tc_fence_before();
         const float wm = warp_max(mx);
         if (lane == 0 && wm > 0.f) atomicMax(a.dzmax[q - 1], __float_as_uint(wm));
+        if (img_scale > 0.f && lane == 0 && wm * img_scale > kImgMaxAbs) a.img_bad[q - 1] = 1u;
         return 1.f;
     } else {
 #pragma unroll
@@ -799,7 +866,7 @@ __device__ __forceinline__ float bwd_epilogue(const BwdArgs& a, int q, float inv
             }
         }
         tc_fence_before();      // accumulator free for the next data gradient
-        return emit_dz<NR>(a, q - 1, y, trow, cg, grow, lane, a_ring, bars);
+        return emit_dz<NR>(a, q - 1, y, trow, cg, grow, lane, a_ring, bars, img_scale);
     }
 }
 
@@ -812,17 +879,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd16_kernel(const __grid_constan
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     griddep_launch();
     const int i0 = blockIdx.x * 128;
+    if (warp == MMA_WARP) tmem_alloc(&bars->tmem_slot, 512);
+    griddep_wait();
+    // weight-gradient images of dZ_q: on when the layer has a buffer and a scale from the previous step
+    float img_scale[MAXF];
+#pragma unroll
+    for (int q = 0; q < MAXF; ++q) img_scale[q] = (q < a.nl && a.dzimg[q] && a.wscale) ? a.wscale[q] : 0.f;
     if (tid == 0) {
+#pragma unroll
         for (int q = 0; q < MAXF; ++q) {
+            // releases of an A stage: the MMA commit (layers >= 1) and the image warp's arrival
+            const uint32_t releases = (q >= 1 ? 1u : 0u) + (img_scale[q] > 0.f ? 1u : 0u);
             for (int s = 0; s < A_STAGES; ++s) {
                 mbar_init(&bars->a_full[q][s], NW);
-                mbar_init(&bars->a_empty[q][s], 1);
+                mbar_init(&bars->a_empty[q][s], releases ? releases : 1u);
             }
             for (int s = 0; s < B_MAX_STAGES; ++s) {
                 mbar_init(&bars->b_full[q][s], 1);
                 mbar_init(&bars->b_empty[q][s], 1);
             }
             mbar_init(&bars->accum[q], 1);
+            mbar_init(&bars->img_done[q], 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&bars->y_full[s], 1);
@@ -830,8 +907,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd16_kernel(const __grid_constan
         }
         fence_mbar_init();
     }
-    if (warp == MMA_WARP) tmem_alloc(&bars->tmem_slot, 512);
-    griddep_wait();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -856,6 +931,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd16_kernel(const __grid_constan
             mma_layer(tmem_base, a.N[q], bn, nh, 0, a_ring, b_ring, bars->a_full[q], bars->a_empty[q], bars->b_full[q],
                       bars->b_empty[q], &bars->accum[q]);
         }
+      } else if (warp == IMG_WARP) {
+        if (lane == 0)
+            for (int q = a.nl - 1; q >= 0; --q) {
+                if (!(img_scale[q] > 0.f)) continue;
+                const int nch = a.N[q] >> 6;
+                image_store_layer(a.dzimg[q] + (size_t)blockIdx.x * nch * (A_STAGE / 2), nch, a_ring, bars->a_full[q],
+                                  bars->a_empty[q], &bars->img_done[q], nch > 4 ? 2 : -1);
+            }
       } else if (warp == Y_WARP) {
         // activation loader: the chunk sequence the workers consume - Y_{nl-1} for the final-layer step, then for every
         // data gradient q the input activations Y_{q-1} of its LayerNorm-backward (twice when they are streamed)
@@ -875,6 +958,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd16_kernel(const __grid_constan
             for (int q = a.nl - 1; q >= 1; --q) {
                 const int nq = a.N[q - 1] >> 6;
                 mbar_wait(&bars->accum[q], 0);            // the MMAs of this data gradient have left the A / B rings
+                if (img_scale[q] > 0.f) mbar_wait(&bars->img_done[q], 0);   // ... and so has the image copy
                 if (nq <= 4) load_chunks(q - 1, nq, a_ring);
                 else {
                     load_chunks(q - 1, nq, b_ring);
@@ -892,22 +976,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd16_kernel(const __grid_constan
         float inv;
         const int nqf = a.N[a.nl - 1] >> 6;
         if (tid == 0) TL(0, 20);
-        if (nqf == 1) inv = bwd_final<1>(a, yp, trow, cg, grow, lane, a_ring, bars);
-        else if (nqf == 2) inv = bwd_final<2>(a, yp, trow, cg, grow, lane, a_ring, bars);
-        else if (nqf == 3) inv = bwd_final<3>(a, yp, trow, cg, grow, lane, a_ring, bars);
-        else inv = bwd_final<4>(a, yp, trow, cg, grow, lane, a_ring, bars);
+        const float sf = img_scale[a.nl - 1];
+        if (nqf == 1) inv = bwd_final<1>(a, yp, trow, cg, grow, lane, a_ring, bars, sf);
+        else if (nqf == 2) inv = bwd_final<2>(a, yp, trow, cg, grow, lane, a_ring, bars, sf);
+        else if (nqf == 3) inv = bwd_final<3>(a, yp, trow, cg, grow, lane, a_ring, bars, sf);
+        else inv = bwd_final<4>(a, yp, trow, cg, grow, lane, a_ring, bars, sf);
         if (tid == 0) TL(0, 21);
         for (int q = a.nl - 1; q >= 1; --q) {
             mbar_wait(&bars->accum[q], 0);
+            if (img_scale[q] > 0.f) mbar_wait(&bars->img_done[q], 0);       // the epilogue reuses the A ring
             __syncwarp();
             tc_fence_after();
             if (tid == 0) TL(0, 22 + 4 * q);
             const int nq = a.N[q - 1] >> 6;
-            if (nq == 1) inv = bwd_epilogue<1>(a, q, inv, yp, tlane, trow, cg, grow, lane, a_ring, b_ring, bars);
-            else if (nq == 2) inv = bwd_epilogue<2>(a, q, inv, yp, tlane, trow, cg, grow, lane, a_ring, b_ring, bars);
-            else if (nq == 3) inv = bwd_epilogue<3>(a, q, inv, yp, tlane, trow, cg, grow, lane, a_ring, b_ring, bars);
-            else if (nq == 4) inv = bwd_epilogue<4>(a, q, inv, yp, tlane, trow, cg, grow, lane, a_ring, b_ring, bars);
-            else inv = bwd_epilogue<8>(a, q, inv, yp, tlane, trow, cg, grow, lane, a_ring, b_ring, bars);
+            const float sq = img_scale[q - 1];
+            if (nq == 1) inv = bwd_epilogue<1>(a, q, inv, yp, tlane, trow, cg, grow, lane, a_ring, b_ring, bars, sq);
+            else if (nq == 2) inv = bwd_epilogue<2>(a, q, inv, yp, tlane, trow, cg, grow, lane, a_ring, b_ring, bars, sq);
+            else if (nq == 3) inv = bwd_epilogue<3>(a, q, inv, yp, tlane, trow, cg, grow, lane, a_ring, b_ring, bars, sq);
+            else if (nq == 4) inv = bwd_epilogue<4>(a, q, inv, yp, tlane, trow, cg, grow, lane, a_ring, b_ring, bars, sq);
+            else inv = bwd_epilogue<8>(a, q, inv, yp, tlane, trow, cg, grow, lane, a_ring, b_ring, bars, sq);
             if (tid == 0) TL(0, 23 + 4 * q);
         }
         if (tid == 0) TL(0, 39);
@@ -1049,16 +1136,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad16_kernel(WgArgs a) {
     const int kvalid = min(L.bn, L.K - k0);
     const int n_mma = (kvalid + 15) & ~15;
 
+    if (warp == MMA_WARP) tmem_alloc(&bars->tmem_slot, 512);
+    griddep_wait();
+    // operands straight from the images the forward / backward kernels left behind (bulk copies, no conversion here),
+    // unless this step's dZ image of the layer was abandoned (first step, or a value outside the stale scale's range)
+    const float wsc = (L.ximg && L.dzimg && L.wscale) ? *L.wscale : 0.f;
+    const bool fast = wsc > 0.f && *L.img_bad == 0u;
     if (tid == 0) {
         for (int s = 0; s < WG_STAGES; ++s) {
-            mbar_init(&bars->full[s], NW);
+            mbar_init(&bars->full[s], fast ? 1 : NW);
             mbar_init(&bars->empty[s], 1);
         }
         mbar_init(&bars->accum, 1);
         fence_mbar_init();
     }
-    if (warp == MMA_WARP) tmem_alloc(&bars->tmem_slot, 512);
-    griddep_wait();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -1067,6 +1158,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad16_kernel(WgArgs a) {
 
     if (warp >= NW) {
         regs_control();
+        if (warp == TMA_WARP && fast && lane == 0) {
+            // per 64-row stage: dZ chunks 2 mt, 2 mt + 1 (hi | lo) and the xhat chunks of this column tile (hi | lo),
+            // 8 KB each (rows 0..63 or 64..127 of a 128-row image tile)
+            const int ncn = L.N >> 6, nck = (L.K + 63) >> 6;
+            const int na = min(2, ncn - 2 * mt), nb = (n_mma + 63) >> 6;
+            const int stage = 2 * WG_A_HALF + 2 * L.bn * 128;
+            const uint32_t bytes = (uint32_t)(2 * (na + nb)) * 8192u;
+            for (int it = 0; it < n_chunks; ++it) {
+                const int s = it % WG_STAGES;
+                mbar_wait(&bars->empty[s], ((uint32_t)(it / WG_STAGES) & 1u) ^ 1u);
+                const int r = r_begin + it * 64;
+                const size_t tile = (size_t)(r >> 7), half = (size_t)((r >> 6) & 1) * 4096;
+                uint8_t* dst = ring + s * stage;
+                mbar_arrive_expect_tx(&bars->full[s], bytes);
+                for (int c = 0; c < na; ++c) {
+                    const uint16_t* src = L.dzimg + (tile * ncn + 2 * mt + c) * 16384 + half;
+                    bulk_g2s(dst + c * 8192, src, 8192, &bars->full[s]);
+                    bulk_g2s(dst + WG_A_HALF + c * 8192, src + 8192, 8192, &bars->full[s]);
+                }
+                for (int c = 0; c < nb; ++c) {
+                    const uint16_t* src = L.ximg + (tile * nck + (k0 >> 6) + c) * 16384 + half;
+                    bulk_g2s(dst + 2 * WG_A_HALF + c * 8192, src, 8192, &bars->full[s]);
+                    bulk_g2s(dst + 2 * WG_A_HALF + L.bn * 128 + c * 8192, src + 8192, 8192, &bars->full[s]);
+                }
+            }
+        }
         if (warp == MMA_WARP) {
             // converged warp, elected lane issues (see mma_layer_impl).  MN-major tiles: LBO = next 64 MN elements
             // (1024 B), SBO = next 8 contraction rows (atoms x 1024 B); one K = 16 step = two 8-row groups.
@@ -1074,7 +1191,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad16_kernel(WgArgs a) {
             const uint32_t sbo_b = (uint32_t)(L.bn / 64) * 1024u;
             const uint32_t idesc = make_idesc_f16(n_mma, 1, 1);
             const uint32_t ring_base = smem_u32(ring);
-            const uint64_t da0 = make_smem_desc(0, 1024, 2048), db0 = make_smem_desc(0, 1024, sbo_b);
+            // converted tiles interleave the 64-wide MN atoms inside every 8-row group (LBO 1024, SBO atoms x 1024); image
+            // tiles keep each atom's 64 rows together (8 KB per 64-wide chunk: LBO 8192, SBO 1024)
+            const uint64_t da0 = fast ? make_smem_desc(0, 8192, 1024) : make_smem_desc(0, 1024, 2048);
+            const uint64_t db0 = fast ? make_smem_desc(0, 8192, 1024) : make_smem_desc(0, 1024, sbo_b);
+            const uint32_t kstep_a = fast ? 2048u : 4096u, kstep_b = fast ? 2048u : 2u * sbo_b;
             const uint32_t a_dhi = (uint32_t)(da0 >> 32), a_dlo = (uint32_t)da0;
             const uint32_t b_dhi = (uint32_t)(db0 >> 32), b_dlo = (uint32_t)db0;
             for (int it = 0; it < n_chunks; ++it) {
@@ -1086,12 +1207,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad16_kernel(WgArgs a) {
                 const uint32_t b_hi = b_dlo | (((ring_base + s * stage + 2 * WG_A_HALF) >> 4) & 0x3FFFu);
                 const uint32_t b_lo = b_hi + (uint32_t)((L.bn * 128) >> 4);
                 const int rem = r_end - (r_begin + it * 64);
-                const int nk = rem >= 64 ? 4 : (rem + 15) >> 4;
+                const int nk = (fast || rem >= 64) ? 4 : (rem + 15) >> 4;       // image rows >= M are zero
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         if (k < nk) {
-                            const uint32_t ka = (uint32_t)(k * 4096) >> 4, kb = (uint32_t)(k * 2 * sbo_b) >> 4;
+                            const uint32_t ka = ((uint32_t)k * kstep_a) >> 4, kb = ((uint32_t)k * kstep_b) >> 4;
                             const uint32_t acc = (it | k) != 0 ? 1u : 0u;
                             mma_f16_lohi(tmem_base + 256, a_lo + ka, a_dhi, b_hi + kb, b_dhi, idesc, acc);
                             mma_f16_lohi(tmem_base + 256, a_hi + ka, a_dhi, b_lo + kb, b_dhi, idesc, 1u);
@@ -1110,11 +1231,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad16_kernel(WgArgs a) {
     } else {
         regs_worker();
         float inv;
-        const float sc = pow2_scale_from_max(__uint_as_float(*L.dzmax), inv);
+        float sc = pow2_scale_from_max(__uint_as_float(*L.dzmax), inv);
         float csum[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) csum[i] = 0.f;
-        if (L.bn == 64) wgrad_worker<64>(L, n0, k0, r_begin, r_end, sc, ring, bars, tid, lane, csum);
+        if (fast) {
+            inv = 1.0f / wsc;
+            sc = wsc;
+            // the tensor core is fed by the loader warp; the workers only add up the bias gradient (column sums of the
+            // fp32 dZ rows: thread = row tid / 8 of a 64-row chunk, every 8th float4 of the 128 columns), two chunks in flight
+            if (ct == 0) {
+                const int ml = tid >> 3, r8 = tid & 7;
+                for (int r = r_begin + ml; r < r_end; r += 128) {
+                    const float* z0 = L.dZ + (size_t)r * L.N + n0;
+                    const bool ok1 = r + 64 < r_end;
+                    const float* z1 = z0 + (size_t)64 * L.N;
+                    float4 v0[4], v1[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int n = (r8 + 8 * e) * 4;
+                        const bool okn = n0 + n < L.N;
+                        v0[e] = okn ? ld4(z0 + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v1[e] = (okn && ok1) ? ld4(z1 + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        csum[4 * e] += v0[e].x; csum[4 * e + 1] += v0[e].y; csum[4 * e + 2] += v0[e].z; csum[4 * e + 3] += v0[e].w;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        csum[4 * e] += v1[e].x; csum[4 * e + 1] += v1[e].y; csum[4 * e + 2] += v1[e].z; csum[4 * e + 3] += v1[e].w;
+                    }
+                }
+            }
+        } else if (L.bn == 64) wgrad_worker<64>(L, n0, k0, r_begin, r_end, sc, ring, bars, tid, lane, csum);
         else if (L.bn == 128) wgrad_worker<128>(L, n0, k0, r_begin, r_end, sc, ring, bars, tid, lane, csum);
         else if (L.bn == 192) wgrad_worker<192>(L, n0, k0, r_begin, r_end, sc, ring, bars, tid, lane, csum);
         else wgrad_worker<256>(L, n0, k0, r_begin, r_end, sc, ring, bars, tid, lane, csum);
@@ -1248,7 +1398,17 @@ __global__ void __launch_bounds__(256) prep16_kernel(PrepArgs t) {
     if (j == t.n) {
         // final layer fold: wf2 = gamma_F w_F, cf2 = c_F + beta_F . w_F (one warp, fixed order)
         for (int k = gtid; k < t.KF; k += gsz) t.wf2[k] = t.gF[k] * t.wF[k];
-        if (t.dzmax && gtid < UB200_MAX_LAYERS) t.dzmax[gtid] = 0u;
+        if (t.dzmax && gtid < UB200_MAX_LAYERS) {
+            if (t.wscale) {
+                // scale of this step's dZ image: the previous step's max lands in [2^7, 2^8) - a factor 128 of head-room
+                // below kImgMaxAbs; without a previous maximum (first step) the old scale, initially 0 = "no image", stays
+                const unsigned int mb = t.dzmax[gtid];
+                const int eb = (int)((mb >> 23) & 255u);
+                if (mb != 0u) t.wscale[gtid] = (eb >= 16 && eb <= 240) ? __uint_as_float((uint32_t)(261 - eb) << 23) : 0.f;
+                t.img_bad[gtid] = 0u;
+            }
+            t.dzmax[gtid] = 0u;
+        }
         if (blockIdx.x == 0 && threadIdx.x < 32) {
             float s = 0.f;
             for (int k = threadIdx.x; k < t.KF; k += 32) s = fmaf(t.bF[k], t.wF[k], s);
@@ -1327,6 +1487,7 @@ int make_tmap_f32(CUtensorMap* m, const float* base, size_t rows, size_t cols) {
     return 0;
 }
 
+size_t img_bytes(int M, int cols) { return (size_t)((M + 127) / 128) * ((cols + 63) / 64) * A_STAGE; }
 size_t prep_bytes_wf(int K, int N) { return (size_t)((K + 63) / 64) * 2 * N * 64 * sizeof(uint16_t); }
 size_t prep_bytes_wd(int K, int N) { return (size_t)((N + 63) / 64) * 2 * K * 64 * sizeof(uint16_t); }
 

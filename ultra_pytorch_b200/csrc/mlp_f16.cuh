@@ -33,6 +33,10 @@ struct PrepArgs {
     float* wf2;                                 // [KF] gamma_F * w_F
     float* cf2;                                 // [1]  c_F + beta_F . w_F
     unsigned int* dzmax;                        // [UB200_MAX_LAYERS] running maxima of this step's backward pass: reset here
+    // operand images of the weight-gradient kernel (see ImgInfo below): before the maxima are reset, the power-of-two
+    // scale of this step's dZ_j images is derived from the maxima the PREVIOUS step left behind; img_bad is cleared
+    float* wscale;                              // [UB200_MAX_LAYERS] (0 = no history: no image this step); nullptr: off
+    unsigned int* img_bad;                      // [UB200_MAX_LAYERS]
 };
 
 struct FwdArgs {
@@ -56,6 +60,11 @@ struct FwdArgs {
     // TMA descriptors of Y[q] viewed as [M rows, N_q cols] fp32 with a 32-column x 128-row box and the 128B swizzle: the
     // epilogue stages 64-column chunks in shared memory and one thread issues the (fully coalesced) tensor stores
     CUtensorMap ymap[MAXF];
+    // training: every A-operand stage this launch builds (normalised input of layer q, fp16 hi | lo, 128 rows x 64
+    // columns, 128B swizzle: 32 KB) is also copied to ximg[q] + (row_tile * ceil(K_q / 64) + chunk) * 32 KB by a bulk
+    // shared->global copy: the K-major [m][k] tile IS the MN-major B operand of the weight gradient, which then gets its
+    // operands from the TMA engine instead of re-reading and re-converting fp32 activations (nullptr: no image)
+    uint16_t* ximg[MAXF];
 };
 // 2-D fp32 tensor map [rows, cols] (row-major), box 32 cols x 128 rows, SWIZZLE_128B
 int make_tmap_f32(CUtensorMap* m, const float* base, size_t rows, size_t cols);
@@ -74,8 +83,17 @@ struct BwdArgs {
     unsigned int* dzmax[MAXF];                  // out: running max |dZ_q| (float bits, atomicMax) for the weight-gradient scale
     CUtensorMap ymap[MAXF];                     // Y[q] / dZ[q] as [M, N_q] fp32, 32-column x 128-row boxes, 128B swizzle
     CUtensorMap dzmap[MAXF];
+    // weight-gradient operand images of dZ_q (same tile format as FwdArgs::ximg; (row_tile * N_q / 64 + chunk) * 32 KB).
+    // They carry ONE power-of-two scale per layer, wscale[q], derived from the previous step's max |dZ_q| (this step's
+    // is only known when the kernel is over).  The data-gradient GEMM uses the same tiles; a row whose values would
+    // leave the fp16 range under that scale falls back to its own row scale and raises img_bad[q], which sends the
+    // weight gradient of that layer down the fp32 path for this step.  nullptr / wscale == 0: no image.
+    uint16_t* dzimg[MAXF];
+    const float* wscale;                        // [>= nl] (device)
+    unsigned int* img_bad;                      // [>= nl] (device)
 };
 
+size_t img_bytes(int M, int cols);                    // operand image of an [M, cols] activation / gradient matrix
 size_t prep_bytes_wf(int K, int N);
 size_t prep_bytes_wd(int K, int N);
 int prep(const PrepArgs& a, cudaStream_t st);
@@ -103,6 +121,11 @@ struct WgLayer {
     int bn;                       // column tile of the B operand in shared memory (64 / 128 / 192 / 256)
     int m_tiles, col_tiles, splits, rows_per_split;
     int cta_begin;                // first CTA of this layer in the grid
+    // operand images written by the forward / backward kernels (nullptr: convert from fp32 in this kernel)
+    const uint16_t* ximg;         // [M / 128 tiles][ceil(K / 64) chunks][hi | lo][128 x 64]
+    const uint16_t* dzimg;        // [M / 128 tiles][N / 64 chunks][hi | lo][128 x 64], scaled by *wscale
+    const float* wscale;
+    const unsigned int* img_bad;  // != 0: this step's dZ image is not usable
 };
 struct WgArgs {
     int n, M, total_ctas;

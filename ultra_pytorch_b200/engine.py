@@ -596,10 +596,12 @@ class RankerEngine(object):
                                     self._pub_host.data_ptr() + 256, _ptr(self._pub_counter),
                                     self._pub_stream.cuda_stream), "ub200_publish")
         self._pub_n = scalars.numel()
+        self._pub_forked = True
 
     def join_publish(self):
         """The side stream must re-join before the step ends (CUDA-graph capture needs a single sink)."""
-        if getattr(self, "_pub_host", None) is not None:
+        if getattr(self, "_pub_forked", False):       # only behind a publish of this step (a join inside a CUDA-graph
+            self._pub_forked = False                  # capture must not depend on the side stream's earlier, uncaptured work)
             torch.cuda.current_stream().wait_stream(self._pub_stream)
 
     def read_published(self, timeout_s=20.0, lag=0):
