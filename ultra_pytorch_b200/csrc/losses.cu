@@ -8,7 +8,8 @@
 
 namespace ub200 {
 
-constexpr int kLossBlocks = 2 * kNumSMs;       // K3 and the DLA variant of K2
+constexpr int kLossBlocks = 3 * kNumSMs;       // workspace rows; K3 and the long-list DLA kernels launch at most 2 per SM,
+                                               // the short-list DLA kernel (<= 80 registers) 3
 constexpr int kLossBlocksWide = 8 * kNumSMs;   // K2 (NA / IPW): enough resident warps to cover the HBM latency
 
 // workspace: [counter (uint, padded to 64 floats)] [partials: kLossBlocks x width floats]
@@ -67,6 +68,14 @@ __device__ __forceinline__ float group_max(float v) {
     return v;
 }
 
+// exp(x) for x <= ~0 as ONE multiply + ex2.approx.ftz (the non-ftz __expf adds a range test and two scalings per call:
+// 5 instructions; results below 2^-126 flush to zero, which the softmax sums do not see)
+__device__ __forceinline__ float exp_ftz(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
+}
+
 template <int MODE, int G, int EPL>   // MODE 0 = no weights, 1 = IPW table
 __global__ void __launch_bounds__(256) softmax_ce_reg_kernel(const float* __restrict__ scores,
                                                               const float* __restrict__ labels, int B, int L,
@@ -112,7 +121,7 @@ __global__ void __launch_bounds__(256) softmax_ce_reg_kernel(const float* __rest
 #pragma unroll
         for (int e = 0; e < EPL; ++e) {
             const bool ok = live && gl + G * e < L;
-            pe[e] = ok ? __expf(sv[e] - m) : 0.f;                      // ex2.approx: |rel err| < 2^-21, argument <= 0
+            pe[e] = ok ? exp_ftz(sv[e] - m) : 0.f;                      // ex2.approx: |rel err| < 2^-21, argument <= 0
             esum += pe[e];
             float pw = 1.f;
             if (MODE == 1) pw = (yv[e] > 0.f) ? tw[e] : 0.f;           // ipw_rank.py:116-128
@@ -258,58 +267,46 @@ __global__ void __launch_bounds__(256) dla_reg_kernel(const float* __restrict__ 
 #pragma unroll
         for (int e = 0; e < EPL; ++e) {
             const bool ok = live && gl + G * e < L;
-            pe[e] = ok ? __expf(sv[e] - m) : 0.f;
+            pe[e] = ok ? exp_ftz(sv[e] - m) : 0.f;
             esum += pe[e];
         }
         esum = group_sum<G>(esum);
-        const float pe0 = __shfl_sync(0xffffffffu, pe[0], gi * G);      // position 0 lives in the group's first lane
-        float W = 0.f, We = 0.f;
+        const float s0 = __shfl_sync(0xffffffffu, sv[0], gi * G);       // position 0 lives in the group's first lane
+        // one reduction phase for everything that is linear in the weights: W = sum w, A = sum w s, and the same for the
+        // examination loss (its targets lp are the log-softmax of the propensity logits).  With d = w / W:
+        //   -sum d (s - lse) = lse - A / W,   sum d = 1,   (softmax(s) sum d - d) W = softmax(s) W - w
+        float W = 0.f, We = 0.f, A = 0.f, Ae = 0.f;
 #pragma unroll
         for (int e = 0; e < EPL; ++e) {
             const bool ok = live && gl + G * e < L;
             const float yl = yv[e] + 1e-7f;
             w[e] = ok ? yl * pwt[e] : 0.f;
-            we[e] = ok ? yl * (pe0 / pe[e]) : 0.f;                       // softmax(s)_0 / softmax(s)_l
+            we[e] = ok ? yl * exp_ftz(s0 - sv[e]) : 0.f;                 // softmax(s)_0 / softmax(s)_l
             W += w[e];
             We += we[e];
+            A = fmaf(w[e], ok ? sv[e] : 0.f, A);
+            Ae = fmaf(we[e], lp[e], Ae);
         }
         W = group_sum<G>(W);
         We = group_sum<G>(We);
-        const float lse = m + logf(esum);
-        const float inv_e = 1.f / esum;
-        const float inv_W = (W != 0.f) ? 1.f / W : 0.f;
-        const float inv_We = (We != 0.f) ? 1.f / We : 0.f;
-        float ll = 0.f, dsum = 0.f, lle = 0.f, dsum_e = 0.f;
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) {
-            const bool ok = live && gl + G * e < L;
-            const float d = w[e] * inv_W, de = we[e] * inv_We;
-            w[e] = d;
-            we[e] = de;
-            if (ok) {
-                ll = fmaf(-d, sv[e] - lse, ll);
-                lle = fmaf(-de, lp[e], lle);
-            }
-            dsum += d;
-            dsum_e += de;
-        }
-        ll = group_sum<G>(ll);
-        dsum = group_sum<G>(dsum);
-        lle = group_sum<G>(lle);
-        dsum_e = group_sum<G>(dsum_e);
+        A = group_sum<G>(A);
+        Ae = group_sum<G>(Ae);
         if (live) {
+            const float lse = m + __logf(esum);
+            const float pW = (W != 0.f) ? __fdividef(W, esum) : 0.f;               // W / Z: softmax(s)_l W = pe_l pW
+            const float pWe = (We != 0.f) ? We : 0.f;
 #pragma unroll
             for (int e = 0; e < EPL; ++e) {
                 const int l = gl + G * e;
                 if (l < L) {
-                    dscores[(size_t)b * L + l] = (pe[e] * inv_e * dsum - w[e]) * W;
-                    gacc[e] += (smp[e] * dsum_e - we[e]) * We;
+                    dscores[(size_t)b * L + l] = fmaf(pe[e], pW, -w[e]);
+                    gacc[e] += fmaf(smp[e], pWe, -we[e]);
                 }
             }
             if (gl == 0) {
-                num += ll * W;
+                num += (W != 0.f) ? fmaf(lse, W, -A) : 0.f;               // ll W = (lse - A / W) W
                 den += W;
-                num_e += lle * We;
+                num_e -= (We != 0.f) ? Ae : 0.f;                         // lle We = -(Ae / We) We
                 den_e += We;
             }
         }
@@ -858,9 +855,9 @@ extern "C" UB200_API size_t ub200_pair_workspace_bytes(int B, int L) {
     return loss_ws_bytes(2 * (L > 0 ? L : 0) + 2);
 }
 
-static int loss_grid(int B, int lists_per_block) {
+static int loss_grid(int B, int lists_per_block, int per_sm = 2) {
     int g = (B + lists_per_block - 1) / lists_per_block;
-    if (g > kLossBlocks) g = kLossBlocks;
+    if (g > per_sm * kNumSMs) g = per_sm * kNumSMs;
     return g < 1 ? 1 : g;
 }
 
@@ -928,13 +925,16 @@ extern "C" UB200_API int ub200_dla_loss(const float* scores, const float* clicks
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (L <= 256) {
         // register-resident lists: G lanes per list, EPL positions per lane (as ub200_softmax_ce)
-        const int G = L <= 64 ? 8 : (L <= 128 ? 16 : 32);
+        // short lists: 4 lanes per list (8 lists per warp instruction, 2-step reductions, no idle register slots at L = 20)
+        const int G = L <= 32 ? 4 : (L <= 64 ? 8 : (L <= 128 ? 16 : 32));
         const int epl = (L + G - 1) / G;
-        const int grid = loss_grid(B, 8 * (32 / G));
+        const int grid = loss_grid(B, 8 * (32 / G), (G == 4 && epl <= 5) ? 3 : 2);
 #define UB_DLA(G_, EPL_)                                                                                           \
         launch_k(dla_reg_kernel<G_, EPL_>, grid, 256, 0, st, scores, clicks, B, L, prop_w, prop_b, dscores, dprop, \
                  sums, w.counter, w.partials)
-        if (G == 8) {
+        if (G == 4) {
+            if (epl <= 3) UB_DLA(4, 3); else if (epl <= 5) UB_DLA(4, 5); else UB_DLA(4, 8);
+        } else if (G == 8) {
             if (epl <= 2) UB_DLA(8, 2); else if (epl <= 3) UB_DLA(8, 3); else if (epl <= 5) UB_DLA(8, 5); else UB_DLA(8, 8);
         } else if (G == 16) {
             if (epl <= 6) UB_DLA(16, 6); else UB_DLA(16, 8);
