@@ -535,6 +535,13 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict
 // ------------------------------------------------------------------------------------------------
 // K3: pairwise losses, one CTA per list
 // ------------------------------------------------------------------------------------------------
+// 1 / x as ONE rcp.approx.ftz (<= 1 ulp; the IEEE division expands to ~8 instructions).  Used on the pair path of K3,
+// where every unordered pair needs four reciprocals of values in [1, 2].
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
 __device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
 __device__ __forceinline__ float safe_div_f(float n, float d) { return d == 0.f ? 0.f : n / d; }
@@ -708,7 +715,7 @@ __global__ void __launch_bounds__(512) pairwise_kernel(const float* __restrict__
                         const float ya = own_first ? yi : ys[j], yb = own_first ? ys[j] : yi;
                         const float w = delta * (own_first ? tpi * rtp[j] : tp[j] * rtpi);     // delta-NDCG * ipw_a * pw_b
                         const float d = sigma * (sa - sb);
-                        const float p = 1.f / (expf(-d) + 1.f);                               // prs_rank.py:139
+                        const float p = rcp_fast(expf(-d) + 1.f);                             // prs_rank.py:139
                         const float t = 0.5f * (1.f + fminf(fmaxf(ya - yb, -1.f), 1.f));
                         // F.binary_cross_entropy clamps both logarithms at -100 and divides by max(p (1 - p), 1e-12)
                         // in its backward pass
@@ -724,17 +731,17 @@ __global__ void __launch_bounds__(512) pairwise_kernel(const float* __restrict__
                     if (act && delta != 0.f) {
                         const float d = sigma * (si - ps[j]);
                         // p_ij = 1 / (exp(-d) + 1), p_ji = 1 / (exp(d) + 1) from ONE exponential of -|d| (no overflow)
-                        const float e = expf(-fabsf(d));
-                        const float p_big = 1.f / (1.f + e), p_small = e * p_big;
+                        const float e = exp_ftz(-fabsf(d));
+                        const float p_big = rcp_fast(1.f + e), p_small = e * p_big;
                         const float pij = d >= 0.f ? p_big : p_small, pji = d >= 0.f ? p_small : p_big;
                         const float Sij = fminf(fmaxf(yi - ys[j], -1.f), 1.f);
                         const float Pij = 0.5f * (1.f + Sij), Pji = 0.5f * (1.f - Sij);
                         // BCEWithLogits applied to the probability p (lambda_rank.py:128): p - p*P + log1p(exp(-p));
                         // its derivative needs sigmoid(p) = 1 / (1 + exp(-p)) of the same exponential
-                        const float uij = __expf(-pij), uji = __expf(-pji);
+                        const float uij = exp_ftz(-pij), uji = exp_ftz(-pji);
                         const float tij = delta * (pij - pij * Pij + __logf(1.f + uij));
                         const float tji = delta * (pji - pji * Pji + __logf(1.f + uji));
-                        const float sgij = 1.f / (1.f + uij), sgji = 1.f / (1.f + uji);
+                        const float sgij = rcp_fast(1.f + uij), sgji = rcp_fast(1.f + uji);
                         const float tpj = tp[j], tmj = tm[j], rtpj = rtp[j], rtmj = rtm[j];
                         const float inv_ij = (tpi * tmj == 0.f) ? 0.f : rtpi * rtmj;      // metrics._safe_div
                         const float inv_ji = (tpj * tmi == 0.f) ? 0.f : rtpj * rtmi;
