@@ -193,6 +193,11 @@ UB200_API int ub200_em_update(float* t_plus, float* t_minus, const float* out, i
  * step of the batch are still running; everything later on the stream stays ordered behind them. */
 UB200_API int ub200_publish(const float* src, int n, float* host_dst, unsigned int* host_seq, unsigned int* dev_counter,
                   void* stream);
+/* L2 regularisation (hparam l2_loss of NavieAlgorithm / IPWrank / DLA / PairDebias / RegressionEM, e.g.
+ * ipw_rank.py:153-157 + base_algorithm.py:332-333): grads[i] += l2 * params[i] * f with f = den[0] (device, the
+ * normaliser ub200_clip_update divides by) or `factor` when den is NULL; half_sumsq[0] = sum(params^2) / 2. */
+UB200_API int ub200_l2_term(const float* params, float* grads, size_t n, float l2, const float* den, float factor,
+                  float* half_sumsq, void* stream);
 UB200_API size_t ub200_opt_workspace_bytes(size_t n);
 UB200_API int ub200_clip_update(float* params, float* grads, float* state_sum, size_t n, const float* den, float scale_const,
                       float max_norm, float lr, int mode, float* norm_out,

@@ -417,7 +417,8 @@ class OracleTrainer:
     DenoisingNet parameters."""
 
     def __init__(self, algo, params, feature_size, hidden, L_train, ipw_table=None, prop_params=None,
-                 learning_rate=None, max_gradient_norm=5.0, sigma=1.0, em_step=0.05, reg_p=1.0, dt=np.float32):
+                 learning_rate=None, max_gradient_norm=5.0, sigma=1.0, em_step=0.05, reg_p=1.0, dt=np.float32,
+                 l2_loss=0.0):
         self.algo = algo
         self.dt = dt
         self.hidden = list(hidden)
@@ -432,6 +433,7 @@ class OracleTrainer:
         self.lr = defaults[algo] if learning_rate is None else learning_rate
         self.max_norm = max_gradient_norm
         self.sigma, self.em_step, self.reg_p = sigma, em_step, reg_p
+        self.l2 = dt(l2_loss)              # hparam l2_loss (NA / IPW / DLA / PairDebias / RegressionEM)
         self.ipw_table = ipw_table
         if algo == "dla":
             self.prop_w = np.array(prop_params["linear_layer.weight"], dtype=dt).reshape(-1)
@@ -483,8 +485,21 @@ class OracleTrainer:
         else:
             raise ValueError(self.algo)
         grads = dnn_backward(scores_grad_to_rows(ds), cache, self.params, self.n_layers, dt)
+        if self.l2 > 0 and self.algo in ("na", "ipw", "dla", "pairdebias", "regem"):
+            # loss += l2 * sum(p ** 2) / 2 for every ranker parameter (ipw_rank.py:153-157, navie_algorithm.py:110-114,
+            # pairwise_debias.py:167-169, regression_EM.py:167-169, base_algorithm.py:332-333; dla.py:146-150 adds it to
+            # rank_loss, whose weight in the total loss is ranker_loss_weight = 1 here) -> gradient l2 * p
+            for n in self.names:
+                loss = loss + self.l2 * dt(np.sum(self.params[n].astype(dt) ** 2) / 2)
+                grads[n] = grads[n] + self.l2 * self.params[n]
         self.last = dict(scores=s, dscores=ds, grads=grads, loss=loss)
+        # with l2_loss > 0 the reference hands clip_grad_norm_ the generator its L2 loop has already exhausted
+        # (ipw_rank.py:153-159, navie_algorithm.py:108-116, pairwise_debias.py:166-171, regression_EM.py:164-178):
+        # nothing is clipped; dla.py:161-163 builds new iterators and clips
+        no_clip = self.l2 > 0 and self.algo in ("na", "ipw", "pairdebias", "regem")
         norm, clipped = clip_grad_norm(grads, self.names, self.max_norm, dt)
+        if no_clip:
+            clipped = {n: grads[n].astype(dt) for n in self.names}
         if self.algo == "dla":
             pg = {"w": extra["dprop_w"], "b": np.asarray(extra["dprop_b"])}
             _, pc = clip_grad_norm(pg, ["w", "b"], self.max_norm, dt)

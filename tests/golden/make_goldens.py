@@ -62,6 +62,10 @@ CASES = [
     ("dla_c5like", "dla", 220, 100, 100, 8, [512, 256, 128], "click", 1, True),
     ("lambdarank_c4like", "lambdarank", 136, 200, 200, 8, [512, 256, 128], "graded", 1, True),
     ("pairdebias_c2net", "pairdebias", 136, 40, 40, 16, [256, 128, 64], "click", 1, True),
+    # a non-default algorithm hparam (trailing string): L2 regularisation of the ranker parameters
+    ("ipw_l2", "ipw", 10, 6, 8, 8, [16, 8], "click", 3, False, "l2_loss=0.01"),
+    ("dla_l2", "dla", 10, 6, 8, 8, [16, 8], "click", 2, False, "l2_loss=0.01"),
+    ("pairdebias_l2", "pairdebias", 10, 6, 6, 8, [16, 8], "click", 2, False, "l2_loss=0.01"),
 ]
 
 
@@ -103,7 +107,7 @@ def state_to_np(sd, prefix):
     return {prefix + k: v.detach().cpu().numpy().copy() for k, v in sd.items()}
 
 
-def run_case(ultra, name, algo, F, L_train, L_max, B, hidden, kind, n_steps, compact=False):
+def run_case(ultra, name, algo, F, L_train, L_max, B, hidden, kind, n_steps, compact=False, hparams=""):
     random.seed(0)
     np.random.seed(0)
     torch.manual_seed(0)
@@ -115,7 +119,7 @@ def run_case(ultra, name, algo, F, L_train, L_max, B, hidden, kind, n_steps, com
     ultra.utils.metrics.RankingMetricKey.MAX_LABEL = 4.0
     exp_settings = {
         "learning_algorithm": ALGOS[algo],
-        "learning_algorithm_hparams": "",
+        "learning_algorithm_hparams": hparams,
         "ranking_model": "ultra.ranking_model.DNN" if hidden else "ultra.ranking_model.Linear",
         "ranking_model_hparams": ("hidden_layer_sizes=%s" % str(hidden)) if hidden else "",
         "selection_bias_cutoff": L_train,
@@ -148,6 +152,7 @@ def run_case(ultra, name, algo, F, L_train, L_max, B, hidden, kind, n_steps, com
     out["meta_hidden"] = np.asarray(hidden, dtype=np.int64)
     out["meta_n_steps"] = np.int64(n_steps)
     out["meta_algo"] = np.asarray(algo)
+    out["meta_hparams"] = np.asarray(hparams)
     out.update(state_to_np(model.model.state_dict(), "init/"))
     if algo == "dla":
         out.update(state_to_np(model.propensity_model.state_dict(), "init_prop/"))

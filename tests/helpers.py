@@ -54,3 +54,14 @@ def grad_floor(grads):
 def assert_close(a, ref, rtol=RTOL, what="", floor=0.0):
     e = scaled_err(a, ref, floor)
     assert e <= rtol, "%s: scaled error %.3e > %.1e" % (what, e, rtol)
+
+
+def golden_hparams(g):
+    """non-default algorithm hparams a golden was generated with (meta_hparams, e.g. "l2_loss=0.01") as keyword
+    arguments of oracle.OracleTrainer"""
+    text = str(g["meta_hparams"]) if "meta_hparams" in g else ""
+    out = {}
+    for item in filter(None, text.split(",")):
+        k, v = item.split("=")
+        out[k] = float(v)
+    return out

@@ -46,6 +46,8 @@ def build_from_golden(g, tmp_path):
         with open(p, "w") as f:
             json.dump({"IPW_list": [float(v) for v in g["ipw_table"]]}, f)
         hp = "propensity_estimator_json=%s" % p
+    if "meta_hparams" in g and str(g["meta_hparams"]):
+        hp = (hp + "," if hp else "") + str(g["meta_hparams"])
     exp_settings = {
         "learning_algorithm_hparams": hp,
         "ranking_model": "ultra_pytorch_b200.ranking_model.%s" % ("DNN" if len(g["meta_hidden"]) else "Linear"),
@@ -132,13 +134,22 @@ def test_train_steps_match_reference(name, tmp_path):
         ref_loss = float(g[pre + "loss"])
         assert abs(loss - ref_loss) <= 1e-5 * abs(ref_loss), (name, step, loss, ref_loss)
         gref = sub(g, pre + "grad/")
+        have_grads = bool(gref)
+        if not have_grads:
+            # l2_loss > 0 under NA / IPW / PairDebias: the reference clips an exhausted parameter generator (nothing), and
+            # the recording hook of make_goldens.py sits in that call - no gradients in the golden; the loss and the
+            # post-step parameters pin the step.  Mask with the plugin's own gradients instead.
+            gref = {n: named[n].grad.detach().cpu().numpy() for n in sub(g, pre + "param/")}
         floor = grad_floor(gref)
         total = np.sqrt(sum(float((v.astype(np.float64) ** 2).sum()) for v in gref.values()))
         coef = min(1.0, 5.0 / (total + 1e-6))          # the plugin leaves the CLIPPED gradient in .grad
-        for n, ref in gref.items():
+        for n, ref in (gref.items() if have_grads else ()):
             got = named[n].grad.detach().cpu().numpy()
             assert_close(got, ref * coef, 1e-5, "%s step %d grad %s" % (name, step, n), floor * coef)
+        nh = len(g["meta_hidden"])
         for n, ref in sub(g, pre + "param/").items():
+            if not have_grads and (n.endswith("layer_norm%d.bias" % nh) or n.endswith("linear%d.bias" % nh)):
+                continue                                # shift-invariant tensors: loss gradient == 0 (see below)
             ok = np.abs(gref[n]) > 1e-3 * floor         # see tests/test_oracle_vs_golden.py on zero gradients
             got = named[n].detach().cpu().numpy()
             assert_close(got[ok], ref[ok], 1e-5, "%s step %d param %s" % (name, step, n))

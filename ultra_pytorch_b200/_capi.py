@@ -48,6 +48,7 @@ SIGNATURES = {
     "ub200_publish": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "ub200_opt_workspace_bytes": (_sz, [_sz]),
     "ub200_clip_update": (_i, [_vp, _vp, _vp, _sz, _vp, _f, _f, _f, _i, _vp, _vp, _sz, _vp]),
+    "ub200_l2_term": (_i, [_vp, _vp, _sz, _f, _vp, _f, _vp, _vp]),
     "ub200_pl_sample": (_i, [_vp, _vp, _i, _i, _i, _f, ctypes.c_ulonglong, ctypes.c_ulonglong, _vp, _vp]),
     "ub200_click_batch": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, ctypes.c_ulonglong,
                                ctypes.c_ulonglong, _vp, _vp, _vp, _vp]),

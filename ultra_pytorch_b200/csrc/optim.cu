@@ -227,6 +227,40 @@ extern "C" UB200_API int ub200_publish(const float* src, int n, float* host_dst,
     return 0;
 }
 
+// L2 regularisation of the reference algorithms (hparam l2_loss, e.g. ipw_rank.py:153-157: loss += l2 * sum(p^2) / 2 over
+// every ranker parameter): adds l2 * p * f to the UN-normalised gradient buffer, f = den[0] (the normaliser the update
+// kernel later divides by) or `factor`, and writes sum(p^2) / 2.  One block: fixed summation order.
+__global__ void __launch_bounds__(1024) l2_term_kernel(const float* __restrict__ p, float* __restrict__ g, size_t n, float l2,
+                                                       const float* __restrict__ den, float factor,
+                                                       float* __restrict__ half_sumsq) {
+    griddep_launch();
+    griddep_wait();
+    __shared__ float red[32];
+    const float f = l2 * (den ? den[0] : factor);
+    float s = 0.f;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = p[i];
+        g[i] = fmaf(f, v, g[i]);
+        s = fmaf(v, v, s);
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) half_sumsq[0] = 0.5f * t;
+    }
+}
+
+extern "C" UB200_API int ub200_l2_term(const float* params, float* grads, size_t n, float l2, const float* den, float factor,
+                                       float* half_sumsq, void* stream) {
+    UB_CHECK(params && grads && half_sumsq && n > 0, 2, "l2_term: null pointer / empty buffer");
+    launch_k(l2_term_kernel, 1, 1024, 0, static_cast<cudaStream_t>(stream), params, grads, n, l2, den, factor, half_sumsq);
+    UB_LAUNCH_CHECK("l2_term_kernel");
+    return 0;
+}
+
 extern "C" UB200_API size_t ub200_opt_workspace_bytes(size_t n) {
     (void)n;
     return opt_ws_bytes();

@@ -626,6 +626,14 @@ class RankerEngine(object):
         return self._pub_np[half:half + self._pub_n].copy()
 
     # ---- optimizer ------------------------------------------------------------------------------------
+    def l2_term(self, l2, den, factor):
+        """grads += l2 * params * (den[0] or factor); returns the device scalar sum(params^2) / 2 (hparam l2_loss)."""
+        if getattr(self, "_l2_half_sumsq", None) is None:
+            self._l2_half_sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
+        check(lib.ub200_l2_term(_ptr(self.params), _ptr(self.grads), self.P, float(l2), _ptr(den), float(factor),
+                                _ptr(self._l2_half_sumsq), _stream()), "ub200_l2_term")
+        return self._l2_half_sumsq
+
     def clip_update(self, params, grads, state_sum, den, scale_const, max_norm, lr, mode, norm_out=None):
         n = params.numel()
         check(lib.ub200_clip_update(_ptr(params), _ptr(grads), _ptr(state_sum), n, _ptr(den), float(scale_const),

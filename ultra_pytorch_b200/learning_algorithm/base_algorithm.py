@@ -151,6 +151,7 @@ class B200Algorithm(_reference_base()):
     # copies the next batch beside it.  The reference has no multi-process mode, so there is no contract to keep; the
     # value is the exact global loss, one step late.  UB200_DP_LAG_LOSS=0 restores the blocking read of the own step.
     LAG_LOSS_DP = os.environ.get("UB200_DP_LAG_LOSS", "1") != "0"
+    L2_EXHAUSTS_CLIP_PARAMS = True      # see _exchange_and_update (DLA overrides)
 
     def _device_step_published(self, st):
         out = self.device_step(st)
@@ -251,6 +252,20 @@ class B200Algorithm(_reference_base()):
         happen in one kernel; otherwise ONE all-reduce (NCCL) and the single-GPU optimizer kernel."""
         eng = self.engine
         mg = self.hparams.max_gradient_norm
+        l2 = float(getattr(self.hparams, "l2_loss", 0.0) or 0.0)
+        if l2 > 0:
+            # loss += l2 * sum(p^2) / 2 over the ranker's parameters (e.g. ipw_rank.py:153-157): its gradient l2 * p joins
+            # the un-normalised buffer scaled by what the update divides by.  Before the exchange every rank adds its
+            # share (the normalisers sum over the ranks; a constant scale is split evenly); in the 'post' phase of the
+            # two-graph NCCL path the buffer already holds the global sums.
+            share = self.world_size() if self._phase is None else 1
+            self._l2_half_sumsq = eng.l2_term(l2, den, 1.0 / (float(scale_const) * share))
+            # Reference behaviour, kept: NA / IPW / PairDebias / RegressionEM loop over `params = self.model.parameters()`
+            # - a generator - to add the L2 terms and then hand the EXHAUSTED generator to clip_grad_norm_ (e.g.
+            # ipw_rank.py:153-159 -> base_algorithm.py:222-225), which therefore clips nothing when l2_loss > 0.
+            # DLA re-creates the iterator (dla.py:161-163) and does clip.
+            if self.L2_EXHAUSTS_CLIP_PARAMS:
+                mg = 0.0
         fused = os.environ.get("UB200_DP_FUSED", "1") != "0"
         if self.world_size() > 1 and eng.peer is not None and fused:
             eng.dp_reduce_update(state_sum, den, scale_const, mg, lr, mode, norm_out)
@@ -378,5 +393,12 @@ class B200Algorithm(_reference_base()):
         return 1 if fresh else 0
 
     def _check_l2(self):
-        if getattr(self.hparams, "l2_loss", 0.0) > 0:
-            raise NotImplementedError("l2_loss > 0 is not implemented in the B200 path (reference default is 0.0)")
+        """l2_loss > 0 is applied in _exchange_and_update (gradient) and _l2_loss_value (reported loss)."""
+        self._l2_half_sumsq = None
+
+    def _l2_loss_value(self):
+        """l2_loss * sum(p^2) / 2 of the parameters the step started from (one extra scalar read; 0.0 when off)."""
+        l2 = float(getattr(self.hparams, "l2_loss", 0.0) or 0.0)
+        if l2 <= 0 or getattr(self, "_l2_half_sumsq", None) is None:
+            return 0.0
+        return l2 * float(self._l2_half_sumsq.item())

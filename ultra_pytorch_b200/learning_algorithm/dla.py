@@ -77,6 +77,8 @@ class DLA(B200Algorithm):
         self._norm = None
         self._norm_pending = False
 
+    L2_EXHAUSTS_CLIP_PARAMS = False     # dla.py:161-163 clips fresh parameter iterators
+
     def device_step(self, st):
         eng = self.engine
         L, B = st.L, st.B
@@ -125,7 +127,7 @@ class DLA(B200Algorithm):
             self.model.train()
         st = self._stage(input_feed, self.rank_list_size)
         s = self._read_scalars(self.run_step(st))
-        self.rank_loss = float(s[0] / s[1])
+        self.rank_loss = float(s[0] / s[1]) + self._l2_loss_value()
         self.exam_loss = float(s[2] / s[3])
         self.loss = self.exam_loss + self.hparams.ranker_loss_weight * self.rank_loss
         if len(s) >= 6:

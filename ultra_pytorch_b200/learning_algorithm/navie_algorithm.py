@@ -55,6 +55,6 @@ class NavieAlgorithm(B200Algorithm):
             self.model.train()
         st = self._stage(input_feed, self.rank_list_size)
         s = self._read_scalars(self.run_step(st))
-        self.loss = float(s[0] / s[1])
+        self.loss = float(s[0] / s[1]) + self._l2_loss_value()
         self._say(self.loss)
         return self.loss, None, self.train_summary

@@ -70,7 +70,7 @@ class PairDebias(B200Algorithm):
             self.model.train()
         st = self._stage(input_feed, self.rank_list_size)
         s = self._read_scalars(self.run_step(st))
-        self.loss = float(s[0]) * self._b_global
+        self.loss = float(s[0]) * self._b_global + self._l2_loss_value()
         if self.VERBOSE:
             print(" Loss %f at Global Step %d" % (self.loss, self.global_step))
         self.global_step += 1

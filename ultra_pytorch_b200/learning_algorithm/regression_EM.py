@@ -73,7 +73,7 @@ class RegressionEM(B200Algorithm):
             self.model.train()
         st = self._stage(input_feed, self.rank_list_size)
         s = self._read_scalars(self.run_step(st))
-        self.loss = float(s[0] / s[1])
+        self.loss = float(s[0] / s[1]) + self._l2_loss_value()
         self.update_propensity_op = self.propensity
         self.global_step += 1
         if self.VERBOSE:
