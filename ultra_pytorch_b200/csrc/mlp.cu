@@ -73,19 +73,6 @@ static bool f16_images_on(const LayerDims& d) {
     }
     return widest >= 100000;
 }
-static bool use_side_streams();
-// Experiment kept behind UB200_XIMG=1 (default off).  Small batches (the forward / data-gradient kernels leave >= 48 SMs
-// idle) of nets that do not write the images inside those kernels: a kernel of its own converts the layer inputs into
-// x-hat images on a side stream while the loss and the data-gradient chain run, and the weight-gradient kernel converts
-// dZ only.  Measured at config 2 (profiles/r02_images_ab.txt): wgrad16 27.5 -> 17.9 us as intended, but the 23.6 MB of
-// image writes per step reach DRAM and slow their neighbours down - bwd16 30.8 -> 36.2 us (concurrent), the NEXT step's
-// fwd16 30.4 -> 41.0 us - a net loss (0.1316 -> 0.1386 ms/step).
-static bool f16_side_images_on(const LayerDims& d, int M) {
-    const int need = TC_F16_FWD | TC_F16_BWD | TC_F16_WGRAD | TC_F16_IMG;
-    if ((tc_mode() & need) != need || !f16_bwd_ok(d) || f16_images_on(d) || !use_side_streams()) return false;
-    static const int on = [] { const char* e = getenv("UB200_XIMG"); return (e && e[0] == '1') ? 1 : 0; }();
-    return on && kNumSMs - (M + 127) / 128 >= 48;
-}
 static bool use_tc(int j, int K, int N, int what = 7) { return (tc_mode() & what) != 0 && tc_layer_ok(j, K, N); }
 
 
@@ -984,29 +971,6 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
     };
 
     const bool chain16 = (tc_mode() & TC_F16_BWD) && f16_bwd_ok(d);
-    const bool side_img = ss && chain16 && (tc_mode() & TC_F16_WGRAD) && w.wscale && f16_side_images_on(d, M);
-    if (side_img) {
-        // x-hat images of every hidden layer's input, on side stream 0 beside the data-gradient chain (joined before the
-        // weight-gradient kernel); event slot UB200_MAX_LAYERS is not used by any layer
-        f16::XimgArgs xa{};
-        xa.n = nl - 1;
-        xa.M = M;
-        for (int j = 0; j < nl - 1; ++j) {
-            xa.X[j] = (j == 0) ? feats : w.Y[j - 1];
-            xa.docid[j] = (j == 0) ? docid : nullptr;
-            xa.stats[j] = w.stats[j];
-            xa.img[j] = w.ximg[j];
-            xa.K[j] = d.K[j];
-            xa.chunk_begin[j + 1] = xa.chunk_begin[j] + (d.K[j] + 63) / 64;
-        }
-        cudaEventRecord(ss->fork_ev[UB200_MAX_LAYERS], st);
-        cudaStreamWaitEvent(ss->s[0], ss->fork_ev[UB200_MAX_LAYERS], 0);
-        {
-            PriorityScope p(prio_lo);
-            if (int rc = f16::ximg(xa, ss->s[0])) return rc;
-        }
-        cudaEventRecord(ss->done_ev[UB200_MAX_LAYERS], ss->s[0]);
-    }
     // final layer (N = 1): parameter-gradient partials (+ dZ_{nl-2} into dz[(nl-2) % 3] on the per-layer path).  With the
     // fused chain this kernel only feeds the final layer's own gradients, so it runs on a side stream next to the chain.
     {
@@ -1078,11 +1042,8 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
                 l.dzimg = w.dzimg[j];
                 l.wscale = w.wscale + j;
                 l.img_bad = w.img_bad + j;
-            } else if (side_img) {
-                l.ximg = w.ximg[j];
             }
         }
-        if (side_img) cudaStreamWaitEvent(st, ss->done_ev[UB200_MAX_LAYERS], 0);
         if (int rc = f16::wgrad(wa, st)) return rc;
         for (int j = nl - 2; j >= 0; --j) {
             const int K = d.K[j], N = d.N[j];

@@ -1041,13 +1041,12 @@ __device__ __forceinline__ uint32_t mn_off(uint32_t m, uint32_t x, uint32_t atom
            (x & 7u) * 2u;
 }
 
-// WITH_B = false: the B operand (x-hat) arrives from its image by bulk copies (loader warp); the workers convert dZ only
-template <int BN, bool WITH_B = true>
+template <int BN>
 __device__ __forceinline__ void wgrad_worker(const WgLayer& L, int n0, int k0, int r_begin, int r_end, float sc,
                                              uint8_t* ring, WgBars* bars, int tid, int lane, float* csum) {
     constexpr int ATOMS_B = BN / 64;
     constexpr int STAGE = 2 * WG_A_HALF + 2 * BN * 128;
-    constexpr int EB = WITH_B ? BN / 32 : 1;             // float4 per thread per chunk of the B operand
+    constexpr int EB = BN / 32;                          // float4 per thread per chunk of the B operand
     const int ml = tid >> 3, r8 = tid & 7;
     const int n_chunks = (r_end - r_begin + 63) >> 6;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1057,12 +1056,8 @@ __device__ __forceinline__ void wgrad_worker(const WgLayer& L, int n0, int k0, i
         const int m = r_begin + it * 64 + ml;
         const bool ok = m < r_end;
         const float* zrow = L.dZ + (size_t)m * L.N + n0;
-        const float* xrow = nullptr;
-        float2 st = make_float2(0.f, 0.f);
-        if (WITH_B) {
-            xrow = L.X + (size_t)(ok ? (L.docid ? L.docid[m] : m) : 0) * L.K + k0;
-            if (ok) st = L.stats[m];
-        }
+        const float* xrow = L.X + (size_t)(ok ? (L.docid ? L.docid[m] : m) : 0) * L.K + k0;
+        const float2 st = ok ? L.stats[m] : make_float2(0.f, 0.f);
         rso = st.y;
         nbo = -st.x * st.y;
 #pragma unroll
@@ -1070,12 +1065,10 @@ __device__ __forceinline__ void wgrad_worker(const WgLayer& L, int n0, int k0, i
             const int n = (r8 + 8 * e) * 4;
             a4[e] = (ok && n0 + n < L.N) ? ld4(zrow + n) : zero4;
         }
-        if (WITH_B) {
 #pragma unroll
-            for (int e = 0; e < EB; ++e) {
-                const int k = (r8 + 8 * e) * 4;
-                b4[e] = (ok && k0 + k < L.K) ? ld4(xrow + k) : make_float4(st.x, st.x, st.x, st.x);   // -> xhat = 0
-            }
+        for (int e = 0; e < EB; ++e) {
+            const int k = (r8 + 8 * e) * 4;
+            b4[e] = (ok && k0 + k < L.K) ? ld4(xrow + k) : make_float4(st.x, st.x, st.x, st.x);   // -> xhat = 0
         }
     };
     if (n_chunks > 0) load_chunk(0, av, bv, nb, rs);
@@ -1098,7 +1091,7 @@ __device__ __forceinline__ void wgrad_worker(const WgLayer& L, int n0, int k0, i
             *reinterpret_cast<uint2*>(a_hi + WG_A_HALF + off) = make_uint2(l0, l1);
         }
 #pragma unroll
-        for (int e = 0; e < (WITH_B ? EB : 0); ++e) {
+        for (int e = 0; e < EB; ++e) {
             const float4 v = bv[e];
             uint32_t h0, h1, l0, l1;
             split_h2(fmaf(v.x, rs, nb), fmaf(v.y, rs, nb), h0, l0);
@@ -1149,13 +1142,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad16_kernel(WgArgs a) {
     // unless this step's dZ image of the layer was abandoned (first step, or a value outside the stale scale's range)
     const float wsc = (L.ximg && L.dzimg && L.wscale) ? *L.wscale : 0.f;
     const bool fast = wsc > 0.f && *L.img_bad == 0u;
-    // x-hat image only (written by ximg_kernel beside the data-gradient chain, or dZ's image abandoned this step): the B
-    // operand arrives by bulk copies, the workers convert dZ alone
-    const bool mixed = !fast && L.ximg != nullptr;
-    const bool b_img = fast || mixed;
     if (tid == 0) {
         for (int s = 0; s < WG_STAGES; ++s) {
-            mbar_init(&bars->full[s], fast ? 1 : (mixed ? NW + 1 : NW));
+            mbar_init(&bars->full[s], fast ? 1 : NW);
             mbar_init(&bars->empty[s], 1);
         }
         mbar_init(&bars->accum, 1);
@@ -1169,11 +1158,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad16_kernel(WgArgs a) {
 
     if (warp >= NW) {
         regs_control();
-        if (warp == TMA_WARP && b_img && lane == 0) {
+        if (warp == TMA_WARP && fast && lane == 0) {
             // per 64-row stage: dZ chunks 2 mt, 2 mt + 1 (hi | lo) and the xhat chunks of this column tile (hi | lo),
             // 8 KB each (rows 0..63 or 64..127 of a 128-row image tile)
             const int ncn = L.N >> 6, nck = (L.K + 63) >> 6;
-            const int na = fast ? min(2, ncn - 2 * mt) : 0, nb = (n_mma + 63) >> 6;
+            const int na = min(2, ncn - 2 * mt), nb = (n_mma + 63) >> 6;
             const int stage = 2 * WG_A_HALF + 2 * L.bn * 128;
             const uint32_t bytes = (uint32_t)(2 * (na + nb)) * 8192u;
             for (int it = 0; it < n_chunks; ++it) {
@@ -1205,8 +1194,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad16_kernel(WgArgs a) {
             // converted tiles interleave the 64-wide MN atoms inside every 8-row group (LBO 1024, SBO atoms x 1024); image
             // tiles keep each atom's 64 rows together (8 KB per 64-wide chunk: LBO 8192, SBO 1024)
             const uint64_t da0 = fast ? make_smem_desc(0, 8192, 1024) : make_smem_desc(0, 1024, 2048);
-            const uint64_t db0 = b_img ? make_smem_desc(0, 8192, 1024) : make_smem_desc(0, 1024, sbo_b);
-            const uint32_t kstep_a = fast ? 2048u : 4096u, kstep_b = b_img ? 2048u : 2u * sbo_b;
+            const uint64_t db0 = fast ? make_smem_desc(0, 8192, 1024) : make_smem_desc(0, 1024, sbo_b);
+            const uint32_t kstep_a = fast ? 2048u : 4096u, kstep_b = fast ? 2048u : 2u * sbo_b;
             const uint32_t a_dhi = (uint32_t)(da0 >> 32), a_dlo = (uint32_t)da0;
             const uint32_t b_dhi = (uint32_t)(db0 >> 32), b_dlo = (uint32_t)db0;
             for (int it = 0; it < n_chunks; ++it) {
@@ -1275,11 +1264,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad16_kernel(WgArgs a) {
                     }
                 }
             }
-        } else if (mixed) {
-            if (L.bn == 64) wgrad_worker<64, false>(L, n0, k0, r_begin, r_end, sc, ring, bars, tid, lane, csum);
-            else if (L.bn == 128) wgrad_worker<128, false>(L, n0, k0, r_begin, r_end, sc, ring, bars, tid, lane, csum);
-            else if (L.bn == 192) wgrad_worker<192, false>(L, n0, k0, r_begin, r_end, sc, ring, bars, tid, lane, csum);
-            else wgrad_worker<256, false>(L, n0, k0, r_begin, r_end, sc, ring, bars, tid, lane, csum);
         } else if (L.bn == 64) wgrad_worker<64>(L, n0, k0, r_begin, r_end, sc, ring, bars, tid, lane, csum);
         else if (L.bn == 128) wgrad_worker<128>(L, n0, k0, r_begin, r_end, sc, ring, bars, tid, lane, csum);
         else if (L.bn == 192) wgrad_worker<192>(L, n0, k0, r_begin, r_end, sc, ring, bars, tid, lane, csum);
@@ -1349,59 +1333,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad16_kernel(WgArgs a) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
-}
-
-// block = one 128-row x 64-column image tile; thread = 32 columns of one row (same arithmetic as the converting
-// producer of wgrad16: xhat = fma(x, rstd, -mean rstd), split into fp16 hi + lo)
-__global__ void __launch_bounds__(256) ximg_kernel(XimgArgs a) {
-    griddep_launch();
-    griddep_wait();
-    const int total_chunks = a.chunk_begin[a.n];
-    const int tile = blockIdx.x / total_chunks, gc = blockIdx.x - tile * total_chunks;
-    int q = 0;
-    while (q + 1 < a.n && gc >= a.chunk_begin[q + 1]) ++q;
-    const int chunk = gc - a.chunk_begin[q], nch = a.chunk_begin[q + 1] - a.chunk_begin[q];
-    const int K = a.K[q];
-    const int row = threadIdx.x >> 1, half = threadIdx.x & 1;
-    const int m = tile * 128 + row;
-    const bool ok = m < a.M;
-    const int c0 = chunk * 64 + half * 32;
-    uint16_t* hi = a.img[q] + ((size_t)tile * nch + chunk) * (A_STAGE / 2);
-    uint16_t* lo = hi + A_HALF / 2;
-    float2 st = make_float2(0.f, 0.f);
-    const float* xr = nullptr;
-    if (ok) {
-        st = a.stats[q][m];
-        xr = a.X[q] + (size_t)(a.docid[q] ? a.docid[q][m] : m) * K;
-    }
-    const float rs = st.y, nb = -st.x * st.y;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {                       // 16-byte units: 8 columns each
-        float v[8];
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            const int c = c0 + u * 8 + p * 4;
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok && c < K) {
-                t = ld4(xr + c);
-                t.x = fmaf(t.x, rs, nb); t.y = fmaf(t.y, rs, nb); t.z = fmaf(t.z, rs, nb); t.w = fmaf(t.w, rs, nb);
-            }
-            v[4 * p] = t.x; v[4 * p + 1] = t.y; v[4 * p + 2] = t.z; v[4 * p + 3] = t.w;
-        }
-        uint32_t h[4], l[4];
-#pragma unroll
-        for (int p = 0; p < 4; ++p) split_h2(v[2 * p], v[2 * p + 1], h[p], l[p]);
-        const uint32_t off = swz128((uint32_t)row, (uint32_t)(half * 4 + u));
-        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(hi) + off) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(lo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
-    }
-}
-
-int ximg(const XimgArgs& a, cudaStream_t st) {
-    const int tiles = (a.M + 127) / 128;
-    launch_k(ximg_kernel, dim3(tiles * a.chunk_begin[a.n]), 256, 0, st, a);
-    UB_LAUNCH_CHECK("ximg_kernel");
-    return 0;
 }
 
 void wgrad_plan(WgArgs* a, int sm_budget) {

@@ -132,19 +132,6 @@ struct WgArgs {
     WgLayer l[UB200_MAX_LAYERS];
 };
 
-// x-hat images by a kernel of their own (small batches: the forward kernel leaves SMs idle, and this kernel runs beside
-// the loss and the data-gradient chain): layer q's normalised input rows -> FwdArgs::ximg tiles
-struct XimgArgs {
-    int n, M;
-    const float* X[UB200_MAX_LAYERS];          // input rows of layer q [*, K_q]
-    const int32_t* docid[UB200_MAX_LAYERS];    // row gather (layer 0) or nullptr
-    const float2* stats[UB200_MAX_LAYERS];     // (mean, rstd) of the input rows [M]
-    uint16_t* img[UB200_MAX_LAYERS];
-    int K[UB200_MAX_LAYERS];
-    int chunk_begin[UB200_MAX_LAYERS + 1];     // prefix sums of ceil(K_q / 64)
-};
-int ximg(const XimgArgs& a, cudaStream_t st);
-
 // fills bn / tiles / splits / cta_begin of every layer for a budget of `sm_budget` CTAs (one wave); rows per split are
 // capped so that one accumulator never sees more than 2048 contraction rows (accumulation error, partial-plane traffic)
 void wgrad_plan(WgArgs* a, int sm_budget);
