@@ -870,6 +870,7 @@ __device__ __forceinline__ float bwd_epilogue(const BwdArgs& a, int q, float inv
     }
 }
 
+template <bool IMG>      // IMG = false: no operand images (the image code is compiled out, as in wgrad16_kernel)
 __global__ void __launch_bounds__(NTHREADS, 1) bwd16_kernel(const __grid_constant__ BwdArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -884,7 +885,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd16_kernel(const __grid_constan
     // weight-gradient images of dZ_q: on when the layer has a buffer and a scale from the previous step
     float img_scale[MAXF];
 #pragma unroll
-    for (int q = 0; q < MAXF; ++q) img_scale[q] = (q < a.nl && a.dzimg[q] && a.wscale) ? a.wscale[q] : 0.f;
+    for (int q = 0; q < MAXF; ++q) img_scale[q] = (IMG && q < a.nl && a.dzimg[q] && a.wscale) ? a.wscale[q] : 0.f;
     if (tid == 0) {
 #pragma unroll
         for (int q = 0; q < MAXF; ++q) {
@@ -931,7 +932,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd16_kernel(const __grid_constan
             mma_layer(tmem_base, a.N[q], bn, nh, 0, a_ring, b_ring, bars->a_full[q], bars->a_empty[q], bars->b_full[q],
                       bars->b_empty[q], &bars->accum[q]);
         }
-      } else if (warp == IMG_WARP) {
+      } else if (IMG && warp == IMG_WARP) {
         if (lane == 0)
             for (int q = a.nl - 1; q >= 0; --q) {
                 if (!(img_scale[q] > 0.f)) continue;
@@ -1112,6 +1113,9 @@ __device__ __forceinline__ void wgrad_worker(const WgLayer& L, int n0, int k0, i
     }
 }
 
+// IMG = false: the converting path only (nets that do not write operand images; kept as its own instantiation because
+// the extra code of the image path cost the converting path ~20 % at large batch through register allocation)
+template <bool IMG>
 __global__ void __launch_bounds__(NTHREADS, 1) wgrad16_kernel(WgArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1140,8 +1144,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad16_kernel(WgArgs a) {
     griddep_wait();
     // operands straight from the images the forward / backward kernels left behind (bulk copies, no conversion here),
     // unless this step's dZ image of the layer was abandoned (first step, or a value outside the stale scale's range)
-    const float wsc = (L.ximg && L.dzimg && L.wscale) ? *L.wscale : 0.f;
-    const bool fast = wsc > 0.f && *L.img_bad == 0u;
+    const float wsc = (IMG && L.ximg && L.dzimg && L.wscale) ? *L.wscale : 0.f;
+    const bool fast = IMG && wsc > 0.f && *L.img_bad == 0u;
     if (tid == 0) {
         for (int s = 0; s < WG_STAGES; ++s) {
             mbar_init(&bars->full[s], fast ? 1 : NW);
@@ -1370,10 +1374,14 @@ void wgrad_plan(WgArgs* a, int sm_budget) {
 int wgrad(const WgArgs& a, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        if (int rc = set_smem(wgrad16_kernel, "wgrad16_kernel")) return rc;
+        if (int rc = set_smem(wgrad16_kernel<false>, "wgrad16_kernel")) return rc;
+        if (int rc = set_smem(wgrad16_kernel<true>, "wgrad16_kernel<img>")) return rc;
         configured = true;
     }
-    launch_k(wgrad16_kernel, dim3(a.total_ctas), NTHREADS, SMEM_BYTES, st, a);
+    bool img = false;
+    for (int i = 0; i < a.n; ++i) img = img || (a.l[i].ximg && a.l[i].dzimg);
+    if (img) launch_k(wgrad16_kernel<true>, dim3(a.total_ctas), NTHREADS, SMEM_BYTES, st, a);
+    else launch_k(wgrad16_kernel<false>, dim3(a.total_ctas), NTHREADS, SMEM_BYTES, st, a);
     UB_LAUNCH_CHECK("wgrad16_kernel");
     return 0;
 }
@@ -1539,10 +1547,14 @@ int bwd_grid(int M) { return (M + 127) / 128; }
 int bwd(const BwdArgs& a, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        if (int rc = set_smem(bwd16_kernel, "bwd16_kernel")) return rc;
+        if (int rc = set_smem(bwd16_kernel<false>, "bwd16_kernel")) return rc;
+        if (int rc = set_smem(bwd16_kernel<true>, "bwd16_kernel<img>")) return rc;
         configured = true;
     }
-    launch_k(bwd16_kernel, dim3(bwd_grid(a.M)), NTHREADS, SMEM_BYTES, st, a);
+    bool img = false;
+    for (int q = 0; q < a.nl; ++q) img = img || a.dzimg[q] != nullptr;
+    if (img) launch_k(bwd16_kernel<true>, dim3(bwd_grid(a.M)), NTHREADS, SMEM_BYTES, st, a);
+    else launch_k(bwd16_kernel<false>, dim3(bwd_grid(a.M)), NTHREADS, SMEM_BYTES, st, a);
     UB_LAUNCH_CHECK("bwd16_kernel");
     return 0;
 }
