@@ -221,3 +221,59 @@ def test_direct_label_feed_is_bit_identical_to_the_reference(use_max):
     same(one, ours_b1.get_next_batch(5, ds)[0])
     with pytest.raises(NotImplementedError):
         ours.get_batch(ds, data_format="ULTRE")
+
+
+@pytest.mark.parametrize("name", ["user_browsing_model", "cascade_model"])
+def test_sequential_click_models_match_the_reference_in_distribution(name):
+    """UserBrowsingModel / CascadeModel (click_models.py:112-236) in array form: per-position click rates AND the rate of
+    a click at position r given the previous click position (the dependence these models add) against the reference's
+    own sampleClicksForOneList, 5 sigma on 40 000 lists each."""
+    ultra = ref_shim.load()
+    from ultra_pytorch_b200.input_layer.click_simulation_feed import load_click_model
+    cm_ref = {"user_browsing_model": ultra.utils.click_models.UserBrowsingModel,
+              "cascade_model": ultra.utils.click_models.CascadeModel}[name](0.1, 1.0, 4, 1.0)
+    desc = cm_ref.getModelJson()
+    cm = load_click_model(json.loads(json.dumps(desc)))
+    L, n = 12, 40000
+    labels = np.array([3, 0, 4, 1, 2, 0, 0, 4, 1, 3, 2, 0], dtype=np.float64)
+    ours = cm.sample(np.tile(labels, (n, 1)), np.random.default_rng(1))
+    random.seed(2)
+    ref = np.array([cm_ref.sampleClicksForOneList(list(labels))[0] for _ in range(n)], dtype=np.float64)
+
+    def prev_click(c):
+        idx = np.where(c > 0, np.arange(L)[None, :], -1)
+        run = np.maximum.accumulate(idx, axis=1)
+        return np.concatenate([np.full((c.shape[0], 1), -1), run[:, :-1]], axis=1)
+    for a, b, what in ((ours.mean(0), ref.mean(0), "marginal"),):
+        se = np.sqrt((a * (1 - a) + b * (1 - b)) / n) + 1e-9
+        assert (np.abs(a - b) <= 5 * se + 1e-3).all(), (name, what, a, b)
+    po, pr = prev_click(ours), prev_click(ref)
+    for r in range(1, L):
+        for last in (-1, r - 1, r - 2):
+            so, sr = po[:, r] == last, pr[:, r] == last
+            if so.sum() < 500 or sr.sum() < 500:
+                continue
+            a, b = ours[so, r].mean(), ref[sr, r].mean()
+            se = np.sqrt(a * (1 - a) / so.sum() + b * (1 - b) / sr.sum()) + 1e-9
+            assert abs(a - b) <= 5 * se + 2e-3, (name, r, last, a, b)
+    # setExamProb(eta) rebuilds the same table as the reference
+    cm.setExamProb(0.5)
+    cm_ref.setExamProb(0.5)
+    assert np.allclose(np.asarray(cm.exam_prob[-1]), np.asarray(cm_ref.exam_prob[-1]))
+
+
+def test_feed_with_a_cascade_click_model(tmp_path):
+    from ultra_pytorch_b200.input_layer import ClickSimulationFeed
+    L, F, B = 7, 5, 64
+    ds = FakeData(80, L, F)
+    p = os.path.join(str(tmp_path), "cascade.json")
+    with open(p, "w") as f:
+        json.dump({"model_name": "cascade_model", "eta": 1.0, "click_prob": [0.1, 0.16, 0.28, 0.52, 1.0],
+                   "exam_prob": [1.0] * 10}, f)
+    feed = ClickSimulationFeed(_model(L, F), B, "click_model_json=%s" % p)
+    random.seed(0)
+    f, _ = feed.get_batch(ds, check_validation=True)
+    clicks = np.stack([f["label%d" % l] for l in range(L)], axis=1)
+    assert (clicks.sum(axis=1) == 1).all()          # cascade: exactly one click per (validated) list
+    with pytest.raises(NotImplementedError):
+        ClickSimulationFeed(_model(L, F), B, "click_model_json=%s,device_batches=True" % p).get_batch(ds, True)

@@ -21,13 +21,113 @@ from .resident import DeviceFeed, ResidentFeatures
 ORIGINAL_EXAM_PROB = [0.68, 0.61, 0.48, 0.34, 0.28, 0.20, 0.11, 0.10, 0.08, 0.06]   # click_models.py:76-77
 
 
-class _PositionBiasedModel(object):
-    """Array form of PositionBiasedModel (click_models.py:68-110)."""
+def load_click_model(desc):
+    """Array form of click_models.loadModelFromJson (click_models.py:7-16)."""
+    name = desc.get('model_name', 'position_biased_model')
+    if name == 'user_browsing_model':
+        return _UserBrowsingModel(desc)
+    if name == 'cascade_model':
+        return _CascadeModel(desc)
+    return _PositionBiasedModel(desc)
+
+
+def _click_prob_of(labels, click_prob):
+    """click_prob[int(label) if label > 0 else 0], last entry for labels beyond the table (click_models.py:98-104)"""
+    rel = np.where(labels > 0, labels, 0).astype(np.int64)
+    rel = np.where(rel < len(click_prob), rel, len(click_prob) - 1)
+    return click_prob[rel]
+
+
+class _SequentialClickModel(object):
+    """Click models whose examination depends on earlier clicks of the same list: sampled position by position for all
+    lists of the batch at once (the reference loops over lists AND positions, sampleClicksForOneList)."""
+    position_independent = False
+
+    def click_probability(self, labels):
+        raise NotImplementedError("%s has no position-wise click probability (clicks depend on earlier clicks); the "
+                                  "device click simulator and the online feed implement the position-biased model only"
+                                  % type(self).__name__)
+
+
+class _UserBrowsingModel(_SequentialClickModel):
+    """Array form of UserBrowsingModel (click_models.py:112-185): P(exam) = table[rank][rank - last_click_rank - 1]."""
+    ORIGINAL_RD_EXAM_TABLE = [
+        [1.0],
+        [0.98, 1.0],
+        [1.0, 0.62, 0.95],
+        [1.0, 0.77, 0.42, 0.82],
+        [1.0, 0.92, 0.55, 0.31, 0.69],
+        [1.0, 0.96, 0.63, 0.4, 0.22, 0.54],
+        [1.0, 0.99, 0.73, 0.46, 0.29, 0.17, 0.47],
+        [1.0, 1.0, 0.89, 0.52, 0.35, 0.24, 0.14, 0.43],
+        [1.0, 1.0, 0.95, 0.68, 0.4, 0.29, 0.19, 0.12, 0.41],
+        [1.0, 1.0, 1.0, 0.96, 0.52, 0.36, 0.27, 0.18, 0.12, 0.43]]         # click_models.py:121-132
 
     def __init__(self, desc):
-        if desc.get('model_name', 'position_biased_model') != 'position_biased_model':
-            raise NotImplementedError("only the position_biased_model click model is vectorised (got %r)"
-                                      % desc.get('model_name'))
+        self.eta = desc['eta']
+        self.click_prob = np.asarray(desc['click_prob'], dtype=np.float64)
+        self._set_table(desc['exam_prob'])
+
+    def _set_table(self, rows):
+        n = len(rows)
+        self.exam_prob = [list(r) for r in rows]
+        self._table = np.zeros((n, n), dtype=np.float64)
+        for i, r in enumerate(rows):
+            self._table[i, :len(r)] = r
+
+    def setExamProb(self, eta):
+        self.eta = eta
+        self._set_table([[pow(x, eta) for x in row] for row in self.ORIGINAL_RD_EXAM_TABLE])
+
+    def exam_probability(self, rank, last_click_rank):
+        """getExamProb (click_models.py:174-185) for an array of last-click ranks"""
+        n = self._table.shape[0]
+        distance = rank - last_click_rank
+        if rank < n:
+            return self._table[rank, distance - 1]
+        last = self._table[n - 1]
+        idx = np.where(distance < n - 1, distance - 1, n - 2)
+        return np.where(distance > rank, last[n - 1], last[idx])
+
+    def sample(self, labels, rng):
+        n, L = labels.shape
+        clicks = np.zeros((n, L), dtype=np.float64)
+        last = np.full(n, -1, dtype=np.int64)
+        cp = _click_prob_of(labels, self.click_prob)
+        u = rng.random((n, L))
+        for r in range(L):
+            c = u[:, r] < self.exam_probability(r, last) * cp[:, r]
+            clicks[:, r] = c
+            last = np.where(c, r, last)
+        return clicks
+
+
+class _CascadeModel(_SequentialClickModel):
+    """Array form of CascadeModel (click_models.py:188-236): the user clicks at most once - every position is sampled
+    with P = exam_prob[rank] * click_prob[label], positions after the first click report no click."""
+
+    def __init__(self, desc):
+        self.eta = desc['eta']
+        self.click_prob = np.asarray(desc['click_prob'], dtype=np.float64)
+        self.exam_prob = np.asarray(desc['exam_prob'], dtype=np.float64)
+
+    def setExamProb(self, eta):
+        self.eta = eta
+        self.exam_prob = np.ones(10, dtype=np.float64)                     # click_models.py:195-197
+
+    def sample(self, labels, rng):
+        L = labels.shape[1]
+        exam = self.exam_prob[np.minimum(np.arange(L), len(self.exam_prob) - 1)]
+        c = rng.random(labels.shape) < exam[None, :] * _click_prob_of(labels, self.click_prob)
+        before = np.cumsum(c, axis=1) - c                                   # clicks strictly before each position
+        return (c & (before == 0)).astype(np.float64)
+
+
+class _PositionBiasedModel(object):
+    """Array form of PositionBiasedModel (click_models.py:68-110)."""
+    position_independent = True
+
+    def __init__(self, desc):
         self.eta = desc['eta']
         self.click_prob = np.asarray(desc['click_prob'], dtype=np.float64)
         self.exam_prob = np.asarray(desc['exam_prob'], dtype=np.float64)
@@ -90,7 +190,7 @@ class ClickSimulationFeed(object):
         self.click_model = None
         if not self.hparams.oracle_mode:
             with open(self.hparams.click_model_json) as fin:
-                self.click_model = _PositionBiasedModel(json.load(fin))
+                self.click_model = load_click_model(json.load(fin))
         self.start_index = 0
         self.count = 1
         self.rank_list_size = model.rank_list_size
@@ -126,6 +226,8 @@ class ClickSimulationFeed(object):
     def _simulate(self, labels):
         if self.hparams.oracle_mode:
             return labels.copy()
+        if not self.click_model.position_independent:
+            return self.click_model.sample(labels, self.rng)
         p = self.click_model.click_probability(labels)
         return (self.rng.random(labels.shape) < p).astype(np.float64)
 
@@ -134,6 +236,8 @@ class ClickSimulationFeed(object):
         P(click) depends only on (query, position), so a batch is one row gather + one uniform draw."""
         if self.hparams.oracle_mode:
             return self._labels[idx].copy()
+        if not self.click_model.position_independent:
+            return self.click_model.sample(self._labels[idx], self.rng)
         key = (id(self._labels), float(self.click_model.eta), self.click_model.exam_prob.tobytes())
         if getattr(self, "_pclick_key", None) != key:
             self._pclick = self.click_model.click_probability(self._labels)
@@ -178,6 +282,10 @@ class ClickSimulationFeed(object):
     # ---- N1 on the device: query sampling + click simulation + batch assembly in one kernel ------------------------
     def _device_batch(self, data_set, check_validation):
         import torch
+        if not self.hparams.oracle_mode and not self.click_model.position_independent:
+            raise NotImplementedError("device_batches=True simulates clicks with the position-biased model only; %s is "
+                                      "sampled on the host (drop device_batches, resident_features=True still applies)"
+                                      % type(self.click_model).__name__)
         eng = getattr(self.model, "engine", None)
         if eng is None:
             raise TypeError("device_batches=True needs a B200 learning algorithm (the batch is assembled in its "

@@ -36,7 +36,11 @@ class StochasticOnlineSimulationFeed(ClickSimulationFeed):
         print(hparam_str)
         self.hparams.parse(hparam_str)
         with open(self.hparams.click_model_json) as fin:
-            self.click_model = _PositionBiasedModel(json.load(fin))
+            desc = json.load(fin)
+        if desc.get('model_name', 'position_biased_model') != 'position_biased_model':
+            raise NotImplementedError("the online-simulation drop-in implements the position_biased_model click model "
+                                      "only (got %r)" % desc.get('model_name'))
+        self.click_model = _PositionBiasedModel(desc)
         self.start_index = 0
         self.count = 1
         self.rank_list_size = model.rank_list_size
