@@ -277,6 +277,14 @@ UB200_API int ub200_dp_reduce_update(float* own, size_t n, const void* const* pe
                            float scale_const, float max_norm, float lr, int mode, float* norm_out, void* ctl,
                            void* stream);
 
+/* ub200_dp_reduce_update + ub200_publish of own[pub_index, pub_index + pub_n) (the step's summed loss scalars) from inside
+ * the same kernel: a data-parallel train() returns the previous step's loss, read from host_dst / host_seq. */
+UB200_API int ub200_dp_reduce_update_publish(float* own, size_t n, const void* const* peer_inbox,
+                           const void* const* peer_flags, int rank, int world, float* params, float* state_sum,
+                           size_t n_params, long long den_index, float scale_const, float max_norm, float lr, int mode,
+                           float* norm_out, void* ctl, void* stream, long long pub_index, int pub_n, float* host_dst,
+                           unsigned int* host_seq, unsigned int* dev_counter);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,3 +10,5 @@ for c in d.get('all_configs', []):
     print(c['workload'], c['value'], c['ms_per_step'])
 PY
 tail -5 gpurun_out/bench_dp2.err | cut -c1-300
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29571 tools/trace_step_dp.py > gpurun_out/trace_dp2.txt 2>&1; tail -14 gpurun_out/trace_dp2.txt | cut -c1-150
+grep "DP " gpurun_out/pytest_dp2.log | head

@@ -60,6 +60,8 @@ SIGNATURES = {
     "ub200_dp_ctl_bytes": (_sz, []),
     "ub200_dp_reduce_update": (_i, [_vp, _sz, _vp, _vp, _i, _i, _vp, _vp, _sz, ctypes.c_longlong, _f, _f, _f, _i, _vp,
                                     _vp, _vp]),
+    "ub200_dp_reduce_update_publish": (_i, [_vp, _sz, _vp, _vp, _i, _i, _vp, _vp, _sz, ctypes.c_longlong, _f, _f, _f, _i,
+                                            _vp, _vp, _vp, ctypes.c_longlong, _i, _vp, _vp, _vp]),
 }
 
 

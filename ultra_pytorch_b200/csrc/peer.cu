@@ -153,7 +153,9 @@ __global__ void __launch_bounds__(256) dp_reduce_update_kernel(PushTable peers, 
                                                                 float* __restrict__ state, size_t n_params,
                                                                 long long den_index, float scale_const, float max_norm,
                                                                 float lr, int mode, float* __restrict__ norm_out,
-                                                                unsigned int* ctl) {
+                                                                unsigned int* ctl, long long pub_index, int pub_n,
+                                                                float* host_dst, unsigned int* host_seq,
+                                                                unsigned int* dev_counter) {
     griddep_launch();
     griddep_wait();
     __shared__ float red[8];
@@ -229,6 +231,19 @@ __global__ void __launch_bounds__(256) dp_reduce_update_kernel(PushTable peers, 
         }
     }
     __syncthreads();
+    if (pub_n > 0 && blockIdx.x == 0) {
+        // the step's summed scalars (loss normalisers in the trailing floats: every block's slice is final behind the
+        // barrier) go to mapped pinned host memory exactly as publish_kernel (optim.cu) writes them - train() of the
+        // NEXT step reads them, so no separate kernel sits at the end of a data-parallel step
+        const unsigned int c = dev_counter[0] + 1u;
+        if ((int)threadIdx.x < pub_n) host_dst[(c & 1u) * 32u + threadIdx.x] = __ldcg(own + pub_index + threadIdx.x);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            dev_counter[0] = c;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned int*>(host_seq) = c;
+        }
+    }
     if (max_norm > 0.f) sc *= fminf(max_norm / (s_norm + 1e-6f), 1.f);   // torch.nn.utils.clip_grad_norm_
     const size_t hip = hi < n_params ? hi : n_params;
     for (size_t i = lo + threadIdx.x; i < hip; i += blockDim.x) {
@@ -261,11 +276,14 @@ extern "C" UB200_API size_t ub200_dp_flag_bytes(int world) {
 }
 extern "C" UB200_API size_t ub200_dp_ctl_bytes(void) { return 64 + sizeof(float) * kNumSMs + 64; }
 
-extern "C" UB200_API int ub200_dp_reduce_update(float* own, size_t n, const void* const* peer_inbox,
-                                                const void* const* peer_flags, int rank, int world, float* params,
-                                                float* state_sum, size_t n_params, long long den_index,
-                                                float scale_const, float max_norm, float lr, int mode,
-                                                float* norm_out, void* ctl, void* stream) {
+static int dp_reduce_update_impl(float* own, size_t n, const void* const* peer_inbox, const void* const* peer_flags,
+                                 int rank, int world, float* params, float* state_sum, size_t n_params,
+                                 long long den_index, float scale_const, float max_norm, float lr, int mode,
+                                 float* norm_out, void* ctl, void* stream, long long pub_index, int pub_n,
+                                 float* host_dst, unsigned int* host_seq, unsigned int* dev_counter) {
+    UB_CHECK(pub_n == 0 || (pub_n > 0 && pub_n <= 32 && pub_index >= 0 && pub_index + pub_n <= (long long)n && host_dst &&
+                            host_seq && dev_counter),
+             1, "dp_reduce_update: bad publish arguments");
     UB_CHECK(own && peer_inbox && peer_flags && params && ctl && n > 0 && n_params <= n, 2,
              "dp_reduce_update: null pointer / bad sizes");
     UB_CHECK(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, 1,
@@ -286,9 +304,32 @@ extern "C" UB200_API int ub200_dp_reduce_update(float* own, size_t n, const void
     if (grid > kNumSMs) grid = kNumSMs;      // every block resident; the same n gives the same grid on every rank
     if (grid < 1) grid = 1;
     launch_k(dp_reduce_update_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), t, rank, world, own, n, params,
-             state_sum, n_params, den_index, scale_const, max_norm, lr, mode, norm_out, static_cast<unsigned int*>(ctl));
+             state_sum, n_params, den_index, scale_const, max_norm, lr, mode, norm_out, static_cast<unsigned int*>(ctl),
+             pub_index, pub_n, host_dst, host_seq, dev_counter);
     UB_LAUNCH_CHECK("dp_reduce_update_kernel");
     return 0;
+}
+
+extern "C" UB200_API int ub200_dp_reduce_update(float* own, size_t n, const void* const* peer_inbox,
+                                                const void* const* peer_flags, int rank, int world, float* params,
+                                                float* state_sum, size_t n_params, long long den_index,
+                                                float scale_const, float max_norm, float lr, int mode,
+                                                float* norm_out, void* ctl, void* stream) {
+    return dp_reduce_update_impl(own, n, peer_inbox, peer_flags, rank, world, params, state_sum, n_params, den_index,
+                                 scale_const, max_norm, lr, mode, norm_out, ctl, stream, 0, 0, nullptr, nullptr, nullptr);
+}
+
+// the same + ub200_publish of own[pub_index, pub_index + pub_n) (the summed scalars of the step) from inside the kernel
+extern "C" UB200_API int ub200_dp_reduce_update_publish(float* own, size_t n, const void* const* peer_inbox,
+                                                        const void* const* peer_flags, int rank, int world,
+                                                        float* params, float* state_sum, size_t n_params,
+                                                        long long den_index, float scale_const, float max_norm, float lr,
+                                                        int mode, float* norm_out, void* ctl, void* stream,
+                                                        long long pub_index, int pub_n, float* host_dst,
+                                                        unsigned int* host_seq, unsigned int* dev_counter) {
+    return dp_reduce_update_impl(own, n, peer_inbox, peer_flags, rank, world, params, state_sum, n_params, den_index,
+                                 scale_const, max_norm, lr, mode, norm_out, ctl, stream, pub_index, pub_n, host_dst,
+                                 host_seq, dev_counter);
 }
 
 extern "C" UB200_API size_t ub200_peer_ctl_bytes(void) { return 256; }

@@ -249,13 +249,35 @@ class RankerEngine(object):
         else:
             dist.all_reduce(self.gradbuf, op=dist.ReduceOp.SUM)
 
-    def dp_reduce_update(self, state_sum, den, scale_const, max_norm, lr, mode, norm_out=None):
+    def _ensure_publish_buffers(self):
+        if getattr(self, "_pub_host", None) is None:
+            self._pub_host = torch.zeros(128, dtype=torch.float32, pin_memory=True)   # 2 x 32 values, [64] seq
+            self._pub_np = self._pub_host.numpy()
+            self._pub_seq_np = self._pub_np[64:65].view(np.uint32)
+            self._pub_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._pub_stream = torch.cuda.Stream(device=self.device)
+            self._pub_launched = 0
+
+    def dp_reduce_update(self, state_sum, den, scale_const, max_norm, lr, mode, norm_out=None, publish=None):
         """Fused exchange + optimizer of the ranker's parameters (csrc/peer.cu: dp_reduce_update_kernel): SUM of the
         whole flat buffer over the ranks through NVLink peer memory, then clip_grad_norm_ + Adagrad / SGD on the summed
         gradient, in ONE kernel.  `den` is a view INTO self.gradbuf (the normaliser is read after the sum)."""
         p = self.peer
         den_index = -1 if den is None else (den.data_ptr() - self.gradbuf.data_ptr()) // 4
         assert den is None or 0 <= den_index < self.gradbuf.numel()
+        if publish is not None:
+            # `publish`: a view INTO self.gradbuf (the step's loss scalars): written to mapped host memory by the kernel
+            self._ensure_publish_buffers()
+            pub_index = (publish.data_ptr() - self.gradbuf.data_ptr()) // 4
+            assert 0 <= pub_index and pub_index + publish.numel() <= self.gradbuf.numel()
+            check(lib.ub200_dp_reduce_update_publish(
+                _ptr(self.gradbuf), self.gradbuf.numel(), p["inbox"], p["pflags"], p["rank"], p["world"],
+                _ptr(self.params), _ptr(state_sum), self.P, den_index, float(scale_const), float(max_norm), float(lr),
+                int(mode), _ptr(norm_out), _ptr(p["dp_ctl"]), _stream(), pub_index, publish.numel(),
+                self._pub_host.data_ptr(), self._pub_host.data_ptr() + 256, _ptr(self._pub_counter)),
+                "ub200_dp_reduce_update_publish")
+            self._pub_n = publish.numel()
+            return
         check(lib.ub200_dp_reduce_update(_ptr(self.gradbuf), self.gradbuf.numel(), p["inbox"], p["pflags"], p["rank"],
                                          p["world"], _ptr(self.params), _ptr(state_sum), self.P, den_index,
                                          float(scale_const), float(max_norm), float(lr), int(mode), _ptr(norm_out),
@@ -582,13 +604,7 @@ class RankerEngine(object):
         """Enqueues the copy of `scalars` (<= 32 floats, device) into mapped pinned host memory + a sequence number
         (csrc/optim.cu: publish_kernel) on a side stream forked from the current one; returns nothing - read with
         `read_published()` after the step has been launched."""
-        if getattr(self, "_pub_host", None) is None:
-            self._pub_host = torch.zeros(128, dtype=torch.float32, pin_memory=True)   # 2 x 32 values, [64] seq
-            self._pub_np = self._pub_host.numpy()
-            self._pub_seq_np = self._pub_np[64:65].view(np.uint32)
-            self._pub_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
-            self._pub_stream = torch.cuda.Stream(device=self.device)
-            self._pub_launched = 0
+        self._ensure_publish_buffers()
         cur = torch.cuda.current_stream()
         self._pub_stream.wait_stream(cur)
         with torch.cuda.stream(self._pub_stream):

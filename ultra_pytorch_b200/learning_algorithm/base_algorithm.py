@@ -154,9 +154,12 @@ class B200Algorithm(_reference_base()):
     L2_EXHAUSTS_CLIP_PARAMS = True      # see _exchange_and_update (DLA overrides)
 
     def _device_step_published(self, st):
+        self._late_fused = False
         out = self.device_step(st)
         self._late = False
-        if out is not None and self.LAG_LOSS_DP and self.world_size() > 1 and out.numel() <= 32:
+        if self._late_fused:
+            self._late = True                    # the exchange kernel has published the scalars
+        elif out is not None and self.LAG_LOSS_DP and self.world_size() > 1 and out.numel() <= 32:
             self.engine.publish(out)
             self.engine.join_publish()
             self._late = True
@@ -268,7 +271,15 @@ class B200Algorithm(_reference_base()):
                 mg = 0.0
         fused = os.environ.get("UB200_DP_FUSED", "1") != "0"
         if self.world_size() > 1 and eng.peer is not None and fused:
-            eng.dp_reduce_update(state_sum, den, scale_const, mg, lr, mode, norm_out)
+            # lagged loss (LAG_LOSS_DP): the step's summed scalars leave through the exchange kernel itself when they live
+            # in the flat buffer (they do for every algorithm: _publish_early records them)
+            pub = getattr(self, "_dp_scalars", None) if self.LAG_LOSS_DP else None
+            if pub is not None and not (eng.gradbuf.data_ptr() <= pub.data_ptr() and
+                                        pub.data_ptr() + 4 * pub.numel() <= eng.gradbuf.data_ptr() + 4 * eng.gradbuf.numel()
+                                        and pub.numel() <= 32):
+                pub = None
+            eng.dp_reduce_update(state_sum, den, scale_const, mg, lr, mode, norm_out, publish=pub)
+            self._late_fused = pub is not None
             return
         if self._phase is None:
             self._allreduce_gradbuf()
@@ -309,6 +320,7 @@ class B200Algorithm(_reference_base()):
         step (data parallel: they are summed by the exchange)."""
         if not self.EARLY_LOSS or self.world_size() > 1:
             self._early = False
+            self._dp_scalars = scalars           # data parallel: published at the end of the step (see LAG_LOSS_DP)
             return False
         self.engine.publish(scalars)
         self._early = True
