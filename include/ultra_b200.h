@@ -121,6 +121,16 @@ UB200_API int ub200_mlp_backward(const float* feats, const int32_t* docid, int L
                        const int* hidden, int n_hidden, const float* params, const float* dscores,
                        float* grads, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same two entry points for the other hidden-layer activations of the reference ranker (hparam activation_func,
+ * base_ranking_model.py:63-69): activation = 0 elu (identical to the calls above), 1 relu, 2 selu, 3 tanh, 4 sigmoid.
+ * ELU runs on the tensor cores; the others through the fp32 CUDA-core kernels. */
+UB200_API int ub200_mlp_forward_act(const float* feats, const int32_t* docid, int L, int B, int F, const int* hidden,
+                          int n_hidden, int activation, const float* params, float* scores, void* workspace,
+                          size_t workspace_bytes, int training, void* stream);
+UB200_API int ub200_mlp_backward_act(const float* feats, const int32_t* docid, int L, int B, int F, const int* hidden,
+                           int n_hidden, int activation, const float* params, const float* dscores, float* grads,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K2: listwise softmax cross-entropy, forward + gradient ----------------------------------------------
  * Replaces BaseAlgorithm.softmax_loss base_algorithm.py:309-330 (+ :18-30) and its autograd, and the pure-Python
  * IPW weight loop ipw_rank.py:116-128 -> propensity_estimator.py:22-42.

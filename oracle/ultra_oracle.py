@@ -59,7 +59,41 @@ def elu(z):
     return np.where(z > 0, z, np.expm1(np.minimum(z, 0)))
 
 
-def dnn_forward(x, params, n_layers, dt=np.float32):
+SELU_ALPHA = 1.6732632423543772848170429916717          # ultra/ranking_model/base_ranking_model.py:27-29
+SELU_SCALE = 1.0507009873554804934193349852946
+
+
+def activation(z, act):
+    """hidden-layer activation, hparam activation_func (base_ranking_model.py:63-69; DNN.py:38-39, 52-53)"""
+    if act == "elu":
+        return elu(z)
+    if act == "relu":
+        return np.maximum(z, 0)
+    if act == "selu":
+        return SELU_SCALE * np.where(z >= 0, z, SELU_ALPHA * elu(z))
+    if act == "tanh":
+        return np.tanh(z)
+    if act == "sigmoid":
+        return 1.0 / (1.0 + np.exp(-z))
+    raise ValueError(act)
+
+
+def activation_grad(z, y, act, dt):
+    """d activation / d z (autograd of the torch modules: nn.ELU / ReLU / Tanh / Sigmoid and the reference's selu)"""
+    if act == "elu":
+        return np.where(z > 0, dt(1.0), y + dt(1.0))
+    if act == "relu":
+        return (z > 0).astype(dt)
+    if act == "selu":
+        return np.where(z >= 0, dt(SELU_SCALE), y + dt(SELU_SCALE * SELU_ALPHA))
+    if act == "tanh":
+        return dt(1.0) - y * y
+    if act == "sigmoid":
+        return y * (dt(1.0) - y)
+    raise ValueError(act)
+
+
+def dnn_forward(x, params, n_layers, dt=np.float32, act="elu"):
     """x [M,K0].  params: dict name -> ndarray.  Returns (scores [M], cache)."""
     cache = []
     h = x.astype(dt)
@@ -75,13 +109,13 @@ def dnn_forward(x, params, n_layers, dt=np.float32):
         a = (xhat * g + b).astype(dt)
         z = (a @ W.T + c).astype(dt)
         last = j == n_layers - 1
-        y = z if last else elu(z).astype(dt)
+        y = z if last else activation(z, act).astype(dt)
         cache.append((xhat, rstd, a, z, y))
         h = y
     return h[:, 0], cache
 
 
-def dnn_backward(dscores, cache, params, n_layers, dt=np.float32):
+def dnn_backward(dscores, cache, params, n_layers, dt=np.float32, act="elu"):
     """dscores [M] -> dict name -> grad (autograd of DNN.py:77 restated)."""
     grads = {}
     dy = dscores.astype(dt)[:, None]
@@ -90,7 +124,7 @@ def dnn_backward(dscores, cache, params, n_layers, dt=np.float32):
         g = params["sequential.layer_norm%d.weight" % j].astype(dt)
         W = params["sequential.linear%d.weight" % j].astype(dt)
         last = j == n_layers - 1
-        dz = dy if last else (dy * np.where(z > 0, dt(1.0), y + dt(1.0))).astype(dt)
+        dz = dy if last else (dy * activation_grad(z, y, act, dt)).astype(dt)
         grads["sequential.linear%d.weight" % j] = (dz.T @ a).astype(dt)
         grads["sequential.linear%d.bias" % j] = dz.sum(axis=0).astype(dt)
         da = (dz @ W).astype(dt)
@@ -103,11 +137,11 @@ def dnn_backward(dscores, cache, params, n_layers, dt=np.float32):
     return grads
 
 
-def ranking_scores(features, docids_lb, params, n_layers, dt=np.float32):
+def ranking_scores(features, docids_lb, params, n_layers, dt=np.float32, act="elu"):
     """BaseAlgorithm.ranking_model (base_algorithm.py:118-132): returns scores [B,L] and the cache."""
     L, B = docids_lb.shape
     x = gather_rows(features, docids_lb, dt)
-    s, cache = dnn_forward(x, params, n_layers, dt)
+    s, cache = dnn_forward(x, params, n_layers, dt, act)
     return s.reshape(L, B).T.copy(), cache
 
 
@@ -418,7 +452,7 @@ class OracleTrainer:
 
     def __init__(self, algo, params, feature_size, hidden, L_train, ipw_table=None, prop_params=None,
                  learning_rate=None, max_gradient_norm=5.0, sigma=1.0, em_step=0.05, reg_p=1.0, dt=np.float32,
-                 l2_loss=0.0):
+                 l2_loss=0.0, activation_func="elu"):
         self.algo = algo
         self.dt = dt
         self.hidden = list(hidden)
@@ -434,6 +468,7 @@ class OracleTrainer:
         self.max_norm = max_gradient_norm
         self.sigma, self.em_step, self.reg_p = sigma, em_step, reg_p
         self.l2 = dt(l2_loss)              # hparam l2_loss (NA / IPW / DLA / PairDebias / RegressionEM)
+        self.act = activation_func         # ranking_model hparam activation_func
         self.ipw_table = ipw_table
         if algo == "dla":
             self.prop_w = np.array(prop_params["linear_layer.weight"], dtype=dt).reshape(-1)
@@ -448,7 +483,8 @@ class OracleTrainer:
 
     def scores(self, features, docids_bl):
         L = docids_bl.shape[1]
-        s, cache = ranking_scores(features, np.ascontiguousarray(docids_bl.T), self.params, self.n_layers, self.dt)
+        s, cache = ranking_scores(features, np.ascontiguousarray(docids_bl.T), self.params, self.n_layers, self.dt,
+                                  self.act)
         return s, cache
 
     def train(self, features, docids_bl, labels_bl):
@@ -484,7 +520,7 @@ class OracleTrainer:
             self.propensity = r["propensity"]
         else:
             raise ValueError(self.algo)
-        grads = dnn_backward(scores_grad_to_rows(ds), cache, self.params, self.n_layers, dt)
+        grads = dnn_backward(scores_grad_to_rows(ds), cache, self.params, self.n_layers, dt, self.act)
         if self.l2 > 0 and self.algo in ("na", "ipw", "dla", "pairdebias", "regem"):
             # loss += l2 * sum(p ** 2) / 2 for every ranker parameter (ipw_rank.py:153-157, navie_algorithm.py:110-114,
             # pairwise_debias.py:167-169, regression_EM.py:167-169, base_algorithm.py:332-333; dla.py:146-150 adds it to

@@ -66,6 +66,12 @@ CASES = [
     ("ipw_l2", "ipw", 10, 6, 8, 8, [16, 8], "click", 3, False, "l2_loss=0.01"),
     ("dla_l2", "dla", 10, 6, 8, 8, [16, 8], "click", 2, False, "l2_loss=0.01"),
     ("pairdebias_l2", "pairdebias", 10, 6, 6, 8, [16, 8], "click", 2, False, "l2_loss=0.01"),
+    # the other hidden-layer activations of the reference ranker (second trailing string: ranking_model hparams)
+    ("ipw_relu", "ipw", 10, 6, 8, 8, [16, 8], "click", 2, False, "", "activation_func=relu"),
+    # (activation_func=selu cannot be generated: the reference's selu is a plain function and nn.Sequential.add_module
+    # raises TypeError for it, DNN.py:52-54)
+    ("dla_tanh", "dla", 10, 6, 8, 8, [16, 8], "click", 2, False, "", "activation_func=tanh"),
+    ("lambdarank_sigmoid", "lambdarank", 10, 6, 6, 8, [16, 8], "graded", 2, False, "", "activation_func=sigmoid"),
 ]
 
 
@@ -107,7 +113,8 @@ def state_to_np(sd, prefix):
     return {prefix + k: v.detach().cpu().numpy().copy() for k, v in sd.items()}
 
 
-def run_case(ultra, name, algo, F, L_train, L_max, B, hidden, kind, n_steps, compact=False, hparams=""):
+def run_case(ultra, name, algo, F, L_train, L_max, B, hidden, kind, n_steps, compact=False, hparams="",
+             model_hparams=""):
     random.seed(0)
     np.random.seed(0)
     torch.manual_seed(0)
@@ -121,7 +128,8 @@ def run_case(ultra, name, algo, F, L_train, L_max, B, hidden, kind, n_steps, com
         "learning_algorithm": ALGOS[algo],
         "learning_algorithm_hparams": hparams,
         "ranking_model": "ultra.ranking_model.DNN" if hidden else "ultra.ranking_model.Linear",
-        "ranking_model_hparams": ("hidden_layer_sizes=%s" % str(hidden)) if hidden else "",
+        "ranking_model_hparams": ",".join(filter(None, [("hidden_layer_sizes=%s" % str(hidden)) if hidden else "",
+                                                        model_hparams])),
         "selection_bias_cutoff": L_train,
         "max_candidate_num": L_max,
         "metrics": ["ndcg", "err", "mrr"],
@@ -153,6 +161,7 @@ def run_case(ultra, name, algo, F, L_train, L_max, B, hidden, kind, n_steps, com
     out["meta_n_steps"] = np.int64(n_steps)
     out["meta_algo"] = np.asarray(algo)
     out["meta_hparams"] = np.asarray(hparams)
+    out["meta_model_hparams"] = np.asarray(model_hparams)
     out.update(state_to_np(model.model.state_dict(), "init/"))
     if algo == "dla":
         out.update(state_to_np(model.propensity_model.state_dict(), "init_prop/"))

@@ -64,4 +64,7 @@ def golden_hparams(g):
     for item in filter(None, text.split(",")):
         k, v = item.split("=")
         out[k] = float(v)
+    for item in filter(None, (str(g["meta_model_hparams"]) if "meta_model_hparams" in g else "").split(",")):
+        k, v = item.split("=")
+        out[k] = v                              # activation_func=...
     return out

@@ -51,8 +51,9 @@ def build_from_golden(g, tmp_path):
     exp_settings = {
         "learning_algorithm_hparams": hp,
         "ranking_model": "ultra_pytorch_b200.ranking_model.%s" % ("DNN" if len(g["meta_hidden"]) else "Linear"),
-        "ranking_model_hparams": ("hidden_layer_sizes=%s" % str([int(h) for h in g["meta_hidden"]]))
-        if len(g["meta_hidden"]) else "",
+        "ranking_model_hparams": ",".join(filter(None, [
+            ("hidden_layer_sizes=%s" % str([int(h) for h in g["meta_hidden"]])) if len(g["meta_hidden"]) else "",
+            str(g["meta_model_hparams"]) if "meta_model_hparams" in g else ""])),
         "selection_bias_cutoff": int(g["meta_L_train"]),
         "max_candidate_num": int(g["meta_L_max"]),
         "metrics": ["ndcg", "err", "mrr"],
@@ -252,6 +253,37 @@ def test_mlp_forward_backward_vs_oracle(F, hidden, L, B):
     eng.forward(feats_dev, docid_dev, L, B, training=True)
     grads3 = eng.backward(feats_dev, docid_dev, L, B, _dev(dsc)).cpu().numpy()
     assert np.array_equal(grads2, grads3)
+
+
+@pytest.mark.parametrize("act", ["relu", "selu", "tanh", "sigmoid"])
+@pytest.mark.parametrize("F,hidden,L,B", [(13, [7, 5], 3, 5), (136, [256, 128, 64], 8, 33)])
+def test_mlp_other_activations_vs_oracle(F, hidden, L, B, act):
+    """hidden-layer activations other than ELU (base_ranking_model.py:63-69) through ub200_mlp_forward_act /
+    ub200_mlp_backward_act (fp32 CUDA-core kernels, also for tensor-core-sized layers) against the float64 oracle"""
+    from ultra_pytorch_b200.engine import RankerEngine
+    rs = np.random.RandomState(F + L + B)
+    n_docs = L * B - 3
+    feats = rs.uniform(-1, 1, size=(n_docs, F)).astype(np.float32)
+    docids = rs.randint(0, n_docs + 1, size=(L, B))
+    params = _random_params(rs, F, hidden)
+    n_layers = len(hidden) + 1
+    dsc = rs.randn(B, L).astype(np.float32)
+    s64, cache = uo.ranking_scores(feats, docids, params, n_layers, np.float64, act)
+    g64 = uo.dnn_backward(uo.scores_grad_to_rows(dsc), cache, params, n_layers, np.float64, act)
+    code = {"relu": 1, "selu": 2, "tanh": 3, "sigmoid": 4}[act]
+    eng = RankerEngine(F, hidden, activation=code)
+    eng.params.copy_(_dev(np.concatenate([params[n].reshape(-1) for n in uo.param_names(n_layers)])))
+    feats_dev = _dev(np.concatenate([feats, np.zeros((1, F), np.float32)]))
+    docid_dev = _dev(docids.reshape(-1), torch.int32)
+    scores = eng.forward(feats_dev, docid_dev, L, B, training=True).clone()
+    assert_close(scores.cpu().numpy(), s64, 1e-5, "scores")
+    grads = eng.backward(feats_dev, docid_dev, L, B, _dev(dsc)).cpu().numpy()
+    floor = grad_floor(g64)
+    off = 0
+    for n in uo.param_names(n_layers):
+        ref = g64[n]
+        assert_close(grads[off:off + ref.size].reshape(ref.shape), ref, 1e-5, "grad " + n, floor)
+        off += ref.size
 
 
 @pytest.mark.parametrize("B,L", [(1, 1), (7, 5), (300, 40), (64, 200), (33, 45), (20, 100), (3, 300), (20000, 40)])

@@ -37,6 +37,8 @@ SIGNATURES = {
     "ub200_mlp_workspace_bytes": (_sz, [_i, _i, _i, _ip, _i, _i]),
     "ub200_mlp_forward": (_i, [_vp, _vp, _i, _i, _i, _ip, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "ub200_mlp_backward": (_i, [_vp, _vp, _i, _i, _i, _ip, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ub200_mlp_forward_act": (_i, [_vp, _vp, _i, _i, _i, _ip, _i, _i, _vp, _vp, _vp, _sz, _i, _vp]),
+    "ub200_mlp_backward_act": (_i, [_vp, _vp, _i, _i, _i, _ip, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ub200_loss_workspace_bytes": (_sz, [_i, _i]),
     "ub200_softmax_ce": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "ub200_dla_loss": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -98,6 +98,31 @@ __device__ __forceinline__ float elu_f(float z) { return z > 0.f ? z : expm1f(z)
 // derivative of ELU expressed through its OUTPUT y: z>0 -> 1, else exp(z) = y + 1
 __device__ __forceinline__ float elu_grad_from_out(float y) { return y > 0.f ? 1.f : y + 1.f; }
 
+// hidden-layer activations of the reference ranker (base_ranking_model.py:63-69: elu, relu, selu, tanh, sigmoid).  The
+// tensor-core kernels implement ELU (the reference default); the others run through the fp32 CUDA-core kernels.
+// Every derivative is a function of the OUTPUT, so the backward pass needs the stored activations only.
+enum { UB200_ACT_ELU = 0, UB200_ACT_RELU = 1, UB200_ACT_SELU = 2, UB200_ACT_TANH = 3, UB200_ACT_SIGMOID = 4 };
+constexpr float kSeluAlpha = 1.6732632423543772848170429916717f;     // base_ranking_model.py:13-17
+constexpr float kSeluScale = 1.0507009873554804934193349852946f;
+__device__ __forceinline__ float act_fwd(float z, int act) {
+    switch (act) {
+        case UB200_ACT_RELU: return fmaxf(z, 0.f);
+        case UB200_ACT_SELU: return kSeluScale * (z >= 0.f ? z : kSeluAlpha * expm1f(z));
+        case UB200_ACT_TANH: return tanhf(z);
+        case UB200_ACT_SIGMOID: return 1.f / (1.f + expf(-z));
+        default: return elu_f(z);
+    }
+}
+__device__ __forceinline__ float act_grad_from_out(float y, int act) {
+    switch (act) {
+        case UB200_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+        case UB200_ACT_SELU: return y >= 0.f ? kSeluScale : y + kSeluScale * kSeluAlpha;
+        case UB200_ACT_TANH: return 1.f - y * y;
+        case UB200_ACT_SIGMOID: return y * (1.f - y);
+        default: return elu_grad_from_out(y);
+    }
+}
+
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Deterministic "last block finishes the reduction" ticket. `counter` must be 0 on entry and is reset to 0.
@@ -121,11 +146,13 @@ struct LayerDims {
     int N[UB200_MAX_LAYERS];
     size_t off_g[UB200_MAX_LAYERS], off_b[UB200_MAX_LAYERS], off_w[UB200_MAX_LAYERS], off_c[UB200_MAX_LAYERS];
     size_t n_params;
+    int act;                        // UB200_ACT_* of the hidden layers (make_dims: ELU)
 };
 
 inline int make_dims(int F, const int* hidden, int n_hidden, LayerDims* d) {
     if (n_hidden < 0 || n_hidden + 1 > UB200_MAX_LAYERS || F <= 0) return 1;
     d->n_layers = n_hidden + 1;
+    d->act = UB200_ACT_ELU;
     size_t off = 0;
     int k = F;
     for (int j = 0; j <= n_hidden; ++j) {

@@ -27,7 +27,15 @@ namespace ub200 {
 enum { TC_FWD = 1, TC_DGRAD = 2, TC_WGRAD = 4, TC_FUSED_FWD = 8, TC_F16_FWD = 16, TC_F16_BWD = 32, TC_F16_WGRAD = 64,
        TC_F16_IMG = 128, TC_ALL = 255 };
 static int g_tc_mode = -1;
+// activations other than ELU run through the fp32 CUDA-core kernels: the entry points pin the mask to 0 for their call
+static thread_local int g_tc_override = -1;
+struct TcOverride {
+    int saved;
+    explicit TcOverride(int m) : saved(g_tc_override) { g_tc_override = m; }
+    ~TcOverride() { g_tc_override = saved; }
+};
 static int tc_mode() {
+    if (g_tc_override >= 0) return g_tc_override;
     if (g_tc_mode < 0) {
         const char* e = getenv("UB200_TC");
         g_tc_mode = e ? atoi(e) & TC_ALL : TC_ALL;
@@ -393,7 +401,8 @@ __global__ void __launch_bounds__(256) final_bwd_kernel(const float* __restrict_
                                                          const float2* __restrict__ stats, int M, int K,
                                                          const float* __restrict__ gamma, const float* __restrict__ w,
                                                          const float* __restrict__ dscores, int L, int B,
-                                                         float* __restrict__ dz_prev, float* __restrict__ colpart) {
+                                                         float* __restrict__ dz_prev, float* __restrict__ colpart,
+                                                         int act) {
     griddep_launch();
     griddep_wait();
     extern __shared__ float sm[];   // [8][K+1]
@@ -423,7 +432,7 @@ __global__ void __launch_bounds__(256) final_bwd_kernel(const float* __restrict_
                 float xh = (xv - st.x) * st.y;
                 float dxh = ds * w[k] * gamma[k];
                 float dx = st.y * (dxh - s1 - xh * s2);
-                dz_prev[(size_t)r * K + k] = dx * elu_grad_from_out(xv);
+                dz_prev[(size_t)r * K + k] = dx * act_grad_from_out(xv, act);
             }
         }
     }
@@ -438,7 +447,7 @@ __global__ void __launch_bounds__(256) final_bwd_kernel(const float* __restrict_
 // dZ_{j-1}[r,:] = LNbwd(dXhat[r,:]) (.) ELU'(X[r,:])   (X = Y_{j-1} is both the LN input and the ELU output)
 __global__ void __launch_bounds__(256) ln_bwd_elu_kernel(const float* __restrict__ dxh, const float* __restrict__ X,
                                                           const float2* __restrict__ stats, int M, int K,
-                                                          float* __restrict__ dz_prev) {
+                                                          float* __restrict__ dz_prev, int act) {
     griddep_launch();
     griddep_wait();
     int lane = threadIdx.x & 31;
@@ -460,7 +469,7 @@ __global__ void __launch_bounds__(256) ln_bwd_elu_kernel(const float* __restrict
         float xv = x[k];
         float xh = (xv - st.x) * st.y;
         float dx = st.y * (g[k] - s1 - xh * s2);
-        dz_prev[(size_t)r * K + k] = dx * elu_grad_from_out(xv);
+        dz_prev[(size_t)r * K + k] = dx * act_grad_from_out(xv, act);
     }
 }
 
@@ -609,7 +618,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs a) {
             float v = acc[p][q];
             if (MODE == MODE_FWD) {
                 v += a.bias[j];
-                if (a.act) v = elu_f(v);
+                if (a.act) v = act_fwd(v, a.act - 1);
             }
             out[(size_t)i * a.J + j] = v;
         }
@@ -833,11 +842,14 @@ extern "C" UB200_API size_t ub200_mlp_workspace_bytes(int L, int B, int F, const
     return w.total_bytes;
 }
 
-extern "C" UB200_API int ub200_mlp_forward(const float* feats, const int32_t* docid, int L, int B, int F, const int* hidden,
-                                 int n_hidden, const float* params, float* scores, void* workspace,
-                                 size_t workspace_bytes, int training, void* stream) {
+static int mlp_forward_impl(const float* feats, const int32_t* docid, int L, int B, int F, const int* hidden,
+                            int n_hidden, const float* params, float* scores, void* workspace, size_t workspace_bytes,
+                            int training, void* stream, int activation) {
     LayerDims d;
     UB_CHECK(make_dims(F, hidden, n_hidden, &d) == 0, 1, "mlp_forward: bad layer spec");
+    UB_CHECK(activation >= UB200_ACT_ELU && activation <= UB200_ACT_SIGMOID, 1, "mlp_forward: bad activation %d", activation);
+    d.act = activation;
+    TcOverride fp32_only(activation != UB200_ACT_ELU ? 0 : g_tc_override);
     UB_CHECK(L > 0 && B > 0, 1, "mlp_forward: bad L=%d B=%d", L, B);
     UB_CHECK(feats && params && scores && workspace, 2, "mlp_forward: null pointer");
     const int M = L * B;
@@ -889,7 +901,7 @@ extern "C" UB200_API int ub200_mlp_forward(const float* feats, const int32_t* do
                 GemmArgs a{};
                 a.I = M; a.J = N; a.C = K;
                 a.X = X; a.docid = idx; a.stats = w.stats[j]; a.gamma = g; a.beta = bt; a.W = W; a.bias = c;
-                a.out = w.Y[j]; a.K = K; a.N = N; a.act = 1;
+                a.out = w.Y[j]; a.K = K; a.N = N; a.act = 1 + d.act;   // 0 = none, 1 + UB200_ACT_* otherwise
                 launch_gemm<MODE_FWD>(a, 1, st);
                 UB_LAUNCH_CHECK("gemm_kernel<FWD>");
             }
@@ -923,11 +935,28 @@ extern "C" UB200_API int ub200_mlp_forward(const float* feats, const int32_t* do
     return 0;
 }
 
-extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* docid, int L, int B, int F, const int* hidden,
-                                  int n_hidden, const float* params, const float* dscores, float* grads,
-                                  void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" UB200_API int ub200_mlp_forward(const float* feats, const int32_t* docid, int L, int B, int F, const int* hidden,
+                                 int n_hidden, const float* params, float* scores, void* workspace,
+                                 size_t workspace_bytes, int training, void* stream) {
+    return mlp_forward_impl(feats, docid, L, B, F, hidden, n_hidden, params, scores, workspace, workspace_bytes, training,
+                            stream, UB200_ACT_ELU);
+}
+extern "C" UB200_API int ub200_mlp_forward_act(const float* feats, const int32_t* docid, int L, int B, int F,
+                                     const int* hidden, int n_hidden, int activation, const float* params, float* scores,
+                                     void* workspace, size_t workspace_bytes, int training, void* stream) {
+    return mlp_forward_impl(feats, docid, L, B, F, hidden, n_hidden, params, scores, workspace, workspace_bytes, training,
+                            stream, activation);
+}
+
+static int mlp_backward_impl(const float* feats, const int32_t* docid, int L, int B, int F, const int* hidden,
+                             int n_hidden, const float* params, const float* dscores, float* grads, void* workspace,
+                             size_t workspace_bytes, void* stream, int activation) {
     LayerDims d;
     UB_CHECK(make_dims(F, hidden, n_hidden, &d) == 0, 1, "mlp_backward: bad layer spec");
+    UB_CHECK(activation >= UB200_ACT_ELU && activation <= UB200_ACT_SIGMOID, 1, "mlp_backward: bad activation %d",
+             activation);
+    d.act = activation;
+    TcOverride fp32_only(activation != UB200_ACT_ELU ? 0 : g_tc_override);
     UB_CHECK(L > 0 && B > 0, 1, "mlp_backward: bad L=%d B=%d", L, B);
     UB_CHECK(feats && params && dscores && grads && workspace, 2, "mlp_backward: null pointer");
     const int M = L * B;
@@ -988,7 +1017,7 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
             PriorityScope p(chain16 && ss ? prio_lo : launch_priority());
             launch_k(final_bwd_kernel, blocks, 256, smem, sf, X, idx, w.stats[j], M, K, params + d.off_g[j],
                      params + d.off_w[j], dscores, L, B, (j == 0 || chain16) ? nullptr : w.dz[(j - 1) % 3],
-                     w.partials[j]);
+                     w.partials[j], d.act);
             UB_LAUNCH_CHECK("final_bwd_kernel");
         }
         cudaStream_t sb = chain16 ? sf : fork(j);
@@ -1128,11 +1157,25 @@ extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* d
             }
             if (!fuse) {
                 if (j + 2 <= nl - 2) wait_branch(j + 2);
-                launch_k(ln_bwd_elu_kernel, row_blocks, 256, 0, st, w.dxh, X, w.stats[j], M, K, w.dz[(j - 1) % 3]);
+                launch_k(ln_bwd_elu_kernel, row_blocks, 256, 0, st, w.dxh, X, w.stats[j], M, K, w.dz[(j - 1) % 3], d.act);
                 UB_LAUNCH_CHECK("ln_bwd_elu_kernel");
             }
         }
     }
     for (int j = 0; j < nl; ++j) wait_branch(j);    // join every branch
     return 0;
+}
+
+extern "C" UB200_API int ub200_mlp_backward(const float* feats, const int32_t* docid, int L, int B, int F, const int* hidden,
+                                  int n_hidden, const float* params, const float* dscores, float* grads,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+    return mlp_backward_impl(feats, docid, L, B, F, hidden, n_hidden, params, dscores, grads, workspace, workspace_bytes,
+                             stream, UB200_ACT_ELU);
+}
+extern "C" UB200_API int ub200_mlp_backward_act(const float* feats, const int32_t* docid, int L, int B, int F,
+                                      const int* hidden, int n_hidden, int activation, const float* params,
+                                      const float* dscores, float* grads, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+    return mlp_backward_impl(feats, docid, L, B, F, hidden, n_hidden, params, dscores, grads, workspace, workspace_bytes,
+                             stream, activation);
 }

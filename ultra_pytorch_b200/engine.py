@@ -132,7 +132,7 @@ class StagingSlot(object):
 
 
 class RankerEngine(object):
-    def __init__(self, feature_size, hidden, device=None, extra_floats=0):
+    def __init__(self, feature_size, hidden, device=None, extra_floats=0, activation=0):
         if not torch.cuda.is_available():
             raise _capi.UltraB200Error("ultra_pytorch_b200 needs a CUDA device (B200, sm_100a); no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -140,6 +140,7 @@ class RankerEngine(object):
         self.hidden = [int(h) for h in hidden]
         self._hidden_c = int_array(self.hidden)
         self.n_hidden = len(self.hidden)
+        self.activation = int(activation)        # UB200_ACT_*: 0 elu (tensor cores), 1 relu, 2 selu, 3 tanh, 4 sigmoid
         self.P = int(lib.ub200_mlp_param_count(self.F, self._hidden_c, self.n_hidden))
         if self.P == 0:
             raise _capi.UltraB200Error("bad ranker spec F=%d hidden=%s" % (self.F, self.hidden))
@@ -532,6 +533,11 @@ class RankerEngine(object):
         if scores is None:
             scores = self.scores_buf(B, L)
         ws = self._mlp_ws(L, B, training)
+        if self.activation:
+            check(lib.ub200_mlp_forward_act(_ptr(feats), _ptr(docid), L, B, self.F, self._hidden_c, self.n_hidden,
+                                            self.activation, _ptr(self.params), _ptr(scores), _ptr(ws), ws.numel(),
+                                            int(bool(training)), _stream()), "ub200_mlp_forward_act")
+            return scores
         check(lib.ub200_mlp_forward(_ptr(feats), _ptr(docid), L, B, self.F, self._hidden_c, self.n_hidden,
                                     _ptr(self.params), _ptr(scores), _ptr(ws), ws.numel(), int(bool(training)),
                                     _stream()), "ub200_mlp_forward")
@@ -539,6 +545,11 @@ class RankerEngine(object):
 
     def backward(self, feats, docid, L, B, dscores):
         ws = self._mlp_ws(L, B, True)
+        if self.activation:
+            check(lib.ub200_mlp_backward_act(_ptr(feats), _ptr(docid), L, B, self.F, self._hidden_c, self.n_hidden,
+                                             self.activation, _ptr(self.params), _ptr(dscores), _ptr(self.grads),
+                                             _ptr(ws), ws.numel(), _stream()), "ub200_mlp_backward_act")
+            return self.grads
         check(lib.ub200_mlp_backward(_ptr(feats), _ptr(docid), L, B, self.F, self._hidden_c, self.n_hidden,
                                      _ptr(self.params), _ptr(dscores), _ptr(self.grads), _ptr(ws), ws.numel(),
                                      _stream()), "ub200_mlp_backward")

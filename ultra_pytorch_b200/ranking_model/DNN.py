@@ -13,6 +13,13 @@ from ..engine import RankerEngine
 from ..hparams import HParams
 
 
+# hparam activation_func -> (UB200_ACT_* code of include/ultra_b200.h, module class; the modules only keep the reference's
+# Sequential layout - they hold no parameters and the plugin never calls them)
+# 'selu' is not offered: the reference's selu is a plain function that nn.Sequential.add_module rejects with a TypeError
+# (DNN.py:52-54), so no reference run with it exists (the kernels and the oracle implement it, code 2, for completeness).
+ACTIVATIONS = {'elu': (0, nn.ELU), 'relu': (1, nn.ReLU), 'tanh': (3, nn.Tanh), 'sigmoid': (4, nn.Sigmoid)}
+
+
 class DNN(nn.Module):
     def __init__(self, hparams_str, feature_size, extra_floats=0):
         super(DNN, self).__init__()
@@ -22,13 +29,16 @@ class DNN(nn.Module):
             norm="layer",                         # DNN.py:31
         )
         self.hparams.parse(hparams_str)
-        if self.hparams.activation_func != 'elu' or self.hparams.norm != 'layer':
+        # base_ranking_model.py:63-69: elu (default; tensor-core kernels), relu / selu / tanh / sigmoid (fp32 CUDA-core
+        # kernels).  norm: 'layer' only - 'batch' builds BatchNorm2d over 2-D activations in the reference, which raises
+        # in its forward pass, and any other string silently drops the normalisation layers.
+        if self.hparams.activation_func not in ACTIVATIONS or self.hparams.norm != 'layer':
             raise NotImplementedError(
-                "ultra_pytorch_b200.DNN implements the reference defaults activation_func='elu', norm='layer' "
-                "(got %r, %r); there is no fallback path" % (self.hparams.activation_func, self.hparams.norm))
-        self._setup(feature_size, self.hparams.hidden_layer_sizes, extra_floats)
+                "ultra_pytorch_b200.DNN implements activation_func in %s with norm='layer' (got %r, %r); there is no "
+                "fallback path" % (sorted(ACTIVATIONS), self.hparams.activation_func, self.hparams.norm))
+        self._setup(feature_size, self.hparams.hidden_layer_sizes, extra_floats, self.hparams.activation_func)
 
-    def _setup(self, feature_size, hidden, extra_floats):
+    def _setup(self, feature_size, hidden, extra_floats, activation='elu'):
         self.feature_size = int(feature_size)
         self.output_sizes = list(hidden) + [1]
         # Build the same module sequence as the reference ON THE CPU first: with the same torch seed the
@@ -39,9 +49,10 @@ class DNN(nn.Module):
             self.sequential.add_module('layer_norm{}'.format(j), nn.LayerNorm(k))
             self.sequential.add_module('linear{}'.format(j), nn.Linear(k, n))
             if j != len(self.output_sizes) - 1:
-                self.sequential.add_module('act{}'.format(j), nn.ELU())
+                self.sequential.add_module('act{}'.format(j), ACTIVATIONS[activation][1]())
             k = n
-        self.engine = RankerEngine(self.feature_size, list(hidden), extra_floats=extra_floats)
+        self.engine = RankerEngine(self.feature_size, list(hidden), extra_floats=extra_floats,
+                                   activation=ACTIVATIONS[activation][0])
         self._bind()
 
     def _bind(self):
