@@ -44,7 +44,19 @@ void count_launch();
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-bool pdl_enabled();     // UB200_PDL (default off: graph kernel-to-kernel gaps measured ~0.1 us, nothing to hide), optim.cu
+// Programmatic dependent launch (UB200_PDL=1 switches it on; optim.cu).  Every kernel of the library raises
+// griddepcontrol.launch_dependents first and touches global memory only behind griddepcontrol.wait, so the next kernel's
+// launch latency and on-chip set-up (barrier init, tensor-memory allocation) can overlap the tail of the previous one.
+// Measured twice on one B200 (all GPU tests pass with it): -3 % per step for the shortest steps (c1, c2 at L = 10 / 20),
+// +1 % at config 2, +4 % at config 5 - no clear win, hence off by default.  Launches of the three big K1 kernels never
+// carry the attribute when their grid exceeds one wave (PdlSuppress).
+bool pdl_enabled();
+int& pdl_suppress();    // thread-local nesting counter: > 0 = the launches of this scope carry no PDL attribute
+struct PdlSuppress {
+    bool on;
+    explicit PdlSuppress(bool cond) : on(cond) { if (on) ++pdl_suppress(); }
+    ~PdlSuppress() { if (on) --pdl_suppress(); }
+};
 // Launch priority of the kernels launched by this host thread from now on (0 = default).  The backward pass gives
 // the data-gradient chain (the critical path) the greatest priority and the weight-gradient side branches the
 // least, so that when both are pending the block scheduler places the critical kernel's CTAs first.
@@ -67,7 +79,7 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
     cfg.stream = st;
     cudaLaunchAttribute at[2];
     unsigned n_at = 0;
-    if (pdl_enabled()) {
+    if (pdl_enabled() && pdl_suppress() == 0) {
         at[n_at].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[n_at].val.programmaticStreamSerializationAllowed = 1;
         ++n_at;

@@ -1380,6 +1380,7 @@ int wgrad(const WgArgs& a, cudaStream_t st) {
     }
     bool img = false;
     for (int i = 0; i < a.n; ++i) img = img || (a.l[i].ximg && a.l[i].dzimg);
+    PdlSuppress multi_wave(a.total_ctas > kNumSMs);
     if (img) launch_k(wgrad16_kernel<true>, dim3(a.total_ctas), NTHREADS, SMEM_BYTES, st, a);
     else launch_k(wgrad16_kernel<false>, dim3(a.total_ctas), NTHREADS, SMEM_BYTES, st, a);
     UB_LAUNCH_CHECK("wgrad16_kernel");
@@ -1527,6 +1528,7 @@ int fwd(const FwdArgs& a, cudaStream_t st) {
         configured = true;
     }
     const int ytiles = a.N[0] / a.bn0;
+    PdlSuppress multi_wave(((a.M + 127) / 128) * ytiles > kNumSMs);
     launch_k(fwd16_kernel, dim3((a.M + 127) / 128, ytiles), NTHREADS, SMEM_BYTES, st, a);
     UB_LAUNCH_CHECK("fwd16_kernel");
     return 0;
@@ -1553,6 +1555,7 @@ int bwd(const BwdArgs& a, cudaStream_t st) {
     }
     bool img = false;
     for (int q = 0; q < a.nl; ++q) img = img || a.dzimg[q] != nullptr;
+    PdlSuppress multi_wave(bwd_grid(a.M) > kNumSMs);
     if (img) launch_k(bwd16_kernel<true>, dim3(bwd_grid(a.M)), NTHREADS, SMEM_BYTES, st, a);
     else launch_k(bwd16_kernel<false>, dim3(bwd_grid(a.M)), NTHREADS, SMEM_BYTES, st, a);
     UB_LAUNCH_CHECK("bwd16_kernel");

@@ -202,6 +202,10 @@ bool pdl_enabled() {
     static const int on = env_flag("UB200_PDL", 0);
     return on != 0;
 }
+int& pdl_suppress() {
+    static thread_local int n = 0;
+    return n;
+}
 int& launch_priority() {
     static thread_local int p = 0;
     return p;
