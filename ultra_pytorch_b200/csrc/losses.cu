@@ -31,10 +31,21 @@ static LossWs loss_ws(void* ws) {
 // deterministic reduction of partials[nblocks][width] into out[width], run by the last block
 __device__ __forceinline__ void reduce_partials(const float* __restrict__ partials, int nblocks, int stride,
                                                 int width, float* __restrict__ out) {
+    // 8 independent accumulators (block b goes to b & 7), combined pairwise at the end: a fixed order, and 8 loads in
+    // flight per thread instead of a chain of nblocks L2 round trips.  (Register use matters here: this function is
+    // inlined into kernels that sit exactly at an occupancy cliff - pairwise_kernel at 64 registers x 512 threads x 2
+    // CTAs - hence 8 accumulators and the explicit minimum-blocks launch bounds of the callers.)
     for (int k = threadIdx.x; k < width; k += blockDim.x) {
-        float s = 0.f;
-        for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * stride + k];
-        out[k] = s;
+        float acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+        int b = 0;
+        for (; b + 8 <= nblocks; b += 8) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] += partials[(size_t)(b + q) * stride + k];
+        }
+        for (; b < nblocks; ++b) acc[b & 7] += partials[(size_t)b * stride + k];
+        out[k] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
     }
 }
 
@@ -353,8 +364,16 @@ __global__ void __launch_bounds__(256) dla_reg_kernel(const float* __restrict__ 
         reduce_partials(partials, gridDim.x, width, 4, sums);
         float local = 0.f;
         for (int l = threadIdx.x; l < L; l += blockDim.x) {
-            float g = 0.f;
-            for (int q = 0; q < (int)gridDim.x; ++q) g += partials[(size_t)q * width + 4 + l];
+            float acc[8];                      // as reduce_partials: 8 loads in flight, fixed combination order
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+            int b = 0;
+            for (; b + 8 <= (int)gridDim.x; b += 8) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] += partials[(size_t)(b + q) * width + 4 + l];
+            }
+            for (; b < (int)gridDim.x; ++b) acc[b & 7] += partials[(size_t)b * width + 4 + l];
+            const float g = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
             const float pre = prop_w[l] + pb;
             const float gp = g * (pre > 0.f ? 1.f : expf(pre));
             dprop[l] = gp;
@@ -577,7 +596,7 @@ struct PairAcc {
 };
 
 template <int KIND>
-__global__ void __launch_bounds__(512) pairwise_kernel(const float* __restrict__ scores,
+__global__ void __launch_bounds__(512, 2) pairwise_kernel(const float* __restrict__ scores,
                                                         const float* __restrict__ labels, int B, int L, float sigma,
                                                         const float* __restrict__ t_plus,
                                                         const float* __restrict__ t_minus,
