@@ -661,7 +661,24 @@ __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __rest
 #pragma unroll
                 for (int q = 0; q < 16; ++q) acc[q] += pn[(size_t)(s + q) * plane + k];
             }
-            for (; s < S; ++s) acc[s & 15] += pn[(size_t)s * plane + k];
+            // ragged tail in batches of 8 / 4 / 2 / 1 with static accumulator indices (a fixed order): a scalar loop here
+            // is a chain of up to 15 dependent L2 round trips (S = 27 and 40 at config 2)
+            if (s + 8 <= S) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] += pn[(size_t)(s + q) * plane + k];
+                s += 8;
+            }
+            if (s + 4 <= S) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[8 + q] += pn[(size_t)(s + q) * plane + k];
+                s += 4;
+            }
+            if (s + 2 <= S) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) acc[12 + q] += pn[(size_t)(s + q) * plane + k];
+                s += 2;
+            }
+            if (s < S) acc[14] += pn[(size_t)s * plane + k];
 #pragma unroll
             for (int q = 0; q < 8; ++q) acc[q] += acc[q + 8];
             g = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
