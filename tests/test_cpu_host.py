@@ -215,3 +215,19 @@ def test_staged_views_layout_and_cache():
     assert c is not a and c.docid.data_ptr() == other.data_ptr()
     cache.get(buf, L, B, n_docs - 2, F)                 # 4th entry: the cache starts over
     assert len(cache.entries) == 1 and cache.get(buf, L, B, n_docs, F) is not a
+
+
+def test_column_ptrs2_addresses_both_halves_of_one_block():
+    """engine.column_ptrs2: docid and label pointer arrays into ONE stacked [2 L, B] copy of the feed's per-position arrays"""
+    import ctypes
+    from ultra_pytorch_b200 import engine as eng
+    L, B = 5, 7
+    d = [np.arange(B, dtype=np.float32) + 10 * l for l in range(L)]
+    y = [np.arange(B, dtype=np.float32) + 100 + 10 * l for l in range(L)]
+    dp, lp, keep = eng.column_ptrs2(d, y, B)
+    for l in range(L):
+        a = np.ctypeslib.as_array(ctypes.cast(dp[l], ctypes.POINTER(ctypes.c_float)), (B,))
+        b = np.ctypeslib.as_array(ctypes.cast(lp[l], ctypes.POINTER(ctypes.c_float)), (B,))
+        assert (a == d[l]).all() and (b == y[l]).all()
+    with pytest.raises(ValueError):
+        eng.column_ptrs2(d, y[:-1], B)
