@@ -269,11 +269,13 @@ Job make_job(const double* src, float* dst, long long n, int n_threads, int n_gr
     }
     long long unit = j.nblocks >> n_groups;
     if (unit < 1) unit = 1;
+    // the first group is at most one block per worker (one ~2.5 us round): its copy leaves as early as possible
+    long long first = (w > 0 && unit > w) ? w : unit;
     int k = 0;
     long long b = 0;
     j.group_first[0] = 0;
-    while (k < n_groups - 1 && b + (unit << k) < j.nblocks) {
-        b += unit << k;
+    while (k < n_groups - 1 && b + (k == 0 ? first : unit << k) < j.nblocks) {
+        b += k == 0 ? first : unit << k;
         j.group_first[++k] = b;
     }
     j.group_first[++k] = j.nblocks;
@@ -398,7 +400,7 @@ static int stage_feed_impl(const double* feats, int n_docs, int F, const float* 
         memset(f32, 0, sizeof(float) * (size_t)F);           // the PAD row
         copy(0, need);
     } else {
-        // The workers start converting at once.  The caller packs the ids / labels block in four slices, polling for
+        // The workers start converting at once.  The caller packs the ids / labels block in eight slices, polling for
         // finished groups in between (the first group of feature rows is usually on its way before the ids are
         // packed), copies it, and then converts / polls with the others.
         Job job = make_job(feats, f32, nf, n_threads, n_groups);
@@ -420,8 +422,8 @@ static int stage_feed_impl(const double* feats, int n_docs, int F, const float* 
         };
         auto pack_head = [&](Slot& s) {
             memset(f32 + nf, 0, sizeof(float) * (size_t)F);      // the PAD row (travels with the last group)
-            for (int part = 0; part < 4; ++part) {
-                bad += pack_ids_part(docid_cols, label_cols, L, B, pinned, n_docs, part, 4);
+            for (int part = 0; part < 8; ++part) {
+                bad += pack_ids_part(docid_cols, label_cols, L, B, pinned, n_docs, part, 8);
                 poll(s);
             }
             copy(0, (size_t)8 * L * B);
