@@ -122,6 +122,27 @@ def test_online_feed_check_validation_redraws_clickless_lists(tmp_path):
     assert (clicks.sum(axis=1) > 0).mean() > 0.999
 
 
+def test_online_feed_with_a_cascade_click_model(tmp_path):
+    """sequential click models (click_models.py:112-236) in the online feed: with the cascade model every validated
+    list carries exactly one click, always on a real position of the prefix"""
+    L_train, L_max, F, B = 4, 6, 3, 500
+    ds = FakeData(50, L_max, F)
+    random.seed(5)
+    p = os.path.join(str(tmp_path), "cascade.json")
+    with open(p, "w") as f:
+        json.dump({"model_name": "cascade_model", "eta": 1.0, "click_prob": [0.1, 0.16, 0.28, 0.52, 1.0],
+                   "exam_prob": [1.0] * 10}, f)
+    feed = _feed_cls_with_host_sampler()(_model(L_train, L_max, F), B, "click_model_json=%s" % p)
+    feed.score_of = lambda f_, docid: np.zeros(docid.shape)
+    f, _ = feed.get_batch(ds, check_validation=True)
+    clicks = np.stack([f["label%d" % l] for l in range(L_max)], axis=1)
+    docid = np.stack([f["docid_input%d" % l] for l in range(L_max)], axis=1)
+    n_docs = len(f["letor_features"])
+    assert np.all(clicks[:, L_train:] == 0)
+    assert np.all(clicks[docid >= n_docs] == 0)
+    assert (clicks.sum(axis=1) == 1).mean() > 0.999
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # GPU: the sampling kernel and the feed on a real B200 algorithm
 # ------------------------------------------------------------------------------------------------------------------

@@ -19,7 +19,7 @@ import random
 import numpy as np
 
 from ..hparams import HParams
-from .click_simulation_feed import ClickSimulationFeed, _PositionBiasedModel
+from .click_simulation_feed import ClickSimulationFeed, load_click_model
 
 
 class StochasticOnlineSimulationFeed(ClickSimulationFeed):
@@ -36,11 +36,7 @@ class StochasticOnlineSimulationFeed(ClickSimulationFeed):
         print(hparam_str)
         self.hparams.parse(hparam_str)
         with open(self.hparams.click_model_json) as fin:
-            desc = json.load(fin)
-        if desc.get('model_name', 'position_biased_model') != 'position_biased_model':
-            raise NotImplementedError("the online-simulation drop-in implements the position_biased_model click model "
-                                      "only (got %r)" % desc.get('model_name'))
-        self.click_model = _PositionBiasedModel(desc)
+            self.click_model = load_click_model(json.load(fin))
         self.start_index = 0
         self.count = 1
         self.rank_list_size = model.rank_list_size
@@ -100,14 +96,20 @@ class StochasticOnlineSimulationFeed(ClickSimulationFeed):
         on a PAD slot (label 0 still has the noise-click probability) must neither survive nor stop the re-draw."""
         if self.hparams.oracle_mode:
             return labels * valid
-        p = self.click_model.click_probability(labels) * valid
-        clicks = (self.rng.random(labels.shape) < p).astype(np.float64)
+        if self.click_model.position_independent:
+            p = self.click_model.click_probability(labels) * valid
+            draw = lambda rows: (self.rng.random((len(rows), labels.shape[1])) < p[rows]).astype(np.float64)
+        else:
+            # user-browsing / cascade model: sampled position by position; the real documents are a prefix of every
+            # list, so a (discarded) click on a PAD slot cannot influence a real position behind it
+            draw = lambda rows: self.click_model.sample(labels[rows], self.rng) * valid[rows]
+        clicks = draw(np.arange(labels.shape[0]))
         if check_validation:
             for _ in range(self.MAX_SAMPLE_ROUND_NUM):
                 redo = np.flatnonzero(clicks.sum(axis=1) == 0)
                 if redo.size == 0:
                     break
-                clicks[redo] = (self.rng.random((redo.size, labels.shape[1])) < p[redo]).astype(np.float64)
+                clicks[redo] = draw(redo)
         return clicks
 
     def simulate_clicks_online(self, input_feed, check_validation=False):
