@@ -257,6 +257,13 @@ UB200_API int ub200_click_batch(const int32_t* init_list, const float* rel, int 
                       int n_exam, const float* click_prob, int n_cp, int oracle_mode, int check_validation,
                       int max_rounds, int B, int pad_id, unsigned long long seed, unsigned long long offset,
                       int32_t* docid, float* labels, int32_t* query_idx, void* stream);
+/* The same for the other click models of click_models.py:112-236: click_model = 0 position biased (as above), 1 cascade
+ * (the first click ends the session), 2 user browsing (exam_prob is the [n_exam x n_exam] table exam_prob[rank][rank -
+ * last_click_rank - 1] of getExamProb); lists of up to 256 positions for 1 and 2. */
+UB200_API int ub200_click_batch_model(const int32_t* init_list, const float* rel, int nq, int L, const float* exam_prob,
+                      int n_exam, const float* click_prob, int n_cp, int click_model, int oracle_mode,
+                      int check_validation, int max_rounds, int B, int pad_id, unsigned long long seed,
+                      unsigned long long offset, int32_t* docid, float* labels, int32_t* query_idx, void* stream);
 
 /* ---- C1: data-parallel exchange of the flat gradient buffer over NVLink peer memory ----------------------------------
  * Nothing in the reference corresponds to this (it is single-process); it is the ONE collective of a data-parallel

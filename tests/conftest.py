@@ -24,3 +24,20 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _metric_max_label():
+    """The reference's data loader sets RankingMetricKey.MAX_LABEL (the ERR normaliser) when a data set is read; tests
+    build their data in memory, so the plugin's copy of that setting gets the value of the 5-level test labels here
+    (every test file on its own, in any order)."""
+    try:
+        from ultra_pytorch_b200 import metrics as b200_metrics
+    except Exception:
+        yield
+        return
+    saved = b200_metrics.MAX_LABEL
+    if saved is None:
+        b200_metrics.MAX_LABEL = 4.0
+    yield
+    b200_metrics.MAX_LABEL = saved

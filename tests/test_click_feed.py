@@ -275,5 +275,3 @@ def test_feed_with_a_cascade_click_model(tmp_path):
     f, _ = feed.get_batch(ds, check_validation=True)
     clicks = np.stack([f["label%d" % l] for l in range(L)], axis=1)
     assert (clicks.sum(axis=1) == 1).all()          # cascade: exactly one click per (validated) list
-    with pytest.raises(NotImplementedError):
-        ClickSimulationFeed(_model(L, F), B, "click_model_json=%s,device_batches=True" % p).get_batch(ds, True)

@@ -95,6 +95,63 @@ def test_device_click_batches_have_the_reference_distribution(check_validation, 
             assert np.all(np.abs(got - p[qi]) <= 5 * np.sqrt(p[qi] * (1 - p[qi]) / sel.sum()) + 1e-6), qi
 
 
+@pytest.mark.parametrize("name", ["cascade_model", "user_browsing_model"])
+def test_device_sequential_click_models_match_the_host_samplers(name, tmp_path):
+    """click_batch_kernel with click_model = 1 / 2 (lane 0 walks the list): per (query, position) click rates and the rate
+    of a click given the previous click position against the array-form host samplers of the same models (which
+    tests/test_click_feed.py checks against the reference's own samplers), 5 sigma"""
+    import ultra_pytorch_b200.learning_algorithm as la
+    from ultra_pytorch_b200.input_layer import ClickSimulationFeed
+    from ultra_pytorch_b200.input_layer.click_simulation_feed import load_click_model
+    la.B200Algorithm.VERBOSE = False
+    nq, L, F, B = 6, 12, 8, 262144
+    ds = FakeData(nq, L, F, ragged=False)
+    if name == "cascade_model":
+        desc = {"model_name": name, "eta": 1.0, "click_prob": [0.1, 0.16, 0.28, 0.52, 1.0], "exam_prob": [1.0] * 10}
+    else:
+        desc = {"model_name": name, "eta": 1.0, "click_prob": [0.1, 0.16, 0.28, 0.52, 1.0],
+                "exam_prob": [[pow(x, 1.0) for x in row] for row in
+                              __import__("ultra_pytorch_b200.input_layer.click_simulation_feed", fromlist=["x"])
+                              ._UserBrowsingModel.ORIGINAL_RD_EXAM_TABLE]}
+    p = os.path.join(str(tmp_path), "cm.json")
+    with open(p, "w") as f:
+        json.dump(desc, f)
+    settings = {"learning_algorithm_hparams": "", "ranking_model": "ultra_pytorch_b200.ranking_model.DNN",
+                "ranking_model_hparams": "hidden_layer_sizes=[32, 16]", "selection_bias_cutoff": L,
+                "max_candidate_num": L, "metrics": ["ndcg"], "metrics_topn": [1, 3]}
+    torch.manual_seed(0)
+    random.seed(0)
+    model = la.NavieAlgorithm(types.SimpleNamespace(feature_size=F), settings)
+    feed = ClickSimulationFeed(model, B, "click_model_json=%s,device_batches=True" % p)
+    f, info = feed.get_batch(ds, check_validation=False)
+    q = np.asarray(info["rank_list_idxs"])
+    clicks = np.stack([f["label%d" % l] for l in range(L)], axis=1).astype(np.float64)
+    _, rel, _ = feed._arrays(ds)
+    host = load_click_model(desc).sample(rel[q], np.random.default_rng(5))
+
+    def prev_click(c):
+        idx = np.where(c > 0, np.arange(L)[None, :], -1)
+        run = np.maximum.accumulate(idx, axis=1)
+        return np.concatenate([np.full((c.shape[0], 1), -1), run[:, :-1]], axis=1)
+    pd_, ph = prev_click(clicks), prev_click(host)
+    for qi in range(nq):
+        sel = q == qi
+        a, b = clicks[sel].mean(0), host[sel].mean(0)
+        se = np.sqrt((a * (1 - a) + b * (1 - b)) / sel.sum()) + 1e-9
+        assert (np.abs(a - b) <= 5 * se + 1e-3).all(), (name, qi, a, b)
+    for r in range(1, L):
+        for last in (-1, r - 1, r - 3):
+            so, sh = pd_[:, r] == last, ph[:, r] == last
+            if so.sum() < 2000 or sh.sum() < 2000:
+                continue
+            # pooled over the queries: same query mix on both sides (q is shared)
+            a, b = clicks[so, r].mean(), host[sh, r].mean()
+            se = np.sqrt(a * (1 - a) / so.sum() + b * (1 - b) / sh.sum()) + 1e-9
+            assert abs(a - b) <= 5 * se + 3e-3, (name, r, last, a, b)
+    if name == "cascade_model":
+        assert (clicks.sum(axis=1) <= 1).all()
+
+
 def test_training_from_device_batches_equals_training_from_their_host_copy(tmp_path):
     import ultra_pytorch_b200.learning_algorithm as la
     nq, L, F, B = 120, 10, 136, 64

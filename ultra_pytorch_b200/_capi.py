@@ -54,6 +54,8 @@ SIGNATURES = {
     "ub200_pl_sample": (_i, [_vp, _vp, _i, _i, _i, _f, ctypes.c_ulonglong, ctypes.c_ulonglong, _vp, _vp]),
     "ub200_click_batch": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, ctypes.c_ulonglong,
                                ctypes.c_ulonglong, _vp, _vp, _vp, _vp]),
+    "ub200_click_batch_model": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, ctypes.c_ulonglong,
+                                     ctypes.c_ulonglong, _vp, _vp, _vp, _vp]),
     "ub200_peer_ctl_bytes": (_sz, []),
     "ub200_peer_flag_bytes": (_sz, [_i]),
     "ub200_peer_allreduce": (_i, [_vp, _vp, _i, _i, _vp, _sz, _vp, _vp]),

@@ -104,12 +104,81 @@ __global__ void __launch_bounds__(256) click_batch_kernel(const int32_t* __restr
                                                            int oracle_mode, int check_validation, int max_rounds, int B,
                                                            int pad_id, unsigned long long seed,
                                                            unsigned long long offset, int32_t* __restrict__ docid,
-                                                           float* __restrict__ labels, int32_t* __restrict__ query_idx) {
+                                                           float* __restrict__ labels, int32_t* __restrict__ query_idx,
+                                                           int click_model) {
     griddep_launch();
     griddep_wait();
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= B) return;
+    if (click_model != 0 && !oracle_mode) {
+        // cascade (1) / user-browsing (2) model: a click depends on the clicks before it (click_models.py:112-236), so
+        // lane 0 walks the list and keeps the clicks as a bit mask (L <= 256); the draws are still counter based
+        // (position, slot, round), the accepted list is written by all lanes
+        const uint2 key2 = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+        const uint32_t o_lo = (uint32_t)offset, o_hi = (uint32_t)(offset >> 32);
+        int q2 = 0;
+        uint32_t bits[8];
+        for (int round = 0; round < max_rounds; ++round) {
+            const uint4 rq = philox4x32_10(make_uint4(0xFFFFFFFFu, (uint32_t)b, o_lo, (o_hi << 12) ^ (uint32_t)round), key2);
+            q2 = (int)(((unsigned long long)rq.x * (unsigned long long)nq) >> 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bits[i] = 0u;
+            if (lane == 0) {
+                int last = -1;
+                bool clicked = false;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    uint32_t word = 0u;
+                    for (int jj = 0; jj < 32; ++jj) {
+                        const int l = 32 * i + jj;
+                        if (l >= L) break;
+                        const float y = rel[(size_t)q2 * L + l];
+                        int yi = y > 0.f ? (int)y : 0;
+                        if (yi >= n_cp) yi = n_cp - 1;
+                        float exam;
+                        if (click_model == 1) {
+                            exam = exam_prob[l < n_exam ? l : n_exam - 1];
+                        } else {
+                            // getExamProb(rank, last_click_rank), click_models.py:174-185; exam_prob = [n_exam x n_exam] table
+                            const int distance = l - last;
+                            if (l < n_exam) exam = exam_prob[l * n_exam + distance - 1];
+                            else if (distance > l) exam = exam_prob[(n_exam - 1) * n_exam + n_exam - 1];
+                            else exam = exam_prob[(n_exam - 1) * n_exam + (distance < n_exam - 1 ? distance - 1 : n_exam - 2)];
+                        }
+                        const uint4 r = philox4x32_10(make_uint4((uint32_t)l, (uint32_t)b, o_lo, (o_hi << 12) ^ (uint32_t)round), key2);
+                        const bool c = u01_open(r.x) < exam * click_prob[yi];
+                        if (c && !(click_model == 1 && clicked)) word |= 1u << jj;    // cascade: only the first click counts
+                        if (c) {
+                            last = l;
+                            clicked = true;
+                        }
+                    }
+                    bits[i] = word;
+                }
+            }
+            uint32_t any = 0u;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                bits[i] = __shfl_sync(0xffffffffu, bits[i], 0);
+                any |= bits[i];
+            }
+            if (!check_validation || any || round == max_rounds - 1) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int l = 32 * i + lane;
+                    if (l < L) {
+                        const int id = init_list[(size_t)q2 * L + l];
+                        docid[(size_t)l * B + b] = id >= 0 ? id : pad_id;
+                        labels[(size_t)b * L + l] = (float)((bits[i] >> lane) & 1u);
+                    }
+                }
+                break;
+            }
+        }
+        if (lane == 0 && query_idx) query_idx[b] = q2;
+        return;
+    }
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     const uint32_t off_lo = (uint32_t)offset, off_hi = (uint32_t)(offset >> 32);
     int q = 0;
@@ -244,20 +313,43 @@ __global__ void regem_update_kernel(float* __restrict__ prop, const float* __res
     if (l < L) prop[l] = (1.0f - em_step) * prop[l] + em_step * (out[2 + l] / (out[1] / (float)L));
 }
 
-extern "C" UB200_API int ub200_click_batch(const int32_t* init_list, const float* rel, int nq, int L,
-                                           const float* exam_prob, int n_exam, const float* click_prob, int n_cp,
-                                           int oracle_mode, int check_validation, int max_rounds, int B, int pad_id,
-                                           unsigned long long seed, unsigned long long offset, int32_t* docid,
-                                           float* labels, int32_t* query_idx, void* stream) {
+static int click_batch_impl(const int32_t* init_list, const float* rel, int nq, int L, const float* exam_prob, int n_exam,
+                            const float* click_prob, int n_cp, int oracle_mode, int check_validation, int max_rounds,
+                            int B, int pad_id, unsigned long long seed, unsigned long long offset, int32_t* docid,
+                            float* labels, int32_t* query_idx, void* stream, int click_model) {
     UB_CHECK(init_list && rel && docid && labels && nq > 0 && L > 0 && B > 0, 2, "click_batch: bad arguments");
+    UB_CHECK(click_model >= 0 && click_model <= 2, 1, "click_batch: click_model must be 0 (position biased), 1 (cascade) "
+             "or 2 (user browsing), got %d", click_model);
+    UB_CHECK(click_model == 0 || oracle_mode || L <= 256, 4, "click_batch: the sequential click models handle lists of up "
+             "to 256 positions (got %d)", L);
     UB_CHECK(oracle_mode || (exam_prob && click_prob && n_exam > 0 && n_cp > 0), 2, "click_batch: click model missing");
     UB_CHECK(max_rounds >= 1 && max_rounds < (1 << 12), 1, "click_batch: max_rounds must be in [1, 4096)");
     const int grid = (B + 7) / 8;
     launch_k(click_batch_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), init_list, rel, nq, L, exam_prob,
              n_exam, click_prob, n_cp, oracle_mode, check_validation, max_rounds, B, pad_id, seed, offset, docid, labels,
-             query_idx);
+             query_idx, click_model);
     UB_LAUNCH_CHECK("click_batch_kernel");
     return 0;
+}
+
+extern "C" UB200_API int ub200_click_batch(const int32_t* init_list, const float* rel, int nq, int L,
+                                           const float* exam_prob, int n_exam, const float* click_prob, int n_cp,
+                                           int oracle_mode, int check_validation, int max_rounds, int B, int pad_id,
+                                           unsigned long long seed, unsigned long long offset, int32_t* docid,
+                                           float* labels, int32_t* query_idx, void* stream) {
+    return click_batch_impl(init_list, rel, nq, L, exam_prob, n_exam, click_prob, n_cp, oracle_mode, check_validation,
+                            max_rounds, B, pad_id, seed, offset, docid, labels, query_idx, stream, 0);
+}
+
+// the same with the click model as a parameter: 0 position biased, 1 cascade (exam_prob [n_exam]), 2 user browsing
+// (exam_prob = the [n_exam x n_exam] examination table, row = rank, column = distance to the last click - 1)
+extern "C" UB200_API int ub200_click_batch_model(const int32_t* init_list, const float* rel, int nq, int L,
+                                                 const float* exam_prob, int n_exam, const float* click_prob, int n_cp,
+                                                 int click_model, int oracle_mode, int check_validation, int max_rounds,
+                                                 int B, int pad_id, unsigned long long seed, unsigned long long offset,
+                                                 int32_t* docid, float* labels, int32_t* query_idx, void* stream) {
+    return click_batch_impl(init_list, rel, nq, L, exam_prob, n_exam, click_prob, n_cp, oracle_mode, check_validation,
+                            max_rounds, B, pad_id, seed, offset, docid, labels, query_idx, stream, click_model);
 }
 
 extern "C" UB200_API int ub200_pl_sample(const float* scores, const int32_t* docid, int n_docs, int B, int L, float tau,

@@ -493,14 +493,16 @@ class RankerEngine(object):
         return st
 
     def click_batch(self, init_list, rel, exam_prob, click_prob, oracle_mode, check_validation, max_rounds, pad_id, seed,
-                    offset, docid, labels, query_idx):
+                    offset, docid, labels, query_idx, click_model=0):
+        """click_model: 0 position biased (exam_prob [n]), 1 cascade (exam_prob [n]), 2 user browsing (exam_prob [n, n])"""
         nq, L = init_list.shape
         B = docid.shape[1]
-        check(lib.ub200_click_batch(_ptr(init_list), _ptr(rel), nq, L, _ptr(exam_prob),
-                                    0 if exam_prob is None else exam_prob.numel(), _ptr(click_prob),
-                                    0 if click_prob is None else click_prob.numel(), int(oracle_mode),
-                                    int(check_validation), int(max_rounds), B, int(pad_id), int(seed), int(offset),
-                                    _ptr(docid), _ptr(labels), _ptr(query_idx), _stream()), "ub200_click_batch")
+        n_exam = 0 if exam_prob is None else (exam_prob.shape[0] if click_model == 2 else exam_prob.numel())
+        check(lib.ub200_click_batch_model(_ptr(init_list), _ptr(rel), nq, L, _ptr(exam_prob), n_exam, _ptr(click_prob),
+                                          0 if click_prob is None else click_prob.numel(), int(click_model),
+                                          int(oracle_mode), int(check_validation), int(max_rounds), B, int(pad_id),
+                                          int(seed), int(offset), _ptr(docid), _ptr(labels), _ptr(query_idx), _stream()),
+              "ub200_click_batch_model")
 
     # bytes of resident feature matrices kept in HBM at once (train / valid / test sets of one run stay resident side by
     # side; the least recently used one goes when the cap would be exceeded)

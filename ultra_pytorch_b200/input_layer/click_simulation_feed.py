@@ -51,6 +51,10 @@ class _SequentialClickModel(object):
 
 class _UserBrowsingModel(_SequentialClickModel):
     """Array form of UserBrowsingModel (click_models.py:112-185): P(exam) = table[rank][rank - last_click_rank - 1]."""
+    DEVICE_CODE = 2                              # ub200_click_batch_model
+
+    def device_exam_table(self):
+        return np.ascontiguousarray(self._table)
     ORIGINAL_RD_EXAM_TABLE = [
         [1.0],
         [0.98, 1.0],
@@ -105,6 +109,10 @@ class _UserBrowsingModel(_SequentialClickModel):
 class _CascadeModel(_SequentialClickModel):
     """Array form of CascadeModel (click_models.py:188-236): the user clicks at most once - every position is sampled
     with P = exam_prob[rank] * click_prob[label], positions after the first click report no click."""
+    DEVICE_CODE = 1
+
+    def device_exam_table(self):
+        return np.asarray(self.exam_prob, dtype=np.float64)
 
     def __init__(self, desc):
         self.eta = desc['eta']
@@ -126,6 +134,10 @@ class _CascadeModel(_SequentialClickModel):
 class _PositionBiasedModel(object):
     """Array form of PositionBiasedModel (click_models.py:68-110)."""
     position_independent = True
+    DEVICE_CODE = 0
+
+    def device_exam_table(self):
+        return self.exam_prob
 
     def __init__(self, desc):
         self.eta = desc['eta']
@@ -282,9 +294,9 @@ class ClickSimulationFeed(object):
     # ---- N1 on the device: query sampling + click simulation + batch assembly in one kernel ------------------------
     def _device_batch(self, data_set, check_validation):
         import torch
-        if not self.hparams.oracle_mode and not self.click_model.position_independent:
-            raise NotImplementedError("device_batches=True simulates clicks with the position-biased model only; %s is "
-                                      "sampled on the host (drop device_batches, resident_features=True still applies)"
+        if not self.hparams.oracle_mode and not self.click_model.position_independent and self.rank_list_size > 256:
+            raise NotImplementedError("device_batches=True samples %s for lists of up to 256 positions (drop "
+                                      "device_batches: the host path has no limit, resident_features=True still applies)"
                                       % type(self.click_model).__name__)
         eng = getattr(self.model, "engine", None)
         if eng is None:
@@ -312,16 +324,17 @@ class ClickSimulationFeed(object):
             self._dev_calls = 0
         oracle = bool(self.hparams.oracle_mode)
         if not oracle:
-            cm_key = (float(self.click_model.eta), self.click_model.exam_prob.tobytes())
+            exam = self.click_model.device_exam_table()
+            cm_key = (float(self.click_model.eta), exam.tobytes())
             if self._dev_cm_key != cm_key:
-                self._dev_exam = torch.from_numpy(self.click_model.exam_prob.astype(np.float32)).to(dev)
+                self._dev_exam = torch.from_numpy(exam.astype(np.float32)).to(dev)
                 self._dev_cp = torch.from_numpy(self.click_model.click_prob.astype(np.float32)).to(dev)
                 self._dev_cm_key = cm_key
         self._dev_calls += 1
         docid, lab, qidx = self._dev_ring[self._dev_calls % len(self._dev_ring)]
         eng.click_batch(self._dev_init, self._dev_rel, None if oracle else self._dev_exam,
                         None if oracle else self._dev_cp, oracle, bool(check_validation), 1000, features.shape[0],
-                        self._dev_seed, self._dev_calls, docid, lab, qidx)
+                        self._dev_seed, self._dev_calls, docid, lab, qidx, click_model=self.click_model.DEVICE_CODE)
         return DeviceFeed(self.model, self._resident_view, docid, lab, qidx, features.shape[0])
 
     def get_batch(self, data_set, check_validation=False, data_format="ULTRA"):
