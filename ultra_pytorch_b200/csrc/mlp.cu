@@ -714,15 +714,28 @@ __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __rest
     }
     __syncthreads();
     if (is_last) {
+        // the per-block partials of this k-tile: thread row ny takes blocks ny, ny + 8, ... and the rows are combined in
+        // order through shared memory - a fixed order, and an 8x shorter chain of L2 round trips than one row walking
+        // all gridDim.y blocks
         __threadfence();
-        if (ny == 0 && k < K) {
-            float tg = 0.f, tb = 0.f;
-            for (unsigned int q = 0; q < gridDim.y; ++q) {
+        float tg = 0.f, tb = 0.f;
+        if (k < K)
+            for (unsigned int q = ny; q < gridDim.y; q += 8) {
                 tg += scratch[((size_t)q * 2 + 0) * K + k];
                 tb += scratch[((size_t)q * 2 + 1) * K + k];
             }
-            dgamma[k] = tg;
-            dbeta[k] = tb;
+        sg[ny][kx] = tg;
+        sb[ny][kx] = tb;
+        __syncthreads();
+        if (ny == 0 && k < K) {
+            float ag2 = 0.f, ab2 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                ag2 += sg[q][kx];
+                ab2 += sb[q][kx];
+            }
+            dgamma[k] = ag2;
+            dbeta[k] = ab2;
         }
     }
 }
